@@ -1,0 +1,181 @@
+"""Deterministic synthetic crops / targets / weights for parity tests and bench.
+
+Follows the input contract of the reference hot path:
+reference `core/gdrn_modeling/engine_utils.py:6-60` (batch_data) and
+`core/gdrn_modeling/data_loader.py:617-632` (SITE translation targets).
+
+All randomness comes from CPU `torch.Generator`s so that the same tensors are
+produced in the build container, on the GPU box, by the oracle and by the
+product path.
+"""
+from __future__ import annotations
+
+import math
+import zlib
+
+import torch
+
+LM_K = [[572.4114, 0.0, 325.2611], [0.0, 573.57043, 242.04899], [0.0, 0.0, 1.0]]  # reference ref/lm_full.py:106
+
+
+def _gen(seed: int, tag: str) -> torch.Generator:
+    g = torch.Generator(device="cpu")
+    g.manual_seed((seed * 1000003 + zlib.crc32(tag.encode())) % (2**63 - 1))
+    return g
+
+
+def random_rotations(n: int, g: torch.Generator) -> torch.Tensor:
+    a = torch.randn(n, 3, 3, generator=g, dtype=torch.float64)
+    q, r = torch.linalg.qr(a)
+    d = torch.diagonal(r, dim1=-2, dim2=-1).sign()
+    q = q * d[:, None, :]
+    det = torch.linalg.det(q)
+    q[:, :, 0] *= det[:, None]
+    return q.float()
+
+
+def discrete_symmetries(kind: str) -> torch.Tensor | None:
+    """Model-to-model symmetry rotation sets like `sym_info` (reference misc.py:233)."""
+    if kind == "none":
+        return None
+
+    def rz(a):
+        c, s = math.cos(a), math.sin(a)
+        return [[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]]
+
+    if kind == "z2":
+        return torch.tensor([rz(0.0), rz(math.pi)], dtype=torch.float32)
+    if kind == "z4":
+        return torch.tensor([rz(i * math.pi / 2) for i in range(4)], dtype=torch.float32)
+    if kind == "cont":  # continuous axis discretised (reference uses up to 314·n steps; 64 keeps tests quick)
+        return torch.tensor([rz(i * 2 * math.pi / 64) for i in range(64)], dtype=torch.float32)
+    raise ValueError(kind)
+
+
+def make_batch(bs: int, seed: int = 0, n_points: int = 3000, with_sym: bool = False, dtype=torch.float32) -> dict:
+    """Synthetic batch with the reference field names (CPU tensors)."""
+    g = _gen(seed, "batch")
+    H = W = 64
+    roi_img = torch.rand(bs, 3, 256, 256, generator=g, dtype=dtype)
+
+    # 2D coords of the crop window in [0,1] (any affine sub-window of the unit meshgrid)
+    lin = torch.linspace(0, 1, W, dtype=dtype)
+    gy, gx = torch.meshgrid(lin, lin, indexing="ij")
+    sc = 0.5 + 0.5 * torch.rand(bs, 1, 1, generator=g, dtype=dtype)
+    ox = (1 - sc) * torch.rand(bs, 1, 1, generator=g, dtype=dtype)
+    oy = (1 - sc) * torch.rand(bs, 1, 1, generator=g, dtype=dtype)
+    roi_coord_2d = torch.stack([ox + sc * gx[None], oy + sc * gy[None]], dim=1)
+
+    # masks: ellipse object, blob occlusion, half-plane truncation
+    cx = 32 + 6 * torch.randn(bs, 1, 1, generator=g)
+    cy = 32 + 6 * torch.randn(bs, 1, 1, generator=g)
+    ax = 14 + 10 * torch.rand(bs, 1, 1, generator=g)
+    ay = 14 + 10 * torch.rand(bs, 1, 1, generator=g)
+    px = torch.arange(W, dtype=torch.float32)[None, None, :]
+    py = torch.arange(H, dtype=torch.float32)[None, :, None]
+    mask_obj = ((((px - cx) / ax) ** 2 + ((py - cy) / ay) ** 2) <= 1.0).float()
+    bx = 64 * torch.rand(bs, 1, 1, generator=g)
+    by = 64 * torch.rand(bs, 1, 1, generator=g)
+    br = 6 + 8 * torch.rand(bs, 1, 1, generator=g)
+    occl = (((px - bx) ** 2 + (py - by) ** 2) <= br**2).float()
+    mask_visib = mask_obj * (1 - occl)
+    cut = 44 + 20 * torch.rand(bs, 1, 1, generator=g)
+    mask_trunc = mask_visib * (px < cut).float()
+
+    roi_xyz = torch.rand(bs, 3, H, W, generator=g, dtype=dtype) * mask_obj[:, None]
+    roi_region = (torch.randint(1, 65, (bs, H, W), generator=g) * mask_obj.long()).long()
+
+    roi_extent = 0.05 + 0.25 * torch.rand(bs, 3, generator=g, dtype=dtype)
+    roi_points = (torch.rand(bs, n_points, 3, generator=g, dtype=dtype) - 0.5) * roi_extent[:, None, :]
+    ego_rot = random_rotations(bs, g).to(dtype)
+    trans = torch.stack(
+        [
+            -0.2 + 0.4 * torch.rand(bs, generator=g),
+            -0.2 + 0.4 * torch.rand(bs, generator=g),
+            0.4 + 1.1 * torch.rand(bs, generator=g),
+        ],
+        dim=1,
+    ).to(dtype)
+    roi_cam = torch.tensor(LM_K, dtype=dtype)[None].repeat(bs, 1, 1)
+    roi_center = torch.stack(
+        [160 + 320 * torch.rand(bs, generator=g), 120 + 240 * torch.rand(bs, generator=g)], dim=1
+    ).to(dtype)
+    roi_wh = (40 + 160 * torch.rand(bs, 2, generator=g)).to(dtype)
+    scale = 1.5 * roi_wh.max(dim=1)[0]
+    resize_ratio = (64.0 / scale).to(dtype)
+    # SITE targets (reference data_loader.py:628-632): centroid offset / bbox size, z scaled by resize ratio
+    proj = (roi_cam @ trans[:, :, None])[:, :, 0]
+    obj_center = proj[:, :2] / proj[:, 2:3]
+    delta_c = obj_center - roi_center
+    trans_ratio = torch.stack(
+        [delta_c[:, 0] / roi_wh[:, 0], delta_c[:, 1] / roi_wh[:, 1], trans[:, 2] / resize_ratio], dim=1
+    ).to(dtype)
+
+    sym_infos = None
+    if with_sym:
+        kinds = ["none", "z2", "cont", "z4"]
+        sym_infos = [discrete_symmetries(kinds[i % len(kinds)]) for i in range(bs)]
+
+    return dict(
+        roi_img=roi_img, roi_coord_2d=roi_coord_2d, roi_xyz=roi_xyz, roi_mask_trunc=mask_trunc,
+        roi_mask_visib=mask_visib, roi_mask_obj=mask_obj, roi_region=roi_region,
+        roi_cls=torch.zeros(bs, dtype=torch.long), roi_cam=roi_cam, roi_center=roi_center, roi_wh=roi_wh,
+        resize_ratio=resize_ratio, roi_extent=roi_extent, roi_points=roi_points, ego_rot=ego_rot, trans=trans,
+        roi_trans_ratio=trans_ratio, sym_info=sym_infos,
+    )
+
+
+def forward_kwargs(batch: dict, train: bool) -> dict:
+    """Maps batch fields to `GDRN.forward` kwargs exactly like reference `engine.py:244-269` /
+    `gdrn_evaluator.py:569-578`."""
+    kw = dict(
+        roi_classes=batch["roi_cls"], roi_coord_2d=batch["roi_coord_2d"], roi_cams=batch["roi_cam"],
+        roi_centers=batch["roi_center"], roi_whs=batch["roi_wh"], roi_extents=batch["roi_extent"],
+        resize_ratios=batch["resize_ratio"],
+    )
+    if train:
+        kw.update(
+            gt_xyz=batch["roi_xyz"], gt_xyz_bin=None, gt_mask_trunc=batch["roi_mask_trunc"],
+            gt_mask_visib=batch["roi_mask_visib"], gt_mask_obj=batch["roi_mask_obj"], gt_region=batch["roi_region"],
+            gt_ego_rot=batch["ego_rot"], gt_points=batch["roi_points"], sym_infos=batch["sym_info"],
+            gt_trans=batch["trans"], gt_trans_ratio=batch["roi_trans_ratio"], do_loss=True,
+        )
+    return kw
+
+
+def seeded_state_dict(template: dict, seed: int = 0) -> dict:
+    """Non-degenerate weights for every entry of `template` (a state_dict giving names/shapes).
+
+    SURVEY.md pitfall P1: the reference init (normal std=1e-3) collapses eval-mode activations,
+    so parity fixtures use Kaiming-scale weights and randomised BN statistics instead.
+    Each tensor is seeded by its own name => independent of iteration order.
+    """
+    out = {}
+    for name, t in template.items():
+        g = _gen(seed, name)
+        shape = tuple(t.shape)
+        if name.endswith("num_batches_tracked"):
+            out[name] = torch.zeros((), dtype=torch.long)
+        elif name.endswith("running_mean"):
+            out[name] = 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith("running_var"):
+            out[name] = 0.5 + torch.rand(shape, generator=g)
+        elif len(shape) == 1 and name.endswith("weight"):  # BN / GN gamma
+            out[name] = 0.5 + torch.rand(shape, generator=g)
+        elif len(shape) == 1 and name.endswith("bias"):
+            out[name] = 0.1 * torch.randn(shape, generator=g)
+        elif len(shape) >= 2:
+            if "rot_head_net.features.0." in name:  # ConvTranspose2d weight is [Cin, Cout, k, k]
+                fan_in = shape[0] * shape[2] * shape[3] / 4.0  # each output sees ~k*k/s^2 taps
+            else:
+                fan_in = 1
+                for s in shape[1:]:
+                    fan_in *= s
+            std = math.sqrt(2.0 / fan_in)
+            if name.startswith("pnp_net.fc_"):
+                std = math.sqrt(1.0 / fan_in)
+            out[name] = std * torch.randn(shape, generator=g)
+        else:
+            out[name] = torch.zeros(shape)
+        out[name] = out[name].to(t.dtype) if t.dtype.is_floating_point else out[name]
+    return out
