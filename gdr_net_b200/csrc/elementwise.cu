@@ -1,0 +1,746 @@
+// HBM-bound elementwise / normalisation kernels of the GDR-Net hot path (NHWC, bf16 hi[/lo] planes,
+// fp32 math, 16-byte vector accesses: one thread = 8 consecutive channels).
+//
+// Reference ops replaced (all ATen / cuDNN library kernels today):
+//   nn.BatchNorm2d train/eval + ReLU (+ residual add)        resnet_backbone.py:69-76, torchvision BasicBlock
+//   nn.MaxPool2d(3, 2, 1)                                    resnet_backbone.py:72
+//   nn.UpsamplingBilinear2d(scale_factor=2) (align_corners)  cdpn_rot_head_region.py:102
+//   nn.GroupNorm(32, 128) + ReLU                             conv_pnp_net.py:76-80
+// and their autograd backward.
+#include "gdrn_internal.h"
+#include "ptx.cuh"
+
+namespace gdrn {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        f[2 * j] = __uint_as_float(w[j] << 16);
+        f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+    }
+}
+// value = hi (+ lo)
+__device__ __forceinline__ void load8(const bf16* hi, const bf16* lo, long off8, float (&f)[8]) {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(hi) + off8), f);
+    if (lo != nullptr) {
+        float g[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(lo) + off8), g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += g[j];
+    }
+}
+__device__ __forceinline__ void store8(bf16* hi, bf16* lo, long off8, const float (&f)[8]) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        h[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+        l[j] = pack_bf16x2(f[2 * j] - __uint_as_float(h[j] << 16), f[2 * j + 1] - __uint_as_float(h[j] & 0xffff0000u));
+    }
+    reinterpret_cast<uint4*>(hi)[off8] = make_uint4(h[0], h[1], h[2], h[3]);
+    if (lo != nullptr) reinterpret_cast<uint4*>(lo)[off8] = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+static inline int ew_grid(long total, int block) {
+    long g = (total + block - 1) / block;
+    const long cap = (long)num_sms() * 8;
+    return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm statistics -> per-channel scale/shift (+ running-stat update)
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* running_mean, float* running_var,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out, int C, float count, float eps, float momentum, int train) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float mean, var;
+    if (train) {
+        const double m = (double)stats[c] / count;
+        double v = (double)stats[C + c] / count - m * m;
+        if (v < 0) v = 0;
+        mean = (float)m;
+        var = (float)v;
+        if (running_mean != nullptr) {
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+            const float unbiased = count > 1.f ? var * (count / (count - 1.f)) : var;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+        }
+    } else {
+        mean = running_mean[c];
+        var = running_var[c];
+    }
+    const float invstd = rsqrtf(var + eps);
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - mean * sc;
+    if (mean_out != nullptr) {
+        mean_out[c] = mean;
+        invstd_out[c] = invstd;
+    }
+}
+
+// y = [relu](x * scale[c] + shift[c] [+ res])
+__global__ void bn_act_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo, const bf16* __restrict__ r_hi,
+                              const bf16* __restrict__ r_lo, bf16* __restrict__ y_hi, bf16* __restrict__ y_lo,
+                              const float* __restrict__ scale, const float* __restrict__ shift, long rows, int C, int relu) {
+    const int cg = C / 8;
+    const long total = rows * cg;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(idx % cg) * 8;
+        float v[8];
+        load8(x_hi, x_lo, idx, v);
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c0)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c0 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + c0)), b1 = __ldg(reinterpret_cast<const float4*>(shift + c0 + 4));
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+        if (r_hi != nullptr) {
+            float r[8];
+            load8(r_hi, r_lo, idx, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += r[j];
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        store8(y_hi, y_lo, idx, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MaxPool 3x3 s2 p1 (first maximum in row-major window order wins, like ATen)
+// ------------------------------------------------------------------------------------------------
+__global__ void maxpool_fwd_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo, bf16* __restrict__ y_hi,
+                                   bf16* __restrict__ y_lo, int B, int H, int W, int C) {
+    const int cg = C / 8, Ho = H / 2, Wo = W / 2;
+    const long total = (long)B * Ho * Wo * cg;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int g = (int)(idx % cg);
+        long t = idx / cg;
+        const int ox = (int)(t % Wo);
+        t /= Wo;
+        const int oy = (int)(t % Ho);
+        const int b = (int)(t / Ho);
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+        for (int dy = 0; dy < 3; ++dy) {
+            const int iy = oy * 2 + dy - 1;
+            if (iy < 0 || iy >= H) continue;
+            for (int dx = 0; dx < 3; ++dx) {
+                const int ix = ox * 2 + dx - 1;
+                if (ix < 0 || ix >= W) continue;
+                float v[8];
+                load8(x_hi, x_lo, (((long)b * H + iy) * W + ix) * cg + g, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] = v[j] > m[j] ? v[j] : m[j];
+            }
+        }
+        store8(y_hi, y_lo, idx, m);
+    }
+}
+
+// dx[iy,ix] = sum over the (<=4) windows containing it whose first-max position is (iy,ix)
+__global__ void maxpool_bwd_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo,
+                                   const bf16* __restrict__ g_hi, const bf16* __restrict__ g_lo, bf16* __restrict__ dx_hi,
+                                   bf16* __restrict__ dx_lo, int B, int H, int W, int C) {
+    const int cg = C / 8, Ho = H / 2, Wo = W / 2;
+    const long total = (long)B * H * W * cg;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int g = (int)(idx % cg);
+        long t = idx / cg;
+        const int ix = (int)(t % W);
+        t /= W;
+        const int iy = (int)(t % H);
+        const int b = (int)(t / H);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        // windows oy with oy*2-1 <= iy <= oy*2+1  <=>  oy in [iy/2, (iy+1)/2]
+        for (int oy = iy / 2; oy <= (iy + 1) / 2; ++oy) {
+            if (oy < 0 || oy >= Ho) continue;
+            for (int ox = ix / 2; ox <= (ix + 1) / 2; ++ox) {
+                if (ox < 0 || ox >= Wo) continue;
+                float m[8];
+                int arg[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    m[j] = -INFINITY;
+                    arg[j] = -1;
+                }
+                for (int dy = 0; dy < 3; ++dy) {
+                    const int yy = oy * 2 + dy - 1;
+                    if (yy < 0 || yy >= H) continue;
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int xx = ox * 2 + dx - 1;
+                        if (xx < 0 || xx >= W) continue;
+                        float v[8];
+                        load8(x_hi, x_lo, (((long)b * H + yy) * W + xx) * cg + g, v);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (v[j] > m[j]) {
+                                m[j] = v[j];
+                                arg[j] = yy * W + xx;
+                            }
+                    }
+                }
+                float gv[8];
+                load8(g_hi, g_lo, (((long)b * Ho + oy) * Wo + ox) * cg + g, gv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (arg[j] == iy * W + ix) acc[j] += gv[j];
+            }
+        }
+        store8(dx_hi, dx_lo, idx, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bilinear x2 upsampling, align_corners=True
+// ------------------------------------------------------------------------------------------------
+__global__ void upsample2x_fwd_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo, bf16* __restrict__ y_hi,
+                                      bf16* __restrict__ y_lo, int B, int H, int W, int C) {
+    const int cg = C / 8, Ho = 2 * H, Wo = 2 * W;
+    const float sh = (float)(H - 1) / (float)(Ho - 1), sw = (float)(W - 1) / (float)(Wo - 1);
+    const long total = (long)B * Ho * Wo * cg;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int g = (int)(idx % cg);
+        long t = idx / cg;
+        const int ox = (int)(t % Wo);
+        t /= Wo;
+        const int oy = (int)(t % Ho);
+        const int b = (int)(t / Ho);
+        const float fy = sh * oy, fx = sw * ox;
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+        const float ly1 = fy - y0, lx1 = fx - x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+        float v00[8], v01[8], v10[8], v11[8], o[8];
+        const long base = (long)b * H;
+        load8(x_hi, x_lo, ((base + y0) * W + x0) * cg + g, v00);
+        load8(x_hi, x_lo, ((base + y0) * W + x1) * cg + g, v01);
+        load8(x_hi, x_lo, ((base + y1) * W + x0) * cg + g, v10);
+        load8(x_hi, x_lo, ((base + y1) * W + x1) * cg + g, v11);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = ly0 * (lx0 * v00[j] + lx1 * v01[j]) + ly1 * (lx0 * v10[j] + lx1 * v11[j]);
+        store8(y_hi, y_lo, idx, o);
+    }
+}
+
+// gather form of the transpose: dx[iy,ix] = sum_{oy,ox} w(oy->iy) * w(ox->ix) * g[oy,ox]
+__global__ void upsample2x_bwd_kernel(const bf16* __restrict__ g_hi, const bf16* __restrict__ g_lo, bf16* __restrict__ dx_hi,
+                                      bf16* __restrict__ dx_lo, int B, int H, int W, int C) {
+    const int cg = C / 8, Ho = 2 * H, Wo = 2 * W;
+    const float sh = (float)(H - 1) / (float)(Ho - 1), sw = (float)(W - 1) / (float)(Wo - 1);
+    const long total = (long)B * H * W * cg;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int g = (int)(idx % cg);
+        long t = idx / cg;
+        const int ix = (int)(t % W);
+        t /= W;
+        const int iy = (int)(t % H);
+        const int b = (int)(t / H);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        const int oy_lo = max(0, 2 * iy - 3), oy_hi = min(Ho - 1, 2 * iy + 3);
+        const int ox_lo = max(0, 2 * ix - 3), ox_hi = min(Wo - 1, 2 * ix + 3);
+        for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+            const float fy = sh * oy;
+            const int y0 = (int)fy;
+            const int y1 = y0 + (y0 < H - 1 ? 1 : 0);
+            const float ly1 = fy - y0, ly0 = 1.f - ly1;
+            float wy = 0.f;
+            if (y0 == iy) wy += ly0;
+            if (y1 == iy) wy += ly1;
+            if (wy == 0.f) continue;
+            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                const float fx = sw * ox;
+                const int x0 = (int)fx;
+                const int x1 = x0 + (x0 < W - 1 ? 1 : 0);
+                const float lx1 = fx - x0, lx0 = 1.f - lx1;
+                float wx = 0.f;
+                if (x0 == ix) wx += lx0;
+                if (x1 == ix) wx += lx1;
+                if (wx == 0.f) continue;
+                float gv[8];
+                load8(g_hi, g_lo, (((long)b * Ho + oy) * Wo + ox) * cg + g, gv);
+                const float w = wy * wx;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, gv[j], acc[j]);
+            }
+        }
+        store8(dx_hi, dx_lo, idx, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// zero insertion (stride-2 transposed convs as stride-1 convs) and its transpose
+//   mode 0: y[2i,2j] = x[i,j], 0 elsewhere (y is [B,2H,2W,C]);  mode 1: y[i,j] = x[2i,2j] (x is [B,2H,2W,C])
+// ------------------------------------------------------------------------------------------------
+__global__ void zero_insert_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo, bf16* __restrict__ y_hi,
+                                   bf16* __restrict__ y_lo, int B, int H, int W, int C, int mode) {
+    const int cg = C / 8;
+    const int Hy = mode == 0 ? 2 * H : H, Wy = mode == 0 ? 2 * W : W;
+    const long total = (long)B * Hy * Wy * cg;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int g = (int)(idx % cg);
+        long t = idx / cg;
+        const int x = (int)(t % Wy);
+        t /= Wy;
+        const int y = (int)(t % Hy);
+        const int b = (int)(t / Hy);
+        uint4 h = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
+        if (mode == 0) {
+            if (((x | y) & 1) == 0) {
+                const long s = (((long)b * H + (y >> 1)) * W + (x >> 1)) * cg + g;
+                h = __ldg(reinterpret_cast<const uint4*>(x_hi) + s);
+                if (x_lo != nullptr) l = __ldg(reinterpret_cast<const uint4*>(x_lo) + s);
+            }
+        } else {
+            const long s = (((long)b * 2 * H + 2 * y) * 2 * W + 2 * x) * cg + g;
+            h = __ldg(reinterpret_cast<const uint4*>(x_hi) + s);
+            if (x_lo != nullptr) l = __ldg(reinterpret_cast<const uint4*>(x_lo) + s);
+        }
+        reinterpret_cast<uint4*>(y_hi)[idx] = h;
+        if (y_lo != nullptr) reinterpret_cast<uint4*>(y_lo)[idx] = l;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm(+ReLU) backward.  g = (ga [+ gb]) * [y > 0];  xhat = (u - mean) * invstd
+//   reduce: sums[0][c] = sum g, sums[1][c] = sum g * xhat
+//   apply : du = gamma*invstd * (g - sums0/n - xhat * sums1/n);  optional g_out = g;  dgamma = sums1, dbeta = sums0
+// ------------------------------------------------------------------------------------------------
+constexpr int kBnBwdThreads = 256;
+
+__global__ void __launch_bounds__(kBnBwdThreads) bn_bwd_reduce_kernel(
+    const bf16* __restrict__ ga_hi, const bf16* __restrict__ ga_lo, const bf16* __restrict__ gb_hi,
+    const bf16* __restrict__ gb_lo, const bf16* __restrict__ y_hi, const bf16* __restrict__ u_hi,
+    const bf16* __restrict__ u_lo, const float* __restrict__ mean, const float* __restrict__ invstd,
+    float* __restrict__ sums, long rows, int C) {
+    // block = (C/8) channel groups x rpb row lanes
+    const int cg = C / 8;
+    const int rpb = kBnBwdThreads / cg;  // cg in {8,16,32,64}: always divides 256
+    const int g = threadIdx.x % cg;
+    const int rl = threadIdx.x / cg;
+    float s0[8], s1[8], mu[8], is[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        s0[j] = 0.f;
+        s1[j] = 0.f;
+        mu[j] = mean[g * 8 + j];
+        is[j] = invstd[g * 8 + j];
+    }
+    for (long r = (long)blockIdx.x * rpb + rl; r < rows; r += (long)gridDim.x * rpb) {
+        const long off = r * cg + g;
+        float gv[8], u[8];
+        load8(ga_hi, ga_lo, off, gv);
+        if (gb_hi != nullptr) {
+            float t[8];
+            load8(gb_hi, gb_lo, off, t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gv[j] += t[j];
+        }
+        if (y_hi != nullptr) {
+            float y[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(y_hi) + off), y);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gv[j] = y[j] > 0.f ? gv[j] : 0.f;
+        }
+        load8(u_hi, u_lo, off, u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s0[j] += gv[j];
+            s1[j] = fmaf(gv[j], (u[j] - mu[j]) * is[j], s1[j]);
+        }
+    }
+    __shared__ float red[2][kBnBwdThreads][8 + 1];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        red[0][threadIdx.x][j] = s0[j];
+        red[1][threadIdx.x][j] = s1[j];
+    }
+    __syncthreads();
+    // thread t < 2*C: which = t / C, channel = t % C
+    for (int t = threadIdx.x; t < 2 * C; t += kBnBwdThreads) {
+        const int which = t / C, c = t % C;
+        const int gg = c / 8, j = c % 8;
+        float a = 0.f;
+        for (int q = 0; q < rpb; ++q) a += red[which][q * cg + gg][j];
+        atomicAdd(sums + which * C + c, a);
+    }
+}
+
+__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ ga_hi, const bf16* __restrict__ ga_lo,
+                                    const bf16* __restrict__ gb_hi, const bf16* __restrict__ gb_lo,
+                                    const bf16* __restrict__ y_hi, const bf16* __restrict__ u_hi,
+                                    const bf16* __restrict__ u_lo, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ sums, bf16* __restrict__ du_hi, bf16* __restrict__ du_lo,
+                                    bf16* __restrict__ gout_hi, bf16* __restrict__ gout_lo, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, long rows, int C, int train) {
+    const int cg = C / 8;
+    const long total = rows * cg;
+    const float inv_n = 1.f / (float)rows;
+    if (blockIdx.x == 0 && dgamma != nullptr) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            dbeta[c] = sums[c];
+            dgamma[c] = sums[C + c];
+        }
+    }
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(idx % cg) * 8;
+        float gv[8], u[8], o[8];
+        load8(ga_hi, ga_lo, idx, gv);
+        if (gb_hi != nullptr) {
+            float t[8];
+            load8(gb_hi, gb_lo, idx, t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gv[j] += t[j];
+        }
+        if (y_hi != nullptr) {
+            float y[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(y_hi) + idx), y);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gv[j] = y[j] > 0.f ? gv[j] : 0.f;
+        }
+        load8(u_hi, u_lo, idx, u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            const float is = invstd[c];
+            if (train) {
+                const float xh = (u[j] - mean[c]) * is;
+                o[j] = gamma[c] * is * (gv[j] - sums[c] * inv_n - xh * sums[C + c] * inv_n);
+            } else {
+                o[j] = gamma[c] * is * gv[j];
+            }
+        }
+        store8(du_hi, du_lo, idx, o);
+        if (gout_hi != nullptr) store8(gout_hi, gout_lo, idx, gv);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm(32 groups) + ReLU, one CTA per sample, tensor [HW][C] (C = 128 => 4 channels per group)
+// ------------------------------------------------------------------------------------------------
+// stats layout: [B][G][2] (mean, rstd).  Each thread owns one 8-channel column group (= 2 GN groups when C/G = 4)
+__global__ void __launch_bounds__(256) gn_relu_fwd_kernel(const bf16* __restrict__ u_hi, const bf16* __restrict__ u_lo,
+                                                          bf16* __restrict__ y_hi, bf16* __restrict__ y_lo,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float* __restrict__ stats, int HW, int C, int G, float eps) {
+    const int b = blockIdx.x;
+    const int cg = C / 8;             // 16
+    const int g = threadIdx.x % cg;   // column group
+    const int rl = threadIdx.x / cg;  // row lane
+    const int rpb = 256 / cg;
+    const int cpg = C / G;  // channels per group (4)
+    __shared__ float sm[2][256][8 + 1];
+    __shared__ float gstat[64][2];
+    float s0[8], s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
+    const long base = (long)b * HW * cg;
+    for (int r = rl; r < HW; r += rpb) {
+        float v[8];
+        load8(u_hi, u_lo, base + (long)r * cg + g, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s0[j] += v[j];
+            s1[j] = fmaf(v[j], v[j], s1[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sm[0][threadIdx.x][j] = s0[j];
+        sm[1][threadIdx.x][j] = s1[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        const int grp = threadIdx.x;
+        double a0 = 0, a1 = 0;
+        for (int c = grp * cpg; c < (grp + 1) * cpg; ++c) {
+            const int gg = c / 8, j = c % 8;
+            for (int q = 0; q < rpb; ++q) {
+                a0 += sm[0][q * cg + gg][j];
+                a1 += sm[1][q * cg + gg][j];
+            }
+        }
+        const double n = (double)HW * cpg;
+        const double m = a0 / n;
+        double var = a1 / n - m * m;
+        if (var < 0) var = 0;
+        const float rstd = rsqrtf((float)var + eps);
+        gstat[grp][0] = (float)m;
+        gstat[grp][1] = rstd;
+        stats[((long)b * G + grp) * 2 + 0] = (float)m;
+        stats[((long)b * G + grp) * 2 + 1] = rstd;
+    }
+    __syncthreads();
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = g * 8 + j;
+        const int grp = c / cpg;
+        sc[j] = gamma[c] * gstat[grp][1];
+        sh[j] = beta[c] - gstat[grp][0] * sc[j];
+    }
+    for (int r = rl; r < HW; r += rpb) {
+        float v[8];
+        const long off = base + (long)r * cg + g;
+        load8(u_hi, u_lo, off, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+        store8(y_hi, y_lo, off, v);
+    }
+}
+
+// du = rstd * (dxh - mean_grp(dxh) - xh * mean_grp(dxh * xh)),  dxh = g*[y>0]*gamma;  dgamma += sum g*xh, dbeta += sum g
+__global__ void __launch_bounds__(256) gn_relu_bwd_kernel(const bf16* __restrict__ g_hi, const bf16* __restrict__ g_lo,
+                                                          const bf16* __restrict__ y_hi, const bf16* __restrict__ u_hi,
+                                                          const bf16* __restrict__ u_lo, const float* __restrict__ gamma,
+                                                          const float* __restrict__ stats, bf16* __restrict__ du_hi,
+                                                          bf16* __restrict__ du_lo, float* __restrict__ dgamma,
+                                                          float* __restrict__ dbeta, int HW, int C, int G) {
+    const int b = blockIdx.x;
+    const int cg = C / 8;
+    const int g = threadIdx.x % cg;
+    const int rl = threadIdx.x / cg;
+    const int rpb = 256 / cg;
+    const int cpg = C / G;
+    __shared__ float sm[2][256][8 + 1];
+    __shared__ float gred[64][2];
+    float mu[8], rs[8], ga[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = g * 8 + j;
+        mu[j] = stats[((long)b * G + c / cpg) * 2 + 0];
+        rs[j] = stats[((long)b * G + c / cpg) * 2 + 1];
+        ga[j] = gamma[c];
+    }
+    float s0[8], s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
+    const long base = (long)b * HW * cg;
+    for (int r = rl; r < HW; r += rpb) {
+        const long off = base + (long)r * cg + g;
+        float gv[8], y[8], u[8];
+        load8(g_hi, g_lo, off, gv);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(y_hi) + off), y);
+        load8(u_hi, u_lo, off, u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float gg = y[j] > 0.f ? gv[j] : 0.f;
+            const float xh = (u[j] - mu[j]) * rs[j];
+            s0[j] += gg;
+            s1[j] = fmaf(gg, xh, s1[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sm[0][threadIdx.x][j] = s0[j];
+        sm[1][threadIdx.x][j] = s1[j];
+    }
+    __syncthreads();
+    // per-channel sums -> dgamma/dbeta (atomics over samples) and per-group means of dxh, dxh*xh
+    __shared__ float chs[2][128];
+    for (int c = threadIdx.x; c < C; c += 256) {
+        const int gg = c / 8, j = c % 8;
+        float a0 = 0.f, a1 = 0.f;
+        for (int q = 0; q < rpb; ++q) {
+            a0 += sm[0][q * cg + gg][j];
+            a1 += sm[1][q * cg + gg][j];
+        }
+        chs[0][c] = a0;
+        chs[1][c] = a1;
+        atomicAdd(dbeta + c, a0);
+        atomicAdd(dgamma + c, a1);
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        const int grp = threadIdx.x;
+        float a0 = 0.f, a1 = 0.f;
+        for (int c = grp * cpg; c < (grp + 1) * cpg; ++c) {
+            a0 += chs[0][c] * gamma[c];
+            a1 += chs[1][c] * gamma[c];
+        }
+        const float n = (float)HW * cpg;
+        gred[grp][0] = a0 / n;
+        gred[grp][1] = a1 / n;
+    }
+    __syncthreads();
+    for (int r = rl; r < HW; r += rpb) {
+        const long off = base + (long)r * cg + g;
+        float gv[8], y[8], u[8], o[8];
+        load8(g_hi, g_lo, off, gv);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(y_hi) + off), y);
+        load8(u_hi, u_lo, off, u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int grp = (g * 8 + j) / cpg;
+            const float gg = y[j] > 0.f ? gv[j] : 0.f;
+            const float xh = (u[j] - mu[j]) * rs[j];
+            o[j] = rs[j] * (gg * ga[j] - gred[grp][0] - xh * gred[grp][1]);
+        }
+        store8(du_hi, du_lo, off, o);
+    }
+}
+
+// out (bf16 hi/lo) = a + b   (gradient merge of two branches)
+__global__ void add2_kernel(const bf16* __restrict__ a_hi, const bf16* __restrict__ a_lo, const bf16* __restrict__ b_hi,
+                            const bf16* __restrict__ b_lo, bf16* __restrict__ o_hi, bf16* __restrict__ o_lo, long n8) {
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n8; idx += (long)gridDim.x * blockDim.x) {
+        float a[8], b[8];
+        load8(a_hi, a_lo, idx, a);
+        load8(b_hi, b_lo, idx, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += b[j];
+        store8(o_hi, o_lo, idx, a);
+    }
+}
+
+// fp32 [rows][C] -> bf16 hi/lo (and the reverse) for API-edge tensors
+__global__ void f32_to_planes_kernel(const float* __restrict__ x, bf16* __restrict__ y_hi, bf16* __restrict__ y_lo, long n8) {
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n8; idx += (long)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * idx), b = __ldg(reinterpret_cast<const float4*>(x) + 2 * idx + 1);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        store8(y_hi, y_lo, idx, v);
+    }
+}
+__global__ void planes_to_f32_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo, float* __restrict__ y, long n8) {
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n8; idx += (long)gridDim.x * blockDim.x) {
+        float v[8];
+        load8(x_hi, x_lo, idx, v);
+        reinterpret_cast<float4*>(y)[2 * idx] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(y)[2 * idx + 1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+}  // namespace gdrn
+
+using namespace gdrn;
+#define STREAM cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_)
+#define BF(p) reinterpret_cast<bf16*>(p)
+#define CBF(p) reinterpret_cast<const bf16*>(p)
+#define LAUNCH_DONE()                  \
+    GDRN_CUDA_OK(cudaGetLastError()); \
+    count_launch();                    \
+    return 0
+
+extern "C" int gdrn_bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean,
+                                float* running_var, float* scale, float* shift, float* mean_out, float* invstd_out, int C,
+                                float count, float eps, float momentum, int train, void* stream_) {
+    STREAM;
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(stats, gamma, beta, running_mean, running_var, scale, shift,
+                                                          mean_out, invstd_out, C, count, eps, momentum, train);
+    LAUNCH_DONE();
+}
+
+extern "C" int gdrn_bn_act(const void* x_hi, const void* x_lo, const void* r_hi, const void* r_lo, void* y_hi, void* y_lo,
+                           const float* scale, const float* shift, long rows, int C, int relu, void* stream_) {
+    STREAM;
+    if (C % 8) return set_error(GDRN_ERR_ARG, "bn_act: C %% 8 != 0");
+    bn_act_kernel<<<ew_grid(rows * (C / 8), 256), 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), CBF(r_hi), CBF(r_lo), BF(y_hi),
+                                                                    BF(y_lo), scale, shift, rows, C, relu);
+    LAUNCH_DONE();
+}
+
+extern "C" int gdrn_maxpool_fwd(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int B, int H, int W, int C,
+                                void* stream_) {
+    STREAM;
+    maxpool_fwd_kernel<<<ew_grid((long)B * (H / 2) * (W / 2) * (C / 8), 256), 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), BF(y_hi),
+                                                                                              BF(y_lo), B, H, W, C);
+    LAUNCH_DONE();
+}
+extern "C" int gdrn_maxpool_bwd(const void* x_hi, const void* x_lo, const void* g_hi, const void* g_lo, void* dx_hi,
+                                void* dx_lo, int B, int H, int W, int C, void* stream_) {
+    STREAM;
+    maxpool_bwd_kernel<<<ew_grid((long)B * H * W * (C / 8), 256), 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), CBF(g_hi), CBF(g_lo),
+                                                                                    BF(dx_hi), BF(dx_lo), B, H, W, C);
+    LAUNCH_DONE();
+}
+extern "C" int gdrn_upsample2x_fwd(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int B, int H, int W, int C,
+                                   void* stream_) {
+    STREAM;
+    upsample2x_fwd_kernel<<<ew_grid((long)B * 4 * H * W * (C / 8), 256), 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), BF(y_hi),
+                                                                                           BF(y_lo), B, H, W, C);
+    LAUNCH_DONE();
+}
+extern "C" int gdrn_upsample2x_bwd(const void* g_hi, const void* g_lo, void* dx_hi, void* dx_lo, int B, int H, int W, int C,
+                                   void* stream_) {
+    STREAM;
+    upsample2x_bwd_kernel<<<ew_grid((long)B * H * W * (C / 8), 256), 256, 0, stream>>>(CBF(g_hi), CBF(g_lo), BF(dx_hi),
+                                                                                       BF(dx_lo), B, H, W, C);
+    LAUNCH_DONE();
+}
+extern "C" int gdrn_zero_insert(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int B, int H, int W, int C,
+                                int mode, void* stream_) {
+    STREAM;
+    const long total = (long)B * H * W * (C / 8) * (mode == 0 ? 4 : 1);
+    zero_insert_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), BF(y_hi), BF(y_lo), B, H, W, C, mode);
+    LAUNCH_DONE();
+}
+
+extern "C" int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_hi, const void* gb_lo, const void* y_hi,
+                           const void* u_hi, const void* u_lo, const float* mean, const float* invstd, const float* gamma,
+                           float* sums, void* du_hi, void* du_lo, void* gout_hi, void* gout_lo, float* dgamma,
+                           float* dbeta, long rows, int C, int train, void* stream_) {
+    STREAM;
+    if (C % 64 || C > 512) return set_error(GDRN_ERR_ARG, "bn_bwd: unsupported C=%d", C);
+    if (train) {
+        GDRN_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream));
+        const int rpb = kBnBwdThreads / (C / 8);
+        long blocks = (rows + rpb - 1) / rpb;
+        const long cap = (long)num_sms() * 4;
+        if (blocks > cap) blocks = cap;
+        bn_bwd_reduce_kernel<<<(int)blocks, kBnBwdThreads, 0, stream>>>(CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo),
+                                                                        CBF(y_hi), CBF(u_hi), CBF(u_lo), mean, invstd, sums,
+                                                                        rows, C);
+        GDRN_CUDA_OK(cudaGetLastError());
+        count_launch();
+    }
+    bn_bwd_apply_kernel<<<ew_grid(rows * (C / 8), 256), 256, 0, stream>>>(
+        CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo), CBF(y_hi), CBF(u_hi), CBF(u_lo), mean, invstd, gamma, sums,
+        BF(du_hi), BF(du_lo), BF(gout_hi), BF(gout_lo), dgamma, dbeta, rows, C, train);
+    LAUNCH_DONE();
+}
+
+extern "C" int gdrn_gn_relu_fwd(const void* u_hi, const void* u_lo, void* y_hi, void* y_lo, const float* gamma,
+                                const float* beta, float* stats, int B, int HW, int C, int G, float eps, void* stream_) {
+    STREAM;
+    if (C != 128 || G > 64 || C % G) return set_error(GDRN_ERR_ARG, "gn_relu_fwd: only C=128 supported");
+    gn_relu_fwd_kernel<<<B, 256, 0, stream>>>(CBF(u_hi), CBF(u_lo), BF(y_hi), BF(y_lo), gamma, beta, stats, HW, C, G, eps);
+    LAUNCH_DONE();
+}
+extern "C" int gdrn_gn_relu_bwd(const void* g_hi, const void* g_lo, const void* y_hi, const void* u_hi, const void* u_lo,
+                                const float* gamma, const float* stats, void* du_hi, void* du_lo, float* dgamma,
+                                float* dbeta, int B, int HW, int C, int G, void* stream_) {
+    STREAM;
+    if (C != 128 || G > 64 || C % G) return set_error(GDRN_ERR_ARG, "gn_relu_bwd: only C=128 supported");
+    gn_relu_bwd_kernel<<<B, 256, 0, stream>>>(CBF(g_hi), CBF(g_lo), CBF(y_hi), CBF(u_hi), CBF(u_lo), gamma, stats, BF(du_hi),
+                                              BF(du_lo), dgamma, dbeta, HW, C, G);
+    LAUNCH_DONE();
+}
+extern "C" int gdrn_add2(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* o_hi, void* o_lo,
+                         long n, void* stream_) {
+    STREAM;
+    add2_kernel<<<ew_grid(n / 8, 256), 256, 0, stream>>>(CBF(a_hi), CBF(a_lo), CBF(b_hi), CBF(b_lo), BF(o_hi), BF(o_lo), n / 8);
+    LAUNCH_DONE();
+}
+extern "C" int gdrn_f32_to_planes(const float* x, void* y_hi, void* y_lo, long n, void* stream_) {
+    STREAM;
+    f32_to_planes_kernel<<<ew_grid(n / 8, 256), 256, 0, stream>>>(x, BF(y_hi), BF(y_lo), n / 8);
+    LAUNCH_DONE();
+}
+extern "C" int gdrn_planes_to_f32(const void* x_hi, const void* x_lo, float* y, long n, void* stream_) {
+    STREAM;
+    planes_to_f32_kernel<<<ew_grid(n / 8, 256), 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), y, n / 8);
+    LAUNCH_DONE();
+}

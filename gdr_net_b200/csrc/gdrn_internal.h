@@ -1,0 +1,33 @@
+// Internal helpers shared by the .cu translation units of libgdrn_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define GDRN_OK 0
+#define GDRN_ERR_ARG (-1)
+#define GDRN_ERR_CUDA (-2)
+
+namespace gdrn {
+
+// thread-local last-error message (never throw across the C ABI)
+int set_error(int code, const char* fmt, ...);
+int cuda_error(cudaError_t e, const char* file, int line);
+int num_sms();
+void count_launch();
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency).
+// bf16 elements, 128-byte swizzle, zero fill for out-of-bounds box elements.
+int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box);
+
+}  // namespace gdrn
+
+#define GDRN_CUDA_OK(expr)                                                      \
+    do {                                                                        \
+        cudaError_t _e = (expr);                                                \
+        if (_e != cudaSuccess) return gdrn::cuda_error(_e, __FILE__, __LINE__); \
+    } while (0)

@@ -1,0 +1,478 @@
+// tcgen05 / TMEM / TMA implicit-GEMM forward kernel (sm_100a).
+//
+// One persistent, warp-specialised kernel serves every GEMM-shaped forward op of the GDR-Net hot
+// path (reference call sites: resnet_backbone.py:69-76 convs, cdpn_rot_head_region.py:82-135,
+// conv_pnp_net.py:76-80 + fc1/fc2/fc_r/fc_t :111-157) and, with flipped weights, every dgrad:
+//
+//   D[M = pixels][N = Cout] = sum_k A[M][K] * W[N][K]          (bf16 operands, fp32 accumulate in TMEM)
+//
+//   * A is never materialised: for a conv, each 64-wide k-block is one (tap, channel-chunk) and its
+//     128x64 A tile is ONE 4-D TMA box {64 ch, Wo, TH, TN} of the NHWC activation tensor at the
+//     tap-shifted coordinate; out-of-image rows/cols are zero-filled by TMA (= conv padding).
+//     Stride-2 convs read from four phase sub-lattices (one tensor map per (row, col) parity).
+//   * W is a K-major [Cout][KH*KW*Cin] bf16 matrix (prepared by pack kernels), 2-D TMA boxes.
+//   * Both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes.
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
+//     warps 4-7 = epilogue (tcgen05.ld -> bias/activation -> bf16 hi[/lo] or fp32 stores, per-channel
+//     sum / sum-of-squares for BatchNorm batch statistics).  Accumulators are double-buffered in
+//     TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   * NSPLIT = 3 is the fp32-faithful mode: operands are (hi, lo) bf16 planes and each k-step issues
+//     hi*hi + hi*lo + lo*hi (the lo*lo term, 2^-18 relative, is dropped).
+#include "gdrn_internal.h"
+#include "ptx.cuh"
+
+namespace gdrn {
+
+struct GemmParams {
+    CUtensorMap tmA[2][4];  // [plane hi/lo][stride-2 phase]
+    CUtensorMap tmB[2];     // [plane hi/lo]
+    int mode;               // 0 = plain 2-D GEMM, 1 = conv (4-D boxes)
+    int M, N;               // valid rows / cols
+    int num_m_tiles, num_n_tiles, num_kb;
+    int cchunks, KW, pad, stride;
+    int tiles_per_img, TH, TN;
+    void* out_hi;
+    void* out_lo;
+    float* out_f32;
+    int ldc;
+    const float* bias;
+    int act;       // 0 none, 1 LeakyReLU(0.1)
+    float* stats;  // [2][N]: sum, sum of squares (accumulated with atomics) or nullptr
+};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kSmemBudget = 227 * 1024;
+constexpr int kAuxBytes = 4096;
+
+template <int BLOCK_N, int NSPLIT>
+struct GemmCfg {
+    static constexpr int NPL = (NSPLIT == 1) ? 1 : 2;
+    static constexpr int A_BYTES = kBlockM * kBlockK * 2;
+    static constexpr int B_BYTES = BLOCK_N * kBlockK * 2;
+    static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
+    static constexpr int STAGES_RAW = (kSmemBudget - kAuxBytes - 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kAuxBytes + 1024;
+    static constexpr int TMEM_COLS = 2 * BLOCK_N;  // double-buffered accumulator
+    static_assert(STAGES >= 2, "pipeline too shallow");
+    static_assert(TMEM_COLS <= 512, "TMEM overflow");
+};
+
+// Sum the 32 lanes' values column-wise: on return lane j holds sum over lanes of v[j] (31 shuffles).
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            float send = upper ? v[i] : v[i + off];
+            float keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+template <int BLOCK_N, int NSPLIT>
+__global__ void __launch_bounds__(256, 1) gemm_fwd_kernel(const __grid_constant__ GemmParams p) {
+    using Cfg = GemmCfg<BLOCK_N, NSPLIT>;
+    constexpr int NPL = Cfg::NPL;
+    constexpr int STAGES = Cfg::STAGES;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* s_stats = reinterpret_cast<float*>(aux + 512);  // [2][BLOCK_N]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        for (int pl = 0; pl < NPL; ++pl) {
+            tma_prefetch_desc(&p.tmB[pl]);
+            tma_prefetch_desc(&p.tmA[pl][0]);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) s_stats[i] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int n_tile = t % p.num_n_tiles;
+                const int m_tile = t / p.num_n_tiles;
+                int n0 = 0, h0 = 0;
+                if (p.mode == 1) {
+                    if (p.TN == 1) {
+                        n0 = m_tile / p.tiles_per_img;
+                        h0 = (m_tile % p.tiles_per_img) * p.TH;
+                    } else {
+                        n0 = m_tile * p.TN;
+                    }
+                }
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+                    if (p.mode == 1) {
+                        const int tap = kb / p.cchunks;
+                        const int cc = kb - tap * p.cchunks;
+                        const int r = tap / p.KW;
+                        const int s = tap - r * p.KW;
+                        int dh = r - p.pad, dw = s - p.pad, map = 0;
+                        if (p.stride == 2) {
+                            map = ((dh & 1) << 1) | (dw & 1);
+                            dh >>= 1;  // arithmetic shift == floor division
+                            dw >>= 1;
+                        }
+#pragma unroll
+                        for (int pl = 0; pl < NPL; ++pl)
+                            tma_load_4d(st + pl * Cfg::A_BYTES, &p.tmA[pl][map], &full_bar[stage], cc * kBlockK, dw,
+                                        h0 + dh, n0);
+                    } else {
+#pragma unroll
+                        for (int pl = 0; pl < NPL; ++pl)
+                            tma_load_2d(st + pl * Cfg::A_BYTES, &p.tmA[pl][0], &full_bar[stage], kb * kBlockK,
+                                        m_tile * kBlockM);
+                    }
+#pragma unroll
+                    for (int pl = 0; pl < NPL; ++pl)
+                        tma_load_2d(st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES, &p.tmB[pl], &full_bar[stage],
+                                    kb * kBlockK, n_tile * BLOCK_N);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (single thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t b_hi = a_hi + NPL * Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        const uint64_t da = make_smem_desc(a_hi + k * 32, 16, 1024);
+                        const uint64_t db = make_smem_desc(b_hi + k * 32, 16, 1024);
+                        umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (NSPLIT == 3) {
+                            const uint64_t da_lo = make_smem_desc(a_hi + Cfg::A_BYTES + k * 32, 16, 1024);
+                            const uint64_t db_lo = make_smem_desc(b_hi + Cfg::B_BYTES + k * 32, 16, 1024);
+                            umma_bf16(d_tmem, da, db_lo, idesc, 1u);
+                            umma_bf16(d_tmem, da_lo, db, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above retire
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue (128 threads)
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;
+        __nv_bfloat16* out_hi = reinterpret_cast<__nv_bfloat16*>(p.out_hi);
+        __nv_bfloat16* out_lo = reinterpret_cast<__nv_bfloat16*>(p.out_lo);
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int n_tile = t % p.num_n_tiles;
+            const int m_tile = t / p.num_n_tiles;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const long grow = (long)m_tile * kBlockM + row;
+            const bool row_ok = grow < p.M;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t raw[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + c * 32, raw);
+                tmem_ld_wait();
+                const int col0 = n_tile * BLOCK_N + c * 32;
+                if (col0 >= p.N) continue;  // warp-uniform
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(raw[j]);
+                const bool full_chunk = (col0 + 32 <= p.N);
+                if (p.bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (full_chunk || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+                }
+                if (p.act == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : 0.1f * f[j];
+                }
+                if (row_ok) {
+                    if (p.out_f32 != nullptr) {
+                        float* dst = p.out_f32 + grow * p.ldc + col0;
+                        if (full_chunk) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < p.ldc) dst[j] = (col0 + j < p.N) ? f[j] : 0.f;
+                        }
+                    }
+                    if (out_hi != nullptr) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float a = f[2 * j], b = f[2 * j + 1];
+                            if (!full_chunk) {
+                                if (col0 + 2 * j >= p.N) a = 0.f;
+                                if (col0 + 2 * j + 1 >= p.N) b = 0.f;
+                            }
+                            hi[j] = pack_bf16x2(a, b);
+                            const float ra = a - __uint_as_float(hi[j] << 16);
+                            const float rb = b - __uint_as_float(hi[j] & 0xffff0000u);
+                            lo[j] = pack_bf16x2(ra, rb);
+                        }
+                        const int ncopy = full_chunk ? 4 : ((min(p.ldc, col0 + 32) - col0) / 8);
+                        uint4* dh = reinterpret_cast<uint4*>(out_hi + grow * p.ldc + col0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j < ncopy) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        if (out_lo != nullptr) {
+                            uint4* dl = reinterpret_cast<uint4*>(out_lo + grow * p.ldc + col0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (j < ncopy)
+                                    dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        }
+                    }
+                }
+                if (p.stats != nullptr) {
+                    float sq[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (!row_ok) f[j] = 0.f;
+                        sq[j] = f[j] * f[j];
+                    }
+                    const float s1 = warp_transpose_reduce(f, lane);
+                    const float s2 = warp_transpose_reduce(sq, lane);
+                    atomicAdd(&s_stats[c * 32 + lane], s1);
+                    atomicAdd(&s_stats[BLOCK_N + c * 32 + lane], s2);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        if (p.stats != nullptr && blockIdx.x < num_tiles) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+            const int n_tile = blockIdx.x % p.num_n_tiles;   // fixed per CTA (grid % num_n_tiles == 0)
+            for (int i = threadIdx.x - 128; i < BLOCK_N; i += 128) {
+                const int col = n_tile * BLOCK_N + i;
+                if (col < p.N) {
+                    atomicAdd(p.stats + col, s_stats[i]);
+                    atomicAdd(p.stats + p.N + col, s_stats[BLOCK_N + i]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int NSPLIT>
+static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+    using Cfg = GemmCfg<BLOCK_N, NSPLIT>;
+    auto kern = gemm_fwd_kernel<BLOCK_N, NSPLIT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GDRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    int grid = tiles < num_sms() ? tiles : num_sms();
+    grid -= grid % p.num_n_tiles;  // every CTA keeps one n_tile => per-CTA BatchNorm partial sums
+    if (grid <= 0) grid = p.num_n_tiles;
+    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(p);
+    GDRN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+static int dispatch_gemm(const GemmParams& p, int block_n, int nsplit, cudaStream_t stream) {
+    if (nsplit == 1) {
+        if (block_n == 256) return launch_gemm<256, 1>(p, stream);
+        if (block_n == 128) return launch_gemm<128, 1>(p, stream);
+        if (block_n == 64) return launch_gemm<64, 1>(p, stream);
+    } else if (nsplit == 3) {
+        if (block_n == 128) return launch_gemm<128, 3>(p, stream);
+        if (block_n == 64) return launch_gemm<64, 3>(p, stream);
+    }
+    return set_error(GDRN_ERR_ARG, "gemm: unsupported block_n=%d nsplit=%d", block_n, nsplit);
+}
+
+static int pick_block_n(int n_pad, int nsplit) {
+    if (nsplit == 1 && n_pad % 256 == 0) return 256;
+    if (n_pad % 128 == 0) return 128;
+    if (n_pad % 64 == 0) return 64;
+    return -1;
+}
+
+}  // namespace gdrn
+
+using namespace gdrn;
+
+extern "C" int gdrn_conv_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, void* y_hi,
+                             void* y_lo, float* y_f32, const float* bias, float* stats, int N, int H, int W, int Cin,
+                             int Cout, int Cout_pad, int KH, int KW, int stride, int pad, int ldc, int act, int nsplit,
+                             void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (nsplit != 1 && nsplit != 3) return set_error(GDRN_ERR_ARG, "conv_fwd: nsplit must be 1 or 3");
+    if (nsplit == 3 && (x_lo == nullptr || w_lo == nullptr)) return set_error(GDRN_ERR_ARG, "conv_fwd: lo planes missing");
+    if (Cin % 64 != 0) return set_error(GDRN_ERR_ARG, "conv_fwd: Cin=%d must be a multiple of 64", Cin);
+    if (stride != 1 && stride != 2) return set_error(GDRN_ERR_ARG, "conv_fwd: stride must be 1 or 2");
+    if (H % stride || W % stride) return set_error(GDRN_ERR_ARG, "conv_fwd: H, W must be divisible by stride");
+    if (ldc % 8 != 0 || ldc < Cout) return set_error(GDRN_ERR_ARG, "conv_fwd: bad ldc=%d", ldc);
+    const int Ho = H / stride, Wo = W / stride;
+    if (Wo > 128 || 128 % Wo != 0) return set_error(GDRN_ERR_ARG, "conv_fwd: unsupported output width %d", Wo);
+    int TH = 128 / Wo;
+    if (TH > Ho) TH = Ho;
+    const int TN = 128 / (Wo * TH);
+    if (Ho % TH != 0) return set_error(GDRN_ERR_ARG, "conv_fwd: Ho=%d not divisible by tile rows %d", Ho, TH);
+    const int block_n = pick_block_n(Cout_pad, nsplit);
+    if (block_n < 0) return set_error(GDRN_ERR_ARG, "conv_fwd: Cout_pad=%d must be a multiple of 64", Cout_pad);
+
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    const int npl = nsplit == 1 ? 1 : 2;
+    const void* xs[2] = {x_hi, x_lo};
+    const void* ws[2] = {w_hi, w_lo};
+    const int K = KH * KW * Cin;
+    for (int pl = 0; pl < npl; ++pl) {
+        const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(xs[pl]);
+        for (int ph = 0; ph < (stride == 2 ? 4 : 1); ++ph) {
+            const int phh = ph >> 1, phw = ph & 1;
+            uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
+            uint64_t strides[3] = {(uint64_t)stride * Cin * 2, (uint64_t)stride * W * Cin * 2, (uint64_t)H * W * Cin * 2};
+            uint32_t box[4] = {64, (uint32_t)Wo, (uint32_t)TH, (uint32_t)TN};
+            const void* base = xb + ((size_t)phh * W + phw) * Cin;
+            if (make_tmap(&p.tmA[pl][ph], base, 4, dims, strides, box)) return GDRN_ERR_CUDA;
+        }
+        uint64_t wdims[2] = {(uint64_t)K, (uint64_t)Cout_pad};
+        uint64_t wstr[1] = {(uint64_t)K * 2};
+        uint32_t wbox[2] = {64, (uint32_t)block_n};
+        if (make_tmap(&p.tmB[pl], ws[pl], 2, wdims, wstr, wbox)) return GDRN_ERR_CUDA;
+    }
+    p.mode = 1;
+    p.M = N * Ho * Wo;
+    p.N = Cout;
+    p.num_m_tiles = (p.M + 127) / 128;
+    p.num_n_tiles = Cout_pad / block_n;
+    p.cchunks = Cin / 64;
+    p.num_kb = KH * KW * p.cchunks;
+    p.KW = KW;
+    p.pad = pad;
+    p.stride = stride;
+    p.TH = TH;
+    p.TN = TN;
+    p.tiles_per_img = (TN == 1) ? Ho / TH : 0;
+    p.out_hi = y_hi;
+    p.out_lo = y_lo;
+    p.out_f32 = y_f32;
+    p.ldc = ldc;
+    p.bias = bias;
+    p.act = act;
+    p.stats = stats;
+    return dispatch_gemm(p, block_n, nsplit, stream);
+}
+
+extern "C" int gdrn_gemm_fwd(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, void* y_hi,
+                             void* y_lo, float* y_f32, const float* bias, float* stats, int M, int N, int N_pad, int K,
+                             int ldc, int act, int nsplit, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (nsplit != 1 && nsplit != 3) return set_error(GDRN_ERR_ARG, "gemm_fwd: nsplit must be 1 or 3");
+    if (nsplit == 3 && (a_lo == nullptr || w_lo == nullptr)) return set_error(GDRN_ERR_ARG, "gemm_fwd: lo planes missing");
+    if (K % 64 != 0) return set_error(GDRN_ERR_ARG, "gemm_fwd: K=%d must be a multiple of 64", K);
+    if (ldc % 8 != 0 || ldc < N) return set_error(GDRN_ERR_ARG, "gemm_fwd: bad ldc=%d", ldc);
+    const int block_n = pick_block_n(N_pad, nsplit);
+    if (block_n < 0) return set_error(GDRN_ERR_ARG, "gemm_fwd: N_pad=%d must be a multiple of 64", N_pad);
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    const int npl = nsplit == 1 ? 1 : 2;
+    const void* as[2] = {a_hi, a_lo};
+    const void* ws[2] = {w_hi, w_lo};
+    for (int pl = 0; pl < npl; ++pl) {
+        uint64_t adims[2] = {(uint64_t)K, (uint64_t)M};
+        uint64_t astr[1] = {(uint64_t)K * 2};
+        uint32_t abox[2] = {64, 128};
+        if (make_tmap(&p.tmA[pl][0], as[pl], 2, adims, astr, abox)) return GDRN_ERR_CUDA;
+        uint64_t wdims[2] = {(uint64_t)K, (uint64_t)N_pad};
+        uint32_t wbox[2] = {64, (uint32_t)block_n};
+        if (make_tmap(&p.tmB[pl], ws[pl], 2, wdims, astr, wbox)) return GDRN_ERR_CUDA;
+    }
+    p.mode = 0;
+    p.M = M;
+    p.N = N;
+    p.num_m_tiles = (M + 127) / 128;
+    p.num_n_tiles = N_pad / block_n;
+    p.num_kb = K / 64;
+    p.out_hi = y_hi;
+    p.out_lo = y_lo;
+    p.out_f32 = y_f32;
+    p.ldc = ldc;
+    p.bias = bias;
+    p.act = act;
+    p.stats = stats;
+    return dispatch_gemm(p, block_n, nsplit, stream);
+}

@@ -1,0 +1,365 @@
+// tcgen05 weight-gradient kernel (sm_100a):  dW[co][tap][ci] = sum_p dY[p][co] * X[p (+) tap][ci]
+//
+// Both operands are "MN-major" for the tensor core: the reduction index is the pixel p, which is the
+// SLOW index of the NHWC tensors, so the 64-pixel x 64-channel TMA boxes land in shared memory as
+// [k = pixel][64 channels = 128 B] rows -- exactly the MN-major 128B-swizzled canonical layout
+// (descriptor a_major = b_major = 1, SBO = 1024 B between 8-pixel groups, LBO = 8192 B between
+// 64-channel chunks).  No transposes are ever materialised.
+//
+//   * A tile = dY  [64 pixels][128 co]      (2 boxes of 64 channels, plain 2-D view [P][Cout])
+//   * B tile = X   [64 pixels][<=256 ci]    (<=4 boxes; for a conv the box is the tap-shifted 4-D
+//                  window of the NHWC input, zero-filled outside the image; stride-2 convs read the
+//                  four parity sub-lattices, like the forward kernel)
+//   * one CTA = (co tile, ci tile, tap, K-split); fp32 accumulator in TMEM (<=256 columns);
+//     partial results go to a [ksplit][Cout][taps*Cin] fp32 workspace that the unpack kernel
+//     (pack.cu) reduces and transposes into the reference's OIHW gradient layout.
+// Backward call sites replaced: autograd wgrad of every nn.Conv2d / ConvTranspose2d / nn.Linear in
+// reference resnet_backbone.py, cdpn_rot_head_region.py, conv_pnp_net.py (cuDNN/cuBLAS today).
+#include "gdrn_internal.h"
+#include "ptx.cuh"
+
+namespace gdrn {
+
+struct WgradParams {
+    CUtensorMap tmA[2];     // dY  [plane]
+    CUtensorMap tmB[2][4];  // X   [plane][phase]
+    int mode;               // 0 = 2-D GEMM (B = [P][Ntot]), 1 = conv
+    int Mvalid;             // Cout
+    int Ntot;               // Cin (conv) or total B columns (gemm)
+    int num_m_tiles, num_n_tiles, taps, ksplit;
+    int kb_total;           // number of 64-pixel blocks
+    int KW, pad, stride;
+    int blocks_per_img, THk, TNk;
+    float* ws;              // [ksplit][num_m_tiles*128][taps*Ntot]
+};
+
+constexpr int kWgStageA = 2 * 8192;
+
+template <int N_TILE, int NSPLIT>
+struct WgradCfg {
+    static constexpr int NPL = (NSPLIT == 1) ? 1 : 2;
+    static constexpr int NCH = N_TILE / 64;
+    static constexpr int A_BYTES = kWgStageA;
+    static constexpr int B_BYTES = NCH * 8192;
+    static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
+    static constexpr int STAGES_RAW = (227 * 1024 - 2048) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048;
+    static constexpr int TMEM_COLS = N_TILE < 32 ? 32 : N_TILE;
+    static_assert(STAGES >= 2, "pipeline too shallow");
+};
+
+template <int N_TILE, int NSPLIT>
+__global__ void __launch_bounds__(192, 1) gemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
+    using Cfg = WgradCfg<N_TILE, NSPLIT>;
+    constexpr int NPL = Cfg::NPL;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int NCH = Cfg::NCH;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* done_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // work item decode: m fastest, then n, tap, ksplit
+    int item = blockIdx.x;
+    const int m_tile = item % p.num_m_tiles;
+    item /= p.num_m_tiles;
+    const int n_tile = item % p.num_n_tiles;
+    item /= p.num_n_tiles;
+    const int tap = item % p.taps;
+    const int ks = item / p.taps;
+    const int kb_per = (p.kb_total + p.ksplit - 1) / p.ksplit;
+    const int kb_begin = ks * kb_per;
+    const int kb_end = min(p.kb_total, kb_begin + kb_per);
+    const int nkb = kb_end - kb_begin;  // may be <= 0 for a ragged last split: then we store zeros
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0 && nkb > 0) {
+            int dh = 0, dw = 0, map = 0;
+            if (p.mode == 1) {
+                const int r = tap / p.KW;
+                const int s = tap - r * p.KW;
+                dh = r - p.pad;
+                dw = s - p.pad;
+                if (p.stride == 2) {
+                    map = ((dh & 1) << 1) | (dw & 1);
+                    dh >>= 1;
+                    dw >>= 1;
+                }
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = kb_begin; kb < kb_end; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+#pragma unroll
+                for (int pl = 0; pl < NPL; ++pl) {
+                    uint8_t* a_dst = st + pl * Cfg::A_BYTES;
+                    tma_load_2d(a_dst, &p.tmA[pl], &full_bar[stage], m_tile * 128, kb * 64);
+                    tma_load_2d(a_dst + 8192, &p.tmA[pl], &full_bar[stage], m_tile * 128 + 64, kb * 64);
+                    uint8_t* b_dst = st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES;
+                    if (p.mode == 1) {
+                        int n0, h0;
+                        if (p.TNk == 1) {
+                            n0 = kb / p.blocks_per_img;
+                            h0 = (kb - n0 * p.blocks_per_img) * p.THk;
+                        } else {
+                            n0 = kb * p.TNk;
+                            h0 = 0;
+                        }
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c)
+                            tma_load_4d(b_dst + c * 8192, &p.tmB[pl][map], &full_bar[stage], n_tile * N_TILE + c * 64, dw,
+                                        h0 + dh, n0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c)
+                            tma_load_2d(b_dst + c * 8192, &p.tmB[pl][0], &full_bar[stage], n_tile * N_TILE + c * 64,
+                                        kb * 64);
+                    }
+                }
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && nkb > 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, N_TILE, 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                const uint32_t b_hi = a_hi + NPL * Cfg::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {  // 16 pixels (= 16 rows of 128 B) per MMA
+                    const uint64_t da = make_smem_desc(a_hi + k * 2048, 8192, 1024);
+                    const uint64_t db = make_smem_desc(b_hi + k * 2048, 8192, 1024);
+                    umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    if (NSPLIT == 3) {
+                        const uint64_t da_lo = make_smem_desc(a_hi + Cfg::A_BYTES + k * 2048, 8192, 1024);
+                        const uint64_t db_lo = make_smem_desc(b_hi + Cfg::B_BYTES + k * 2048, 8192, 1024);
+                        umma_bf16(tmem_base, da, db_lo, idesc, 1u);
+                        umma_bf16(tmem_base, da_lo, db, idesc, 1u);
+                    }
+                }
+                umma_commit(&empty_bar[stage]);
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            umma_commit(done_bar);
+        }
+    } else {
+        // epilogue warps 2..5: TMEM lane quadrant = warp % 4
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int co = m_tile * 128 + row;
+        if (nkb > 0) {
+            mbar_wait(done_bar, 0);
+            tc_fence_after();
+        }
+        const size_t ld = (size_t)p.taps * p.Ntot;
+        float* dst_row = p.ws + ((size_t)ks * p.num_m_tiles * 128 + co) * ld + (size_t)tap * p.Ntot + n_tile * N_TILE;
+#pragma unroll 1
+        for (int c = 0; c < N_TILE / 32; ++c) {
+            uint32_t raw[32];
+            if (nkb > 0) {
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, raw);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) raw[j] = 0u;
+            }
+            if (n_tile * N_TILE + c * 32 < p.Ntot) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<uint4*>(dst_row + c * 32 + j) = make_uint4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+template <int N_TILE, int NSPLIT>
+static int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
+    using Cfg = WgradCfg<N_TILE, NSPLIT>;
+    auto kern = gemm_wgrad_kernel<N_TILE, NSPLIT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GDRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int grid = p.num_m_tiles * p.num_n_tiles * p.taps * p.ksplit;
+    kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(p);
+    GDRN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+static int dispatch_wgrad(const WgradParams& p, int n_tile, int nsplit, cudaStream_t stream) {
+    if (nsplit == 1) {
+        if (n_tile == 256) return launch_wgrad<256, 1>(p, stream);
+        if (n_tile == 128) return launch_wgrad<128, 1>(p, stream);
+        if (n_tile == 64) return launch_wgrad<64, 1>(p, stream);
+    } else if (nsplit == 3) {
+        if (n_tile == 128) return launch_wgrad<128, 3>(p, stream);
+        if (n_tile == 64) return launch_wgrad<64, 3>(p, stream);
+    }
+    return set_error(GDRN_ERR_ARG, "wgrad: unsupported n_tile=%d nsplit=%d", n_tile, nsplit);
+}
+
+static int pick_n_tile(int ntot, int nsplit) {
+    if (nsplit == 1 && ntot % 256 == 0) return 256;
+    if (ntot % 128 == 0) return 128;
+    if (ntot % 64 == 0) return 64;
+    return -1;
+}
+
+}  // namespace gdrn
+
+using namespace gdrn;
+
+// Workspace size query + K-split choice shared by conv and gemm wgrad.
+static int choose_ksplit(int base_items, int kb_total, int requested) {
+    if (requested > 0) return requested < kb_total ? requested : kb_total;
+    int ks = (2 * num_sms() + base_items - 1) / base_items;  // aim at ~2 waves of work items
+    int max_ks = kb_total / 4;                               // keep >= 4 k-blocks per split
+    if (max_ks < 1) max_ks = 1;
+    if (ks > max_ks) ks = max_ks;
+    if (ks < 1) ks = 1;
+    return ks;
+}
+
+extern "C" int gdrn_conv_wgrad(const void* dy_hi, const void* dy_lo, const void* x_hi, const void* x_lo, float* ws,
+                               long ws_floats, long* ws_need_out, int* ksplit_out, int N, int H, int W, int Cin, int Cout, int KH, int KW,
+                               int stride, int pad, int ksplit, int nsplit, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (nsplit != 1 && nsplit != 3) return set_error(GDRN_ERR_ARG, "conv_wgrad: nsplit must be 1 or 3");
+    if (nsplit == 3 && (dy_lo == nullptr || x_lo == nullptr)) return set_error(GDRN_ERR_ARG, "conv_wgrad: lo planes missing");
+    if (Cin % 64 || Cout % 64) return set_error(GDRN_ERR_ARG, "conv_wgrad: Cin/Cout must be multiples of 64");
+    if (stride != 1 && stride != 2) return set_error(GDRN_ERR_ARG, "conv_wgrad: stride must be 1 or 2");
+    const int Ho = H / stride, Wo = W / stride;
+    if (Wo > 64 || 64 % Wo != 0) return set_error(GDRN_ERR_ARG, "conv_wgrad: unsupported output width %d", Wo);
+    int THk = 64 / Wo;
+    if (THk > Ho) THk = Ho;
+    const int TNk = 64 / (Wo * THk);
+    if (Ho % THk != 0 || (N % TNk) != 0) return set_error(GDRN_ERR_ARG, "conv_wgrad: shape not tileable by 64 pixels");
+    const long P = (long)N * Ho * Wo;
+    if (P % 64 != 0) return set_error(GDRN_ERR_ARG, "conv_wgrad: N*Ho*Wo must be a multiple of 64");
+    const int n_tile = pick_n_tile(Cin, nsplit);
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.mode = 1;
+    p.Mvalid = Cout;
+    p.Ntot = Cin;
+    p.num_m_tiles = (Cout + 127) / 128;
+    p.num_n_tiles = Cin / n_tile;
+    p.taps = KH * KW;
+    p.kb_total = (int)(P / 64);
+    p.ksplit = choose_ksplit(p.num_m_tiles * p.num_n_tiles * p.taps, p.kb_total, ksplit);
+    p.KW = KW;
+    p.pad = pad;
+    p.stride = stride;
+    p.THk = THk;
+    p.TNk = TNk;
+    p.blocks_per_img = (TNk == 1) ? Ho / THk : 0;
+    p.ws = ws;
+    if (ksplit_out) *ksplit_out = p.ksplit;
+    const long need = (long)p.ksplit * p.num_m_tiles * 128 * p.taps * Cin;
+    if (ws_need_out) *ws_need_out = need;
+    if (ws == nullptr) return 0;  // size query only
+    if (ws_floats < need) return set_error(GDRN_ERR_ARG, "conv_wgrad: workspace too small (%ld < %ld floats)", ws_floats, need);
+    const int npl = nsplit == 1 ? 1 : 2;
+    const void* dys[2] = {dy_hi, dy_lo};
+    const void* xs[2] = {x_hi, x_lo};
+    for (int pl = 0; pl < npl; ++pl) {
+        uint64_t adims[2] = {(uint64_t)Cout, (uint64_t)P};
+        uint64_t astr[1] = {(uint64_t)Cout * 2};
+        uint32_t abox[2] = {64, 64};
+        if (make_tmap(&p.tmA[pl], dys[pl], 2, adims, astr, abox)) return GDRN_ERR_CUDA;
+        const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(xs[pl]);
+        for (int ph = 0; ph < (stride == 2 ? 4 : 1); ++ph) {
+            const int phh = ph >> 1, phw = ph & 1;
+            uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
+            uint64_t strides[3] = {(uint64_t)stride * Cin * 2, (uint64_t)stride * W * Cin * 2, (uint64_t)H * W * Cin * 2};
+            uint32_t box[4] = {64, (uint32_t)Wo, (uint32_t)THk, (uint32_t)TNk};
+            if (make_tmap(&p.tmB[pl][ph], xb + ((size_t)phh * W + phw) * Cin, 4, dims, strides, box)) return GDRN_ERR_CUDA;
+        }
+    }
+    return dispatch_wgrad(p, n_tile, nsplit, stream);
+}
+
+// dW[M][Ntot] = sum_p A[p][M] * B[p][Ntot]   (A = dY [P][M], B = X [P][Ntot]; P zero-padded to 64 by TMA)
+extern "C" int gdrn_gemm_wgrad(const void* dy_hi, const void* dy_lo, const void* x_hi, const void* x_lo, float* ws,
+                               long ws_floats, long* ws_need_out, int* ksplit_out, long P, int M, int Ntot, int ksplit, int nsplit,
+                               void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (nsplit != 1 && nsplit != 3) return set_error(GDRN_ERR_ARG, "gemm_wgrad: nsplit must be 1 or 3");
+    if (nsplit == 3 && (dy_lo == nullptr || x_lo == nullptr)) return set_error(GDRN_ERR_ARG, "gemm_wgrad: lo planes missing");
+    if (M % 8 || Ntot % 64) return set_error(GDRN_ERR_ARG, "gemm_wgrad: M %% 8 and Ntot %% 64 required");
+    const int n_tile = pick_n_tile(Ntot, nsplit);
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.mode = 0;
+    p.Mvalid = M;
+    p.Ntot = Ntot;
+    p.num_m_tiles = (M + 127) / 128;
+    p.num_n_tiles = Ntot / n_tile;
+    p.taps = 1;
+    p.kb_total = (int)((P + 63) / 64);
+    p.ksplit = choose_ksplit(p.num_m_tiles * p.num_n_tiles, p.kb_total, ksplit);
+    p.ws = ws;
+    if (ksplit_out) *ksplit_out = p.ksplit;
+    const long need = (long)p.ksplit * p.num_m_tiles * 128 * Ntot;
+    if (ws_need_out) *ws_need_out = need;
+    if (ws == nullptr) return 0;
+    if (ws_floats < need) return set_error(GDRN_ERR_ARG, "gemm_wgrad: workspace too small (%ld < %ld floats)", ws_floats, need);
+    const int npl = nsplit == 1 ? 1 : 2;
+    const void* dys[2] = {dy_hi, dy_lo};
+    const void* xs[2] = {x_hi, x_lo};
+    for (int pl = 0; pl < npl; ++pl) {
+        uint64_t adims[2] = {(uint64_t)M, (uint64_t)P};
+        uint64_t astr[1] = {(uint64_t)M * 2};
+        uint32_t abox[2] = {64, 64};
+        if (make_tmap(&p.tmA[pl], dys[pl], 2, adims, astr, abox)) return GDRN_ERR_CUDA;
+        uint64_t bdims[2] = {(uint64_t)Ntot, (uint64_t)P};
+        uint64_t bstr[1] = {(uint64_t)Ntot * 2};
+        if (make_tmap(&p.tmB[pl][0], xs[pl], 2, bdims, bstr, abox)) return GDRN_ERR_CUDA;
+    }
+    return dispatch_wgrad(p, n_tile, nsplit, stream);
+}

@@ -1,0 +1,142 @@
+// Layout conversion kernels (HBM-bound, coalesced on the destination side):
+//   * fp32 OIHW / IOHW / [N][K] parameters  ->  K-major bf16 (hi, lo) GEMM operands
+//   * fp32 split-K weight-gradient workspace ->  fp32 gradients in the reference's parameter layout
+//   * NCHW fp32 input crops                 ->  im2col matrix of the 7x7/2 stem (bf16 hi, lo)
+// Parameter layouts follow the reference state_dict: Conv2d OIHW, ConvTranspose2d
+// IOHW (cdpn_rot_head_region.py:82-91), Linear [out][in] with fc1's input flattened from NCHW
+// (conv_pnp_net.py:145).
+#include "gdrn_internal.h"
+#include "ptx.cuh"
+
+namespace gdrn {
+
+// dst[o][tap * ipad + i] = src[o*so + i*si + r'*sr + s'*ss],  zero for i >= I, o >= O or columns >= taps*ipad
+__global__ void pack_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst_hi,
+                                   __nv_bfloat16* __restrict__ dst_lo, int O, int I, int KH, int KW, int opad, int ipad,
+                                   int krow, long so, long si, long sr, long ss, int flip) {
+    const long total = (long)opad * krow;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int o = (int)(idx / krow);
+        const int col = (int)(idx - (long)o * krow);
+        const int tap = col / ipad;
+        const int i = col - tap * ipad;
+        float v = 0.f;
+        if (o < O && i < I && tap < KH * KW) {
+            int r = tap / KW, s = tap - (tap / KW) * KW;
+            if (flip) {
+                r = KH - 1 - r;
+                s = KW - 1 - s;
+            }
+            v = __ldg(src + o * so + i * si + r * sr + s * ss);
+        }
+        const float h = bf16_round(v);
+        dst_hi[idx] = __float2bfloat16(h);
+        if (dst_lo != nullptr) dst_lo[idx] = __float2bfloat16(v - h);
+    }
+}
+
+// grad[o*so + i*si + r'*sr + s'*ss] (+)= sum_ks ws[ks][o][tap*ipad + i]
+__global__ void unpack_wgrad_kernel(const float* __restrict__ ws, float* __restrict__ grad, int O, int I, int KH, int KW,
+                                    int ipad, int ksplit, long ks_stride, long so, long si, long sr, long ss, int flip,
+                                    int accumulate) {
+    const int taps = KH * KW;
+    const long krow = (long)taps * ipad;
+    const long total = (long)O * taps * I;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        // read-coalesced order: (o, tap, i)
+        const int i = (int)(idx % I);
+        const long t2 = idx / I;
+        const int tap = (int)(t2 % taps);
+        const int o = (int)(t2 / taps);
+        const float* src = ws + (long)o * krow + (long)tap * ipad + i;
+        float acc = 0.f;
+        for (int ks = 0; ks < ksplit; ++ks) acc += src[ks * ks_stride];
+        int r = tap / KW, s = tap - (tap / KW) * KW;
+        if (flip) {
+            r = KH - 1 - r;
+            s = KW - 1 - s;
+        }
+        float* d = grad + o * so + i * si + r * sr + s * ss;
+        *d = accumulate ? (*d + acc) : acc;
+    }
+}
+
+// Stem im2col: x NCHW fp32 [B,3,H,W] -> A[(b,oh,ow)][192] with k = (r*7+s)*3 + c (147 valid), conv 7x7 s2 p3.
+// One thread produces 8 consecutive k (one 16-byte store per plane).
+__global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a_hi,
+                                   __nv_bfloat16* __restrict__ a_lo, int B, int H, int W) {
+    const int Ho = H / 2, Wo = W / 2;
+    const long total = (long)B * Ho * Wo * 24;  // 24 groups of 8 columns
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int g = (int)(idx % 24);
+        const long pix = idx / 24;
+        const int ow = (int)(pix % Wo);
+        const int oh = (int)((pix / Wo) % Ho);
+        const int b = (int)(pix / ((long)Wo * Ho));
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = g * 8 + j;
+            float val = 0.f;
+            if (k < 147) {
+                const int tap = k / 3, c = k - tap * 3;
+                const int r = tap / 7, s = tap - r * 7;
+                const int ih = oh * 2 + r - 3, iw = ow * 2 + s - 3;
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = __ldg(x + (((long)b * 3 + c) * H + ih) * W + iw);
+            }
+            v[j] = val;
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            lo[j] = pack_bf16x2(v[2 * j] - __uint_as_float(hi[j] << 16), v[2 * j + 1] - __uint_as_float(hi[j] & 0xffff0000u));
+        }
+        reinterpret_cast<uint4*>(a_hi)[idx] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (a_lo != nullptr) reinterpret_cast<uint4*>(a_lo)[idx] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+static inline int grid_for(long total, int block) {
+    long g = (total + block - 1) / block;
+    const long cap = (long)num_sms() * 16;
+    return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+}  // namespace gdrn
+
+using namespace gdrn;
+
+extern "C" int gdrn_pack_weight(const float* src, void* dst_hi, void* dst_lo, int O, int I, int KH, int KW, int opad,
+                                int ipad, int krow, long so, long si, long sr, long ss, int flip, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (krow < KH * KW * ipad || opad < O || ipad < I) return set_error(GDRN_ERR_ARG, "pack_weight: bad padding");
+    const long total = (long)opad * krow;
+    pack_weight_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, (__nv_bfloat16*)dst_hi, (__nv_bfloat16*)dst_lo, O, I,
+                                                                KH, KW, opad, ipad, krow, so, si, sr, ss, flip);
+    GDRN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int gdrn_unpack_wgrad(const float* ws, float* grad, int O, int I, int KH, int KW, int ipad, int ksplit,
+                                 long ks_stride, long so, long si, long sr, long ss, int flip, int accumulate,
+                                 void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    const long total = (long)O * KH * KW * I;
+    unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, stream>>>(ws, grad, O, I, KH, KW, ipad, ksplit, ks_stride, so, si,
+                                                                 sr, ss, flip, accumulate);
+    GDRN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int gdrn_stem_im2col(const float* x, void* a_hi, void* a_lo, int B, int H, int W, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (H % 2 || W % 2) return set_error(GDRN_ERR_ARG, "stem_im2col: H, W must be even");
+    const long total = (long)B * (H / 2) * (W / 2) * 24;
+    stem_im2col_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo, B, H, W);
+    GDRN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}

@@ -1,0 +1,122 @@
+/* libgdrn_b200.so -- C ABI of the B200-native GDR-Net hot path.
+ *
+ * Drop-in boundary: the reference has no native code on this path -- every op below is
+ * today an ATen / cuDNN / cuBLAS call issued by the `nn.Module`s cited per function.  The in-repo
+ * precedent for a C-ABI extension is core/csrc/fps/src/ext.h:1-14 (raw pointers, caller-owned
+ * buffers).  Conventions:
+ *
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates everything);
+ *     kernels never allocate, no pointer is retained after return;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - return 0 on success, <0 on error (GDRN_ERR_ARG / GDRN_ERR_CUDA) with a thread-local message
+ *     from gdrn_last_error(); nothing throws across the ABI; entry points are re-entrant;
+ *   - activations are NHWC bf16 "planar pairs": a hi plane and an optional lo plane with
+ *     value = hi + lo.  nsplit = 1: bf16 tensor-core math on the hi plane only (lo pointers NULL);
+ *     nsplit = 3: fp32-faithful mode, three tcgen05 MMAs per k-step (hi*hi + hi*lo + lo*hi).
+ */
+#ifndef GDRN_B200_H
+#define GDRN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDRN_OK 0
+#define GDRN_ERR_ARG (-1)
+#define GDRN_ERR_CUDA (-2)
+
+const char* gdrn_last_error(void);
+long gdrn_launch_count(void); /* kernels launched by this library since load */
+int gdrn_abi_version(void);
+
+/* ---- tcgen05 implicit-GEMM convolution, forward (and dgrad with flipped/transposed weights) ------------
+ * replaces nn.Conv2d / nn.ConvTranspose2d forward: resnet_backbone.py:21-49,69-76 (torchvision BasicBlock),
+ * cdpn_rot_head_region.py:82-135, conv_pnp_net.py:76-80.
+ * x [N,H,W,Cin] (Cin % 64 == 0), w packed [Cout_pad][KH*KW*Cin] (gdrn_pack_weight), outputs row-major
+ * [N*Ho*Wo][ldc]: bf16 planes (y_hi/y_lo) and/or fp32 (y_f32).  bias[Cout] / act (1 = LeakyReLU 0.1) optional.
+ * stats (optional) [2][Cout] fp32 += per-channel sum and sum of squares of the fp32 accumulators
+ * (BatchNorm batch statistics, reference get_norm("BN") layers). */
+int gdrn_conv_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, void* y_hi, void* y_lo,
+                  float* y_f32, const float* bias, float* stats, int N, int H, int W, int Cin, int Cout, int Cout_pad,
+                  int KH, int KW, int stride, int pad, int ldc, int act, int nsplit, void* stream);
+
+/* ---- plain GEMM  y[M][N] = a[M][K] * w[N_pad][K]^T (+bias, act); replaces nn.Linear (conv_pnp_net.py:89-92,
+ * 152-156), the 7x7 stem over its im2col matrix (resnet_backbone.py:69) and their dgrads. */
+int gdrn_gemm_fwd(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, void* y_hi, void* y_lo,
+                  float* y_f32, const float* bias, float* stats, int M, int N, int N_pad, int K, int ldc, int act,
+                  int nsplit, void* stream);
+
+/* ---- weight gradients (autograd wgrad of the layers above).  Split-K partials are written to the fp32
+ * workspace ws [ksplit][ceil(Cout/128)*128][KH*KW*Cin]; reduce with gdrn_unpack_wgrad.
+ * ws == NULL: size query only (*ws_need_out floats, *ksplit_out). ksplit <= 0: automatic. */
+int gdrn_conv_wgrad(const void* dy_hi, const void* dy_lo, const void* x_hi, const void* x_lo, float* ws, long ws_floats,
+                    long* ws_need_out, int* ksplit_out, int N, int H, int W, int Cin, int Cout, int KH, int KW,
+                    int stride, int pad, int ksplit, int nsplit, void* stream);
+int gdrn_gemm_wgrad(const void* dy_hi, const void* dy_lo, const void* x_hi, const void* x_lo, float* ws, long ws_floats,
+                    long* ws_need_out, int* ksplit_out, long P, int M, int Ntot, int ksplit, int nsplit, void* stream);
+
+/* ---- parameter layout conversion.  dst[o][tap*ipad + i] = src[o*so + i*si + r*sr + s*ss] (r,s flipped if flip).
+ * Source layouts: Conv2d OIHW, ConvTranspose2d IOHW, Linear [out][in] (state_dict of the reference). */
+int gdrn_pack_weight(const float* src, void* dst_hi, void* dst_lo, int O, int I, int KH, int KW, int opad, int ipad,
+                     int krow, long so, long si, long sr, long ss, int flip, void* stream);
+int gdrn_unpack_wgrad(const float* ws, float* grad, int O, int I, int KH, int KW, int ipad, int ksplit, long ks_stride,
+                      long so, long si, long sr, long ss, int flip, int accumulate, void* stream);
+/* im2col of the 7x7/2 stem: x NCHW fp32 [B,3,H,W] -> [B*H/2*W/2][192] bf16 planes, k = (r*7+s)*3 + c */
+int gdrn_stem_im2col(const float* x, void* a_hi, void* a_lo, int B, int H, int W, void* stream);
+
+/* ---- BatchNorm2d(eps, momentum) train/eval (+ReLU, + residual add) and backward -- detectron2/torch
+ * BatchNorm2d via core/utils/layer_utils.py:17-39; torchvision BasicBlock residual. */
+int gdrn_bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                     float* scale, float* shift, float* mean_out, float* invstd_out, int C, float count, float eps,
+                     float momentum, int train, void* stream);
+int gdrn_bn_act(const void* x_hi, const void* x_lo, const void* r_hi, const void* r_lo, void* y_hi, void* y_lo,
+                const float* scale, const float* shift, long rows, int C, int relu, void* stream);
+int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_hi, const void* gb_lo, const void* y_hi,
+                const void* u_hi, const void* u_lo, const float* mean, const float* invstd, const float* gamma,
+                float* sums, void* du_hi, void* du_lo, void* gout_hi, void* gout_lo, float* dgamma, float* dbeta,
+                long rows, int C, int train, void* stream);
+
+/* ---- MaxPool2d(3,2,1) resnet_backbone.py:72; UpsamplingBilinear2d(x2) cdpn_rot_head_region.py:102;
+ * zero insertion (stride-2 transposed convs); GroupNorm(32)+ReLU conv_pnp_net.py:76-80 */
+int gdrn_maxpool_fwd(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int B, int H, int W, int C, void* stream);
+int gdrn_maxpool_bwd(const void* x_hi, const void* x_lo, const void* g_hi, const void* g_lo, void* dx_hi, void* dx_lo,
+                     int B, int H, int W, int C, void* stream);
+int gdrn_upsample2x_fwd(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int B, int H, int W, int C, void* stream);
+int gdrn_upsample2x_bwd(const void* g_hi, const void* g_lo, void* dx_hi, void* dx_lo, int B, int H, int W, int C, void* stream);
+int gdrn_zero_insert(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int B, int H, int W, int C, int mode,
+                     void* stream);
+int gdrn_gn_relu_fwd(const void* u_hi, const void* u_lo, void* y_hi, void* y_lo, const float* gamma, const float* beta,
+                     float* stats, int B, int HW, int C, int G, float eps, void* stream);
+int gdrn_gn_relu_bwd(const void* g_hi, const void* g_lo, const void* y_hi, const void* u_hi, const void* u_lo,
+                     const float* gamma, const float* stats, void* du_hi, void* du_lo, float* dgamma, float* dbeta, int B,
+                     int HW, int C, int G, void* stream);
+int gdrn_add2(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* o_hi, void* o_lo, long n,
+              void* stream);
+int gdrn_f32_to_planes(const float* x, void* y_hi, void* y_lo, long n, void* stream);
+int gdrn_planes_to_f32(const void* x_hi, const void* x_lo, float* y, long n, void* stream);
+
+/* ---- geometry glue + per-pixel losses (GDRN.py:156-169, 341-400; conv_pnp_net.py:120-125).
+ * logits fp32 [B*HW][72] (0 mask | 1..3 xyz | 4 bg | 5..68 regions), Patch-PnP input bf16 [B*HW][128]. */
+int gdrn_head_glue_fwd(const float* logits, const float* coord2d, const float* extents, void* out_hi, void* out_lo, int B,
+                       int HW, void* stream);
+int gdrn_pixel_loss_fwd(const float* logits, const float* gt_xyz, const float* m_visib, const float* m_trunc,
+                        const long long* labels, double* sums, int B, int HW, void* stream);
+int gdrn_head_bwd(const float* logits, const float* gt_xyz, const float* m_visib, const float* m_trunc,
+                  const long long* labels, const double* sums, const float* gw, const void* din_hi, const void* din_lo,
+                  const float* extents, void* out_hi, void* out_lo, int B, int HW, void* stream);
+
+/* ---- rot6d -> R, SITE translation, allo -> ego, PM loss (+ closest symmetric GT), centroid / z losses, re/te
+ * (rot_reps.py:34-49, pose_from_pred_centroid_z.py:144-227, utils.py:208-236, pm_loss.py:82-114,
+ *  pose_utils.py:430-482, GDRN.py:439-471, model_utils.py:40-52).  pred [B][ld_pred]: cols 0..5 rot6d, 6..8 t. */
+int gdrn_pose_loss(const float* pred, int ld_pred, const float* cams, const float* centers, const float* whs,
+                   const float* ratios, const float* extents, const float* points, const float* gt_rot,
+                   const float* gt_trans, const float* gt_ratio, const float* syms, const int* sym_off, const float* gw,
+                   float* out_rot, float* out_trans, double* sums, float* vis, void* dy_hi, void* dy_lo, int B, int n_pts,
+                   int do_loss, void* stream);
+int gdrn_loss_finalize(const double* pix_sums, const double* pose_sums, const float* vis, float* losses, float* vis_out,
+                       int B, int HW, int n_pts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDRN_B200_H */

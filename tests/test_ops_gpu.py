@@ -1,0 +1,300 @@
+"""GPU: every C-ABI op against a plain PyTorch fp32 reference of the same op (TF32 disabled).
+nsplit = 1 (bf16 operands): the reference is evaluated on bf16-rounded operands, so only fp32
+accumulation order differs.  nsplit = 3 (hi/lo planes): the reference is full fp32."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _setup():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def _ops():
+    from gdr_net_b200 import ops
+
+    return ops
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def _operand(x, planes):
+    """What the kernel effectively multiplies: bf16-rounded for planes=1, ~fp32 for planes=2."""
+    return x.bfloat16().float() if planes == 1 else x
+
+
+def _nhwc(x_nchw, planes):
+    ops = _ops()
+    return ops.PT.from_float(x_nchw.permute(0, 2, 3, 1).contiguous(), planes)
+
+
+TOL = {1: 5e-5, 2: 5e-5}
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 128, 192), (300, 256, 512), (64, 1024, 8192), (2, 9, 256), (1000, 69, 256)])
+def test_gemm_fwd(planes, M, N, K):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    bias = torch.randn(N, device="cuda", generator=g)
+    A = ops.PT.from_float(a, planes)
+    Wp = ops.pack_linear(w, planes)
+    ldc = (N + 7) // 8 * 8
+    out32 = torch.full((M, ldc), float("nan"), device="cuda")
+    out = ops.gemm_fwd(A, Wp, N, out_f32=out32, bias=bias, act=1, ldc=ldc)
+    torch.cuda.synchronize()
+    ref = F.leaky_relu(_operand(a, planes) @ _operand(w, planes).t() + bias, 0.1)
+    assert _rel(out32[:, :N], ref) < TOL[planes]
+    got = out.float()[:, :N]
+    assert _rel(got, ref) < (5e-3 if planes == 1 else 3e-5)  # planes=1: output rounded to bf16
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k, stride, pad
+    (2, 64, 64, 64, 64, 3, 1, 1),
+    (2, 32, 32, 128, 128, 3, 1, 1),
+    (2, 16, 16, 256, 256, 3, 1, 1),
+    (4, 8, 8, 512, 512, 3, 1, 1),
+    (3, 8, 8, 128, 128, 3, 1, 1),     # odd batch: half-empty last tile
+    (2, 64, 64, 64, 128, 3, 2, 1),
+    (2, 64, 64, 64, 128, 1, 2, 0),
+    (2, 16, 16, 256, 512, 3, 2, 1),
+    (2, 64, 64, 128, 128, 3, 2, 1),   # Patch-PnP first conv shape (Cin padded 69 -> 128)
+    (2, 64, 64, 256, 69, 1, 1, 0),    # head output conv (N tail, bias)
+]
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd(planes, case):
+    ops = _ops()
+    N, H, W, Cin, Cout, k, stride, pad = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case))
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / math.sqrt(Cin * k * k)
+    X = _nhwc(x, planes)
+    Wp = ops.pack_conv_fwd(w, planes)
+    ldc = (Cout + 7) // 8 * 8
+    Ho, Wo = H // stride, W // stride
+    out32 = torch.zeros(N, Ho, Wo, ldc, device="cuda")
+    stats = torch.zeros(2, Cout, device="cuda")
+    bias = torch.randn(Cout, device="cuda", generator=g) if Cout == 69 else None
+    ops.conv_fwd(X, Wp, Cout, k, k, stride, pad, out_f32=out32, stats=stats if bias is None else None, bias=bias, ldc=ldc,
+                 want_planes=False)
+    torch.cuda.synchronize()
+    ref = F.conv2d(_operand(x, planes), _operand(w, planes), bias, stride=stride, padding=pad).permute(0, 2, 3, 1)
+    assert _rel(out32[..., :Cout], ref) < TOL[planes]
+    if bias is None:
+        s1 = ref.reshape(-1, Cout).sum(0)
+        s2 = (ref.reshape(-1, Cout) ** 2).sum(0)
+        assert float((stats[0] - s1).abs().max()) < 1e-3 * float(s2.max().sqrt()) + 1e-3
+        assert _rel(stats[1], s2) < 1e-4
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+def test_conv_dgrad_as_conv(planes):
+    """dX of a 3x3 s1 conv = conv(dY, flipped/transposed weights); of a s2 conv = same over zero-inserted dY."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for (N, H, Cin, Cout, stride) in [(2, 32, 64, 128, 1), (2, 32, 64, 128, 2)]:
+        x = torch.randn(N, Cin, H, H, device="cuda", generator=g, requires_grad=True)
+        w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / 24
+        w_eff = _operand(w, planes)
+        y = F.conv2d(x, w_eff, None, stride=stride, padding=1)
+        dy = torch.randn_like(y)
+        (gx,) = torch.autograd.grad(y, x, _operand(dy, planes))
+        DY = _nhwc(dy, planes)
+        if stride == 2:
+            DY = ops.zero_insert(DY)
+        Wd = ops.pack_conv_dgrad(w, planes)
+        out32 = torch.zeros(N, H, H, Cin, device="cuda")
+        ops.conv_fwd(DY, Wd, Cin, 3, 3, 1, 1, out_f32=out32, want_planes=False)
+        torch.cuda.synchronize()
+        assert _rel(out32, gx.permute(0, 2, 3, 1)) < TOL[planes]
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+def test_deconv_fwd_and_dgrad(planes):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    N, Cin, Cout = 2, 512, 256
+    x = torch.randn(N, Cin, 8, 8, device="cuda", generator=g, requires_grad=True)
+    wt = torch.randn(Cin, Cout, 3, 3, device="cuda", generator=g) / 34
+    y = F.conv_transpose2d(_operand(x, planes), _operand(wt, planes), None, stride=2, padding=1, output_padding=1)
+    Z = ops.zero_insert(_nhwc(x.detach(), planes))
+    out32 = torch.zeros(N, 16, 16, Cout, device="cuda")
+    ops.conv_fwd(Z, ops.pack_deconv_fwd(wt, planes), Cout, 3, 3, 1, 1, out_f32=out32, want_planes=False)
+    torch.cuda.synchronize()
+    assert _rel(out32, y.permute(0, 2, 3, 1)) < TOL[planes]
+    dy = torch.randn_like(y)
+    y2 = F.conv_transpose2d(x, _operand(wt, planes), None, stride=2, padding=1, output_padding=1)
+    (gx,) = torch.autograd.grad(y2, x, _operand(dy, planes))
+    dx32 = torch.zeros(N, 8, 8, Cin, device="cuda")
+    ops.conv_fwd(_nhwc(dy, planes), ops.pack_deconv_dgrad(wt, planes), Cin, 3, 3, 2, 1, out_f32=dx32, want_planes=False)
+    torch.cuda.synchronize()
+    assert _rel(dx32, gx.permute(0, 2, 3, 1)) < TOL[planes]
+
+
+WGRAD_CASES = [(2, 64, 64, 64, 64, 3, 1, 1), (2, 32, 32, 128, 128, 3, 1, 1), (4, 16, 16, 256, 256, 3, 1, 1),
+               (8, 8, 8, 512, 512, 3, 1, 1), (2, 64, 64, 64, 128, 3, 2, 1), (2, 64, 64, 64, 128, 1, 2, 0),
+               (2, 64, 64, 256, 128, 1, 1, 0)]
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_conv_wgrad(planes, case):
+    ops = _ops()
+    N, H, W, Cin, Cout, k, stride, pad = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case) + 1)
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g)
+    w = torch.zeros(Cout, Cin, k, k, device="cuda", requires_grad=True)
+    y = F.conv2d(_operand(x, planes), w, None, stride=stride, padding=pad)
+    dy = torch.randn_like(y) / 8
+    (gw,) = torch.autograd.grad(y, w, _operand(dy, planes))
+    ws = ops.Workspace()
+    buf, ks, ks_stride = ops.conv_wgrad(_nhwc(dy, planes), _nhwc(x, planes), ws, Cout, k, k, stride, pad)
+    grad = torch.zeros_like(w)
+    ops.unpack_wgrad(buf, grad, Cout, Cin, k, k, Cin, ks, ks_stride, Cin * k * k, k * k, k, 1)
+    torch.cuda.synchronize()
+    assert _rel(grad, gw) < 5e-5
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+@pytest.mark.parametrize("P,M,N", [(64, 1024, 8192), (2, 64, 256), (4096, 64, 192), (300, 256, 1024)])
+def test_gemm_wgrad(planes, P, M, N):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(P + M + N)
+    dy = torch.randn(P, M, device="cuda", generator=g)
+    x = torch.randn(P, N, device="cuda", generator=g)
+    ws = ops.Workspace()
+    buf, ks, ks_stride = ops.gemm_wgrad(ops.PT.from_float(dy, planes), ops.PT.from_float(x, planes), ws)
+    grad = torch.zeros(M, N, device="cuda")
+    ops.unpack_wgrad(buf, grad, M, N, 1, 1, N, ks, ks_stride, N, 1, 0, 0)
+    torch.cuda.synchronize()
+    ref = _operand(dy, planes).t() @ _operand(x, planes)
+    assert _rel(grad, ref) < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+@pytest.mark.parametrize("planes", [1, 2])
+def test_pack_roundtrip_and_planes(planes):
+    ops = _ops()
+    x = torch.randn(4, 64, 64, device="cuda")
+    P = ops.PT.from_float(x, planes)
+    tol = 4e-3 if planes == 1 else 2e-5
+    assert _rel(P.to_float(), x) < tol and _rel(P.float(), x) < tol
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+@pytest.mark.parametrize("C_", [64, 256])
+def test_bn_train_fwd_bwd(planes, C_):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(C_)
+    N, H = 3, 16
+    u = torch.randn(N, C_, H, H, device="cuda", generator=g) * 2 + 0.5
+    res = torch.randn(N, C_, H, H, device="cuda", generator=g)
+    gamma = torch.rand(C_, device="cuda", generator=g) + 0.5
+    beta = torch.randn(C_, device="cuda", generator=g) * 0.1
+    rm, rv = torch.zeros(C_, device="cuda"), torch.ones(C_, device="cuda")
+    U, R = _nhwc(u, planes), _nhwc(res, planes)
+    uf, rf = U.float().permute(0, 3, 1, 2).clone().requires_grad_(True), R.float().permute(0, 3, 1, 2)
+    gam = gamma.clone().requires_grad_(True)
+    bet = beta.clone().requires_grad_(True)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    y_ref = F.relu(F.batch_norm(uf, rm_ref, rv_ref, gam, bet, True, 0.1, 1e-5) + rf)
+    # our path: stats straight from the tensor (the conv epilogue normally provides them)
+    flat = U.float().reshape(-1, C_)
+    stats = torch.stack([flat.sum(0), (flat * flat).sum(0)]).contiguous()
+    scale, shift, mean, invstd = (torch.empty(C_, device="cuda") for _ in range(4))
+    ops.bn_finalize(stats, gamma, beta, rm, rv, scale, shift, mean, invstd, C_, flat.shape[0], 1e-5, 0.1, True)
+    Y = ops.bn_act(U, scale, shift, True, res=R)
+    torch.cuda.synchronize()
+    tol = 8e-3 if planes == 1 else 3e-5
+    assert _rel(Y.float().permute(0, 3, 1, 2), y_ref) < tol
+    assert _rel(rm, rm_ref) < 1e-5 and _rel(rv, rv_ref) < 1e-5
+    gy = torch.randn_like(y_ref)
+    GY = _nhwc(gy, planes)
+    gu_ref, gg_ref, gb_ref = torch.autograd.grad(y_ref, (uf, gam, bet), GY.float().permute(0, 3, 1, 2))
+    sums = torch.zeros(2, C_, device="cuda")
+    dgamma, dbeta = torch.zeros(C_, device="cuda"), torch.zeros(C_, device="cuda")
+    DU, GOUT = ops.bn_bwd(GY, None, Y, U, mean, invstd, gamma, sums, dgamma, dbeta, True, want_gout=True)
+    torch.cuda.synchronize()
+    tolb = 2e-2 if planes == 1 else 1e-4
+    assert _rel(DU.float().permute(0, 3, 1, 2), gu_ref) < tolb
+    assert _rel(dgamma, gg_ref) < tolb and _rel(dbeta, gb_ref) < tolb
+    mask = (Y.float() > 0).float()
+    assert _rel(GOUT.float(), GY.float() * mask) < (8e-3 if planes == 1 else 3e-5)
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+def test_maxpool_upsample_zero_insert(planes):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(2, 64, 32, 32, device="cuda", generator=g)
+    X = _nhwc(x, planes)
+    xf = X.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    tol = 8e-3 if planes == 1 else 3e-5
+    # maxpool
+    y_ref = F.max_pool2d(xf, 3, 2, 1)
+    Y = ops.maxpool_fwd(X)
+    assert _rel(Y.float().permute(0, 3, 1, 2), y_ref) < tol
+    gy = torch.randn_like(y_ref)
+    GY = _nhwc(gy, planes)
+    (gx_ref,) = torch.autograd.grad(y_ref, xf, GY.float().permute(0, 3, 1, 2))
+    GX = ops.maxpool_bwd(X, GY)
+    assert _rel(GX.float().permute(0, 3, 1, 2), gx_ref) < tol
+    # bilinear x2, align_corners=True
+    xf2 = X.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    y_ref = F.interpolate(xf2, scale_factor=2, mode="bilinear", align_corners=True)
+    Y = ops.upsample2x_fwd(X)
+    assert _rel(Y.float().permute(0, 3, 1, 2), y_ref) < tol
+    gy = torch.randn_like(y_ref)
+    GY = _nhwc(gy, planes)
+    (gx_ref,) = torch.autograd.grad(y_ref, xf2, GY.float().permute(0, 3, 1, 2))
+    GX = ops.upsample2x_bwd(GY)
+    assert _rel(GX.float().permute(0, 3, 1, 2), gx_ref) < tol
+    # zero insertion and its transpose
+    Z = ops.zero_insert(X)
+    zf = Z.float()
+    assert torch.equal(zf[:, ::2, ::2], X.float()) and float(zf[:, 1::2].abs().max()) == 0 and float(zf[:, :, 1::2].abs().max()) == 0
+    assert torch.equal(ops.extract_even(Z).float(), X.float())
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+def test_groupnorm_relu(planes):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, H = 3, 16
+    u = torch.randn(B, 128, H, H, device="cuda", generator=g) * 1.5 + 0.3
+    gamma = (torch.rand(128, device="cuda", generator=g) + 0.5).requires_grad_(True)
+    beta = (torch.randn(128, device="cuda", generator=g) * 0.1).requires_grad_(True)
+    U = _nhwc(u, planes)
+    uf = U.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    y_ref = F.relu(F.group_norm(uf, 32, gamma, beta, 1e-5))
+    stats = torch.zeros(B, 32, 2, device="cuda")
+    Y = ops.gn_relu_fwd(U, gamma.detach(), beta.detach(), stats)
+    tol = 8e-3 if planes == 1 else 3e-5
+    assert _rel(Y.float().permute(0, 3, 1, 2), y_ref) < tol
+    gy = torch.randn_like(y_ref)
+    GY = _nhwc(gy, planes)
+    gu_ref, gg_ref, gb_ref = torch.autograd.grad(y_ref, (uf, gamma, beta), GY.float().permute(0, 3, 1, 2))
+    dgamma, dbeta = torch.zeros(128, device="cuda"), torch.zeros(128, device="cuda")
+    DU = ops.gn_relu_bwd(GY, Y, U, gamma.detach(), stats, dgamma, dbeta)
+    torch.cuda.synchronize()
+    tolb = 2e-2 if planes == 1 else 1e-4
+    assert _rel(DU.float().permute(0, 3, 1, 2), gu_ref) < tolb
+    assert _rel(dgamma, gg_ref) < tolb and _rel(dbeta, gb_ref) < tolb
