@@ -623,6 +623,48 @@ __global__ void planes_to_f32_kernel(const bf16* __restrict__ x_hi, const bf16* 
     }
 }
 
+
+// out[c] (+)= sum_rows x[r][c]   (bias gradients).  Block = 256 threads = (ld/8) column groups x row lanes.
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo,
+                                                     float* __restrict__ out, long rows, int ld) {
+    const int cg = ld / 8;
+    const int rpb = 256 / cg;
+    const int g = threadIdx.x % cg, rl = threadIdx.x / cg;
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    if (rl < rpb) {
+        for (long r = (long)blockIdx.x * rpb + rl; r < rows; r += (long)gridDim.x * rpb) {
+            float v[8];
+            load8(x_hi, x_lo, r * cg + g, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] += v[j];
+        }
+    }
+    __shared__ float red[256][8 + 1];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = s[j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < ld; c += 256) {
+        float a = 0.f;
+        for (int q = 0; q < rpb; ++q) a += red[q * cg + c / 8][c % 8];
+        atomicAdd(out + c, a);
+    }
+}
+
+// LeakyReLU(0.1) backward through the saved OUTPUT y (sign(y) == sign(pre-activation)): g *= y > 0 ? 1 : 0.1
+__global__ void leaky_bwd_kernel(const bf16* __restrict__ g_hi, const bf16* __restrict__ g_lo, const bf16* __restrict__ y_hi,
+                                 bf16* __restrict__ o_hi, bf16* __restrict__ o_lo, long n8) {
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n8; idx += (long)gridDim.x * blockDim.x) {
+        float g[8], y[8];
+        load8(g_hi, g_lo, idx, g);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(y_hi) + idx), y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = y[j] > 0.f ? g[j] : 0.1f * g[j];
+        store8(o_hi, o_lo, idx, g);
+    }
+}
+
 }  // namespace gdrn
 
 using namespace gdrn;
@@ -694,7 +736,7 @@ extern "C" int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_
                            float* dbeta, long rows, int C, int train, void* stream_) {
     STREAM;
     if (C % 64 || C > 512) return set_error(GDRN_ERR_ARG, "bn_bwd: unsupported C=%d", C);
-    if (train) {
+    {  // the reductions also provide dgamma / dbeta when BN runs on frozen (eval) statistics
         GDRN_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream));
         const int rpb = kBnBwdThreads / (C / 8);
         long blocks = (rows + rpb - 1) / rpb;
@@ -742,5 +784,24 @@ extern "C" int gdrn_f32_to_planes(const float* x, void* y_hi, void* y_lo, long n
 extern "C" int gdrn_planes_to_f32(const void* x_hi, const void* x_lo, float* y, long n, void* stream_) {
     STREAM;
     planes_to_f32_kernel<<<ew_grid(n / 8, 256), 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), y, n / 8);
+    LAUNCH_DONE();
+}
+
+extern "C" int gdrn_colsum(const void* x_hi, const void* x_lo, float* out, long rows, int ld, void* stream_) {
+    STREAM;
+    if (ld % 8 || ld / 8 > 256 || 256 % (ld / 8)) return set_error(GDRN_ERR_ARG, "colsum: unsupported ld=%d", ld);
+    GDRN_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * ld, stream));
+    const int rpb = 256 / (ld / 8);
+    long blocks = (rows + rpb - 1) / rpb;
+    const long cap = (long)num_sms() * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    colsum_kernel<<<(int)blocks, 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), out, rows, ld);
+    LAUNCH_DONE();
+}
+extern "C" int gdrn_leaky_bwd(const void* g_hi, const void* g_lo, const void* y_hi, void* o_hi, void* o_lo, long n,
+                              void* stream_) {
+    STREAM;
+    leaky_bwd_kernel<<<ew_grid(n / 8, 256), 256, 0, stream>>>(CBF(g_hi), CBF(g_lo), CBF(y_hi), BF(o_hi), BF(o_lo), n / 8);
     LAUNCH_DONE();
 }

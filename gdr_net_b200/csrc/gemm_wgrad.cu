@@ -270,7 +270,7 @@ extern "C" int gdrn_conv_wgrad(const void* dy_hi, const void* dy_lo, const void*
                                int stride, int pad, int ksplit, int nsplit, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (nsplit != 1 && nsplit != 3) return set_error(GDRN_ERR_ARG, "conv_wgrad: nsplit must be 1 or 3");
-    if (nsplit == 3 && (dy_lo == nullptr || x_lo == nullptr)) return set_error(GDRN_ERR_ARG, "conv_wgrad: lo planes missing");
+    if (ws != nullptr && nsplit == 3 && (dy_lo == nullptr || x_lo == nullptr)) return set_error(GDRN_ERR_ARG, "conv_wgrad: lo planes missing");
     if (Cin % 64 || Cout % 64) return set_error(GDRN_ERR_ARG, "conv_wgrad: Cin/Cout must be multiples of 64");
     if (stride != 1 && stride != 2) return set_error(GDRN_ERR_ARG, "conv_wgrad: stride must be 1 or 2");
     const int Ho = H / stride, Wo = W / stride;
@@ -330,7 +330,7 @@ extern "C" int gdrn_gemm_wgrad(const void* dy_hi, const void* dy_lo, const void*
                                void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (nsplit != 1 && nsplit != 3) return set_error(GDRN_ERR_ARG, "gemm_wgrad: nsplit must be 1 or 3");
-    if (nsplit == 3 && (dy_lo == nullptr || x_lo == nullptr)) return set_error(GDRN_ERR_ARG, "gemm_wgrad: lo planes missing");
+    if (ws != nullptr && nsplit == 3 && (dy_lo == nullptr || x_lo == nullptr)) return set_error(GDRN_ERR_ARG, "gemm_wgrad: lo planes missing");
     if (M % 8 || Ntot % 64) return set_error(GDRN_ERR_ARG, "gemm_wgrad: M %% 8 and Ntot %% 64 required");
     const int n_tile = pick_n_tile(Ntot, nsplit);
     WgradParams p;

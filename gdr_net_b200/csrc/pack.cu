@@ -35,12 +35,12 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, __nv_bfloat16*
     }
 }
 
-// grad[o*so + i*si + r'*sr + s'*ss] (+)= sum_ks ws[ks][o][tap*ipad + i]
+// grad[o*so + i*si + r'*sr + s'*ss] (+)= sum_ks ws[ks][o*krow + tap*ipad + i]
 __global__ void unpack_wgrad_kernel(const float* __restrict__ ws, float* __restrict__ grad, int O, int I, int KH, int KW,
-                                    int ipad, int ksplit, long ks_stride, long so, long si, long sr, long ss, int flip,
+                                    int ipad, int krow_, int ksplit, long ks_stride, long so, long si, long sr, long ss, int flip,
                                     int accumulate) {
     const int taps = KH * KW;
-    const long krow = (long)taps * ipad;
+    const long krow = krow_;
     const long total = (long)O * taps * I;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         // read-coalesced order: (o, tap, i)
@@ -119,12 +119,12 @@ extern "C" int gdrn_pack_weight(const float* src, void* dst_hi, void* dst_lo, in
     return 0;
 }
 
-extern "C" int gdrn_unpack_wgrad(const float* ws, float* grad, int O, int I, int KH, int KW, int ipad, int ksplit,
+extern "C" int gdrn_unpack_wgrad(const float* ws, float* grad, int O, int I, int KH, int KW, int ipad, int krow, int ksplit,
                                  long ks_stride, long so, long si, long sr, long ss, int flip, int accumulate,
                                  void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     const long total = (long)O * KH * KW * I;
-    unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, stream>>>(ws, grad, O, I, KH, KW, ipad, ksplit, ks_stride, so, si,
+    unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, stream>>>(ws, grad, O, I, KH, KW, ipad, krow, ksplit, ks_stride, so, si,
                                                                  sr, ss, flip, accumulate);
     GDRN_CUDA_OK(cudaGetLastError());
     count_launch();

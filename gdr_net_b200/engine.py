@@ -1,0 +1,454 @@
+"""Forward / backward orchestration of the GDR-Net hot path over the C ABI (libgdrn_b200.so).
+
+Mirrors reference `GDRN.forward` (core/gdrn_modeling/models/GDRN.py:83-306), `gdrn_loss` (:308-521) and the
+autograd backward of both, but every tensor op is one of our sm_100a kernels (gdr_net_b200/csrc).  PyTorch is
+used for device memory, streams and the autograd/DDP boundary only.
+
+precision = "bf16"   : activations/gradients are bf16 NHWC tensors, one tcgen05 pass per k-step
+precision = "fp32x3" : (hi, lo) bf16 planes, three tcgen05 passes (fp32-faithful; the 1e-3 parity mode)
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .capi import C
+from .ops import PT, _stream
+
+LOSS_NAMES = ["loss_coor_x", "loss_coor_y", "loss_coor_z", "loss_mask", "loss_region", "loss_PM_R", "loss_centroid", "loss_z"]
+HEAD_CONVS = [(3, 4, False), (6, 7, False), (10, 11, True), (13, 14, False), (17, 18, True), (20, 21, False)]
+
+
+class _BN:
+    """Per-BatchNorm scratch: scale/shift (forward), mean/invstd (backward), statistic slices."""
+
+    def __init__(self, C_, dev):
+        self.scale = torch.empty(C_, device=dev)
+        self.shift = torch.empty(C_, device=dev)
+        self.mean = torch.empty(C_, device=dev)
+        self.invstd = torch.empty(C_, device=dev)
+        self.sums = torch.empty(2, C_, device=dev)
+        self.stats = None  # view into Engine.stats_all
+
+
+class Engine:
+    def __init__(self, model, precision: str = "bf16"):
+        assert precision in ("bf16", "fp32x3")
+        C.load()  # fail loudly if the CUDA library is missing
+        self.model = model
+        self.precision = precision
+        self.planes = 1 if precision == "bf16" else 2
+        self.dev = next(model.parameters()).device
+        if self.dev.type != "cuda":
+            raise RuntimeError("gdr_net_b200 engine needs CUDA parameters (model.to('cuda')); no CPU fallback exists")
+        self.ws = ops.Workspace(self.dev)
+        self.named_params = list(model.named_parameters())
+        self.bn: Dict[str, _BN] = {}
+        total = 0
+        self._bn_mods = {}
+        for name, m in model.named_modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                self.bn[name] = _BN(m.num_features, self.dev)
+                self._bn_mods[name] = m
+                total += 2 * m.num_features
+        self.stats_all = torch.zeros(total, device=self.dev)
+        off = 0
+        for name, m in self._bn_mods.items():
+            n = 2 * m.num_features
+            self.bn[name].stats = self.stats_all[off:off + n]
+            off += n
+        # flat gradient buffer (one NCCL-friendly allocation); per-parameter views
+        self.flat_grad = torch.zeros(sum(p.numel() for _, p in self.named_params), device=self.dev)
+        self.grads: Dict[str, torch.Tensor] = {}
+        off = 0
+        for name, p in self.named_params:
+            self.grads[name] = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.saved = None
+        self.wf: Dict[str, PT] = {}
+        self.wd: Dict[str, PT] = {}
+        self.grad_hook = None  # optional callable(engine) invoked at bucket boundaries during backward (DDP overlap)
+
+    # ------------------------------------------------------------------------------------------ weights
+    def _conv_modules(self):
+        m = self.model
+        out = [("backbone.conv1", m.backbone.conv1)]
+        for li in range(1, 5):
+            for bi, blk in enumerate(getattr(m.backbone, f"layer{li}")):
+                p = f"backbone.layer{li}.{bi}"
+                out.append((p + ".conv1", blk.conv1))
+                out.append((p + ".conv2", blk.conv2))
+                if blk.downsample is not None:
+                    out.append((p + ".downsample.0", blk.downsample[0]))
+        for ci, _bi, _u in HEAD_CONVS:
+            out.append((f"rot_head_net.features.{ci}", m.rot_head_net.features[ci]))
+        out.append(("rot_head_net.features.23", m.rot_head_net.features[23]))
+        for ci in (0, 3, 6):
+            out.append((f"pnp_net.features.{ci}", m.pnp_net.features[ci]))
+        return out
+
+    def prepare_weights(self, need_dgrad: bool):
+        """fp32 parameters -> K-major bf16 (hi, lo) GEMM operands (re-done every step: weights change)."""
+        m, pl = self.model, self.planes
+        wf, wd = self.wf, self.wd
+        for key, conv in self._conv_modules():
+            if key == "backbone.conv1":
+                continue  # the 7x7 stem is a GEMM over its im2col matrix (_pack_stem)
+            wf[key] = ops.pack_conv_fwd(conv.weight, pl, out=wf.get(key))
+            if need_dgrad:
+                wd[key] = ops.pack_conv_dgrad(conv.weight, pl, out=wd.get(key))
+        dc = m.rot_head_net.features[0]
+        wf["deconv"] = ops.pack_deconv_fwd(dc.weight, pl, out=wf.get("deconv"))
+        if need_dgrad:
+            wd["deconv"] = ops.pack_deconv_dgrad(dc.weight, pl, out=wd.get("deconv"))
+        pn = m.pnp_net
+        wf["fc1"] = ops.pack_linear(pn.fc1.weight, pl, out=wf.get("fc1"), nhwc_from=(128, 8, 8))
+        wf["fc2"] = ops.pack_linear(pn.fc2.weight, pl, out=wf.get("fc2"))
+        self.w_rt = torch.cat([pn.fc_r.weight, pn.fc_t.weight], 0).contiguous()
+        self.b_rt = torch.cat([pn.fc_r.bias, pn.fc_t.bias], 0).contiguous()
+        wf["fc_rt"] = ops.pack_linear(self.w_rt, pl, out=wf.get("fc_rt"))
+        if need_dgrad:
+            wd["fc1"] = ops.pack_linear(pn.fc1.weight, pl, out=wd.get("fc1"), nhwc_from=(128, 8, 8), transpose=True)
+            wd["fc2"] = ops.pack_linear(pn.fc2.weight, pl, out=wd.get("fc2"), transpose=True)
+            wd["fc_rt"] = ops.pack_linear(self.w_rt, pl, out=wd.get("fc_rt"), transpose=True)
+
+    def _pack_stem(self):
+        """7x7 stem weight [64][3][7][7] -> [64][192] with k = (r*7+s)*3 + c (matches gdrn_stem_im2col)."""
+        w = self.model.backbone.conv1.weight
+        out = self.wf.get("stem") or PT((64, 192), self.planes, device=self.dev)
+        C.gdrn_pack_weight(w.data_ptr(), out.hi_ptr, out.lo_ptr, 64, 3, 7, 7, 64, 3, 192, 147, 49, 7, 1, 0, _stream())
+        self.wf["stem"] = out
+
+    # ------------------------------------------------------------------------------------------ building blocks
+    def _bn_fwd(self, key: str, u: PT, relu: bool, train_bn: bool, res: Optional[PT] = None) -> PT:
+        mod, st = self._bn_mods[key], self.bn[key]
+        Cc = mod.num_features
+        count = u.numel() // Cc
+        mom = mod.momentum if mod.momentum is not None else 0.1
+        ops.bn_finalize(st.stats if train_bn else None, mod.weight, mod.bias, mod.running_mean, mod.running_var, st.scale,
+                        st.shift, st.mean, st.invstd, Cc, count, mod.eps, mom, train_bn)
+        if train_bn and mod.num_batches_tracked is not None:
+            mod.num_batches_tracked += 1
+        return ops.bn_act(u, st.scale, st.shift, relu, res=res)
+
+    def _conv_bn(self, x: PT, ckey: str, conv, bkey: str, relu: bool, train_bn: bool, res: Optional[PT] = None,
+                 wkey: Optional[str] = None, kind: str = "conv"):
+        st = self.bn[bkey]
+        stats = st.stats if train_bn else None
+        k, stride, pad = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        if kind == "deconv":
+            u = ops.conv_fwd(x, self.wf["deconv"], conv.out_channels, 3, 3, 1, 1, stats=stats)
+        else:
+            u = ops.conv_fwd(x, self.wf[wkey or ckey], conv.out_channels, k, k, stride, pad, stats=stats)
+        y = self._bn_fwd(bkey, u, relu, train_bn, res)
+        return u, y
+
+    # ------------------------------------------------------------------------------------------ forward
+    def run(self, x, *, roi_coord_2d, roi_cams, roi_centers, roi_whs, roi_extents, resize_ratios, gt_xyz=None,
+            gt_mask_trunc=None, gt_mask_visib=None, gt_region=None, gt_ego_rot=None, gt_points=None, sym_infos=None,
+            gt_trans=None, gt_trans_ratio=None, do_loss=False, train_bn=False, want_maps=False):
+        aux = dict(roi_coord_2d=roi_coord_2d, roi_cams=roi_cams, roi_centers=roi_centers, roi_whs=roi_whs,
+                   roi_extents=roi_extents, resize_ratios=resize_ratios, gt_xyz=gt_xyz, gt_mask_trunc=gt_mask_trunc,
+                   gt_mask_visib=gt_mask_visib, gt_region=gt_region, gt_ego_rot=gt_ego_rot, gt_points=gt_points,
+                   sym_infos=sym_infos, gt_trans=gt_trans, gt_trans_ratio=gt_trans_ratio)
+        for k_, v in aux.items():
+            if isinstance(v, torch.Tensor):
+                v = v.to(self.dev)
+                aux[k_] = (v if v.dtype == torch.long else v.float()).contiguous()
+        if roi_cams is not None and aux["roi_cams"].dim() == 2:
+            aux["roi_cams"] = aux["roi_cams"].unsqueeze(0).contiguous()
+        x = x.to(self.dev).float().contiguous()
+        if not do_loss:
+            with torch.no_grad():
+                return self.forward(x, aux, train_bn=train_bn, do_loss=False, want_maps=want_maps)
+        params = [p for _, p in self.named_params]
+        losses, vis = _GDRNFunction.apply(self, x, aux, train_bn, *params)
+        return dict(losses=losses, vis=vis)
+
+    def forward(self, x: torch.Tensor, aux: dict, train_bn: bool, do_loss: bool, want_maps: bool = False) -> dict:
+        m, pl, dev = self.model, self.planes, self.dev
+        B = x.shape[0]
+        assert x.shape[1:] == (3, 256, 256), x.shape
+        self.prepare_weights(need_dgrad=do_loss)
+        self._pack_stem()
+        if train_bn:
+            self.stats_all.zero_()
+        S = dict(B=B, train_bn=train_bn) if do_loss else None
+
+        # ---- a1: backbone (resnet_backbone.py:69-76)
+        a_col = PT((B * 128 * 128, 192), pl, device=dev)
+        C.gdrn_stem_im2col(x.data_ptr(), a_col.hi_ptr, a_col.lo_ptr, B, 256, 256, _stream())
+        st0 = self.bn["backbone.bn1"]
+        u0 = ops.gemm_fwd(a_col, self.wf["stem"], 64, stats=st0.stats if train_bn else None).view(B, 128, 128, 64)
+        a0 = self._bn_fwd("backbone.bn1", u0, True, train_bn)
+        cur = ops.maxpool_fwd(a0)
+        if S is not None:
+            S["stem"] = dict(a_col=a_col, u0=u0, a0=a0)
+            S["blocks"] = []
+        for li in range(1, 5):
+            for bi, blk in enumerate(getattr(m.backbone, f"layer{li}")):
+                p = f"backbone.layer{li}.{bi}"
+                u1, a1 = self._conv_bn(cur, p + ".conv1", blk.conv1, p + ".bn1", True, train_bn)
+                ud = None
+                if blk.downsample is not None:
+                    ud, idn = self._conv_bn(cur, p + ".downsample.0", blk.downsample[0], p + ".downsample.1", False, train_bn)
+                else:
+                    idn = cur
+                u2, out = self._conv_bn(a1, p + ".conv2", blk.conv2, p + ".bn2", True, train_bn, res=idn)
+                if S is not None:
+                    S["blocks"].append(dict(p=p, blk=blk, x_in=cur, u1=u1, a1=a1, u2=u2, out=out, ud=ud))
+                cur = out
+        feat = cur  # [B,8,8,512]
+
+        # ---- a2: geometry head (cdpn_rot_head_region.py:80-135)
+        hf = m.rot_head_net.features
+        z = ops.zero_insert(feat)
+        u, y = self._conv_bn(z, "deconv", hf[0], "rot_head_net.features.1", True, train_bn, kind="deconv")
+        if S is not None:
+            S["deconv"] = dict(z=z, u=u, y=y)
+            S["head"] = []
+        cur = y
+        for ci, bi, up in HEAD_CONVS:
+            if up:
+                cur = ops.upsample2x_fwd(cur)
+            u, y = self._conv_bn(cur, f"rot_head_net.features.{ci}", hf[ci], f"rot_head_net.features.{bi}", True, train_bn)
+            if S is not None:
+                S["head"].append(dict(ci=ci, bi=bi, up=up, x_in=cur, u=u, y=y))
+            cur = y
+        head_in = cur  # [B,64,64,256]
+        logits = torch.empty(B * 4096, 72, device=dev)
+        ops.conv_fwd(head_in, self.wf["rot_head_net.features.23"], 69, 1, 1, 1, 0, out_f32=logits, bias=hf[23].bias, ldc=72,
+                     want_planes=False)
+
+        # ---- a3 + a4: glue and Patch-PnP (GDRN.py:156-181, conv_pnp_net.py:111-157)
+        pnp_in = PT((B, 64, 64, 128), pl, device=dev)
+        C.gdrn_head_glue_fwd(logits.data_ptr(), aux["roi_coord_2d"].data_ptr(), aux["roi_extents"].data_ptr(), pnp_in.hi_ptr,
+                             pnp_in.lo_ptr, B, 4096, _stream())
+        pf = m.pnp_net.features
+        cur = pnp_in
+        pnp_saved = []
+        for ci, gi in ((0, 1), (3, 4), (6, 7)):
+            u = ops.conv_fwd(cur, self.wf[f"pnp_net.features.{ci}"], 128, 3, 3, 2, 1)
+            gstats = torch.empty(B, 32, 2, device=dev)
+            y = ops.gn_relu_fwd(u, pf[gi].weight, pf[gi].bias, gstats, G=pf[gi].num_groups, eps=pf[gi].eps)
+            pnp_saved.append(dict(ci=ci, gi=gi, x_in=cur, u=u, y=y, gstats=gstats))
+            cur = y
+        flat = cur.view(B, 8192)
+        pn = m.pnp_net
+        h1 = ops.gemm_fwd(flat, self.wf["fc1"], 1024, bias=pn.fc1.bias, act=1)
+        h2 = ops.gemm_fwd(h1, self.wf["fc2"], 256, bias=pn.fc2.bias, act=1)
+        pred = torch.zeros(B, 16, device=dev)  # cols 0..5 rot6d, 6..8 (centroid dx, dy, z)
+        ops.gemm_fwd(h2, self.wf["fc_rt"], 9, out_f32=pred, bias=self.b_rt, ldc=16, want_planes=False)
+
+        # ---- a5/a6 pose decode (+ a7..a10 losses)
+        out_rot = torch.empty(B, 3, 3, device=dev)
+        out_trans = torch.empty(B, 3, device=dev)
+        res = dict(rot=out_rot, trans=out_trans, pred=pred)
+        if not do_loss:
+            C.gdrn_pose_loss(pred.data_ptr(), 16, aux["roi_cams"].data_ptr(), aux["roi_centers"].data_ptr(),
+                             aux["roi_whs"].data_ptr(), aux["resize_ratios"].data_ptr(), aux["roi_extents"].data_ptr(), None,
+                             None, None, None, None, None, None, out_rot.data_ptr(), out_trans.data_ptr(), None, None, None,
+                             None, B, 0, 0, _stream())
+            if want_maps:
+                maps = logits.view(B, 64, 64, 72).permute(0, 3, 1, 2)
+                res.update(mask=maps[:, 0:1], coor_x=maps[:, 1:2], coor_y=maps[:, 2:3], coor_z=maps[:, 3:4], region=maps[:, 4:69])
+            res["logits"] = logits
+            return res
+
+        pix_sums = torch.empty(6, dtype=torch.float64, device=dev)
+        C.gdrn_pixel_loss_fwd(logits.data_ptr(), aux["gt_xyz"].data_ptr(), aux["gt_mask_visib"].data_ptr(),
+                              aux["gt_mask_trunc"].data_ptr(), aux["gt_region"].data_ptr(), pix_sums.data_ptr(), B, 4096, _stream())
+        S.update(logits=logits, pnp_in=pnp_in, pnp=pnp_saved, flat=flat, h1=h1, h2=h2, pred=pred, head_in=head_in,
+                 pix_sums=pix_sums, aux=aux)
+        self.saved = S
+        # the pose kernel needs the upstream loss gradients to emit dY9; forward calls it with unit weights and
+        # backward re-runs it (cheap: B CTAs) with the actual ones.
+        self._pose(S, gw=None)
+        losses = torch.empty(8, device=dev)
+        vis2 = torch.empty(2, device=dev)
+        n_pts = aux["gt_points"].shape[1]
+        C.gdrn_loss_finalize(pix_sums.data_ptr(), S["pose_sums"].data_ptr(), S["vis_ps"].data_ptr(), losses.data_ptr(),
+                             vis2.data_ptr(), B, 4096, n_pts, _stream())
+        vis = torch.cat([vis2, out_trans_first(S["out_trans"]), pred[0, 6:9], aux["gt_trans"][0], aux["gt_trans_ratio"][0]])
+        res.update(rot=S["out_rot"], trans=S["out_trans"], losses=losses, vis=vis)
+        return res
+
+    def _pose(self, S, gw):
+        aux, B, dev = S["aux"], S["B"], self.dev
+        if "out_rot" not in S:
+            S["out_rot"] = torch.empty(B, 3, 3, device=dev)
+            S["out_trans"] = torch.empty(B, 3, device=dev)
+            S["pose_sums"] = torch.empty(4, dtype=torch.float64, device=dev)
+            S["vis_ps"] = torch.empty(B, 2, device=dev)
+            S["dy9"] = PT((B, 64), self.planes, device=dev)
+            syms, offs = None, None
+            if aux.get("sym_infos") is not None:
+                mats, offs_l = [], [0]
+                for s in aux["sym_infos"]:
+                    if s is not None:
+                        s = torch.as_tensor(s, dtype=torch.float32).reshape(-1, 3, 3)
+                        mats.append(s)
+                        offs_l.append(offs_l[-1] + s.shape[0])
+                    else:
+                        offs_l.append(offs_l[-1])
+                if mats:
+                    syms = torch.cat(mats, 0).to(dev).contiguous()
+                    offs = torch.tensor(offs_l, dtype=torch.int32, device=dev)
+            S["syms"], S["sym_off"] = syms, offs
+        if gw is None:
+            gw = torch.ones(3, device=dev)
+        n_pts = aux["gt_points"].shape[1]
+        C.gdrn_pose_loss(S["pred"].data_ptr(), 16, aux["roi_cams"].data_ptr(), aux["roi_centers"].data_ptr(),
+                         aux["roi_whs"].data_ptr(), aux["resize_ratios"].data_ptr(), aux["roi_extents"].data_ptr(),
+                         aux["gt_points"].data_ptr(), aux["gt_ego_rot"].data_ptr(), aux["gt_trans"].data_ptr(),
+                         aux["gt_trans_ratio"].data_ptr(), ops.ptr(S["syms"]), ops.ptr(S["sym_off"]), gw.data_ptr(),
+                         S["out_rot"].data_ptr(), S["out_trans"].data_ptr(), S["pose_sums"].data_ptr(), S["vis_ps"].data_ptr(),
+                         S["dy9"].hi_ptr, S["dy9"].lo_ptr, B, n_pts, 1, _stream())
+
+    # ------------------------------------------------------------------------------------------ backward
+    def _wgrad_conv(self, du: PT, x_in: PT, conv, wname: str, ipad: Optional[int] = None):
+        O, I, k = conv.out_channels, conv.in_channels, conv.kernel_size[0]
+        buf, ks, kss = ops.conv_wgrad(du, x_in, self.ws, O, k, k, conv.stride[0], conv.padding[0])
+        ops.unpack_wgrad(buf, self.grads[wname], O, I, k, k, ipad or x_in.shape[-1], ks, kss, I * k * k, k * k, k, 1)
+
+    def _dgrad_conv(self, du: PT, conv, wkey: str) -> PT:
+        k, stride, pad = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        z = ops.zero_insert(du) if stride == 2 else du
+        return ops.conv_fwd(z, self.wd[wkey], conv.in_channels, k, k, 1, k - 1 - pad)
+
+    def _bn_bwd(self, bkey: str, ga: PT, gb: Optional[PT], y: Optional[PT], u: PT, want_gout=False):
+        mod, st = self._bn_mods[bkey], self.bn[bkey]
+        return ops.bn_bwd(ga, gb, y, u, st.mean, st.invstd, mod.weight, st.sums, self.grads[bkey + ".weight"],
+                          self.grads[bkey + ".bias"], self.saved["train_bn"], want_gout=want_gout)
+
+    def backward(self, grad_losses: torch.Tensor):
+        """grad_losses: [8] upstream gradients of LOSS_NAMES.  Fills self.grads (views of self.flat_grad)."""
+        S, m, dev = self.saved, self.model, self.dev
+        assert S is not None, "backward called without a do_loss forward"
+        B, aux, pn = S["B"], S["aux"], m.pnp_net
+        self.flat_grad.zero_()
+        gw = grad_losses.float().contiguous()
+        self._pose(S, gw=gw[5:8].contiguous())
+        dy9 = S["dy9"]
+        tmp = torch.empty(1024, device=dev)
+
+        # ---- FC stack (conv_pnp_net.py:152-156)
+        buf, ks, kss = ops.gemm_wgrad(dy9, S["h2"], self.ws)
+        ops.unpack_wgrad(buf, self.grads["pnp_net.fc_r.weight"], 6, 256, 1, 1, 256, ks, kss, 256, 1, 0, 0)
+        ops.unpack_wgrad(buf[6 * 256:], self.grads["pnp_net.fc_t.weight"], 3, 256, 1, 1, 256, ks, kss, 256, 1, 0, 0)
+        C.gdrn_colsum(dy9.hi_ptr, dy9.lo_ptr, tmp.data_ptr(), B, 64, _stream())
+        self.grads["pnp_net.fc_r.bias"].copy_(tmp[0:6])
+        self.grads["pnp_net.fc_t.bias"].copy_(tmp[6:9])
+        dh2 = ops.gemm_fwd(dy9, self.wd["fc_rt"], 256)
+        dz2 = self._leaky_bwd(dh2, S["h2"])
+        buf, ks, kss = ops.gemm_wgrad(dz2, S["h1"], self.ws)
+        ops.unpack_wgrad(buf, self.grads["pnp_net.fc2.weight"], 256, 1024, 1, 1, 1024, ks, kss, 1024, 1, 0, 0)
+        C.gdrn_colsum(dz2.hi_ptr, dz2.lo_ptr, self.grads["pnp_net.fc2.bias"].data_ptr(), B, 256, _stream())
+        dh1 = ops.gemm_fwd(dz2, self.wd["fc2"], 1024)
+        dz1 = self._leaky_bwd(dh1, S["h1"])
+        buf, ks, kss = ops.gemm_wgrad(dz1, S["flat"], self.ws)
+        ops.unpack_wgrad(buf, self.grads["pnp_net.fc1.weight"], 1024, 128, 8, 8, 128, ks, kss, 8192, 64, 8, 1)
+        C.gdrn_colsum(dz1.hi_ptr, dz1.lo_ptr, self.grads["pnp_net.fc1.bias"].data_ptr(), B, 1024, _stream())
+        g = ops.gemm_fwd(dz1, self.wd["fc1"], 8192).view(B, 8, 8, 128)
+
+        # ---- Patch-PnP convs (conv_pnp_net.py:76-80)
+        pf = pn.features
+        for L in reversed(S["pnp"]):
+            ci, gi = L["ci"], L["gi"]
+            du = ops.gn_relu_bwd(g, L["y"], L["u"], pf[gi].weight, L["gstats"], self.grads[f"pnp_net.features.{gi}.weight"],
+                                 self.grads[f"pnp_net.features.{gi}.bias"], G=pf[gi].num_groups)
+            self._wgrad_conv(du, L["x_in"], pf[ci], f"pnp_net.features.{ci}.weight")
+            g = self._dgrad_conv(du, pf[ci], f"pnp_net.features.{ci}")
+        d_pnp_in = g  # [B,64,64,128]
+        if self.grad_hook:
+            self.grad_hook(self, "pnp_net")
+
+        # ---- glue + per-pixel losses backward (one fused pass over the logits)
+        dlog = PT((B * 4096, 128), self.planes, device=dev)
+        C.gdrn_head_bwd(S["logits"].data_ptr(), aux["gt_xyz"].data_ptr(), aux["gt_mask_visib"].data_ptr(),
+                        aux["gt_mask_trunc"].data_ptr(), aux["gt_region"].data_ptr(), S["pix_sums"].data_ptr(), gw.data_ptr(),
+                        d_pnp_in.hi_ptr, d_pnp_in.lo_ptr, aux["roi_extents"].data_ptr(), dlog.hi_ptr, dlog.lo_ptr, B, 4096,
+                        _stream())
+        hf = m.rot_head_net.features
+        head_in = S["head_in"]
+        buf, ks, kss = ops.gemm_wgrad(dlog, head_in.view(B * 4096, 256), self.ws)
+        ops.unpack_wgrad(buf, self.grads["rot_head_net.features.23.weight"], 69, 256, 1, 1, 256, ks, kss, 256, 1, 0, 0)
+        tmp128 = torch.empty(128, device=dev)
+        C.gdrn_colsum(dlog.hi_ptr, dlog.lo_ptr, tmp128.data_ptr(), B * 4096, 128, _stream())
+        self.grads["rot_head_net.features.23.bias"].copy_(tmp128[:69])
+        g = ops.gemm_fwd(dlog, self.wd["rot_head_net.features.23"], 256).view(B, 64, 64, 256)
+
+        # ---- head convs (cdpn_rot_head_region.py:95-125)
+        for L in reversed(S["head"]):
+            ci, bi = L["ci"], L["bi"]
+            du, _ = self._bn_bwd(f"rot_head_net.features.{bi}", g, None, L["y"], L["u"])
+            self._wgrad_conv(du, L["x_in"], hf[ci], f"rot_head_net.features.{ci}.weight")
+            g = self._dgrad_conv(du, hf[ci], f"rot_head_net.features.{ci}")
+            if L["up"]:
+                g = ops.upsample2x_bwd(g)
+        D = S["deconv"]
+        du, _ = self._bn_bwd("rot_head_net.features.1", g, None, D["y"], D["u"])
+        buf, ks, kss = ops.conv_wgrad(du, D["z"], self.ws, 256, 3, 3, 1, 1)
+        # ConvTranspose2d weight is IOHW [512][256][3][3] with flipped taps relative to the equivalent conv
+        ops.unpack_wgrad(buf, self.grads["rot_head_net.features.0.weight"], 256, 512, 3, 3, 512, ks, kss, 9, 256 * 9, 3, 1, flip=1)
+        g = ops.conv_fwd(du, self.wd["deconv"], 512, 3, 3, 2, 1)  # [B,8,8,512]
+        if self.grad_hook:
+            self.grad_hook(self, "rot_head_net")
+
+        # ---- backbone (torchvision BasicBlock backward)
+        ga, gb = g, None
+        for Lb in reversed(S["blocks"]):
+            p, blk = Lb["p"], Lb["blk"]
+            du2, gout = self._bn_bwd(p + ".bn2", ga, gb, Lb["out"], Lb["u2"], want_gout=True)
+            self._wgrad_conv(du2, Lb["a1"], blk.conv2, p + ".conv2.weight")
+            da1 = self._dgrad_conv(du2, blk.conv2, p + ".conv2")
+            du1, _ = self._bn_bwd(p + ".bn1", da1, None, Lb["a1"], Lb["u1"])
+            self._wgrad_conv(du1, Lb["x_in"], blk.conv1, p + ".conv1.weight")
+            dx_main = self._dgrad_conv(du1, blk.conv1, p + ".conv1")
+            if blk.downsample is not None:
+                dud, _ = self._bn_bwd(p + ".downsample.1", gout, None, None, Lb["ud"])
+                self._wgrad_conv(dud, Lb["x_in"], blk.downsample[0], p + ".downsample.0.weight")
+                dx_ds = self._dgrad_conv(dud, blk.downsample[0], p + ".downsample.0")
+                ga, gb = dx_main, dx_ds
+            else:
+                ga, gb = dx_main, gout
+        g_pool = ops.add2(ga, gb)
+        St = S["stem"]
+        g_a0 = ops.maxpool_bwd(St["a0"], g_pool)
+        du0, _ = self._bn_bwd("backbone.bn1", g_a0, None, St["a0"], St["u0"])
+        buf, ks, kss = ops.gemm_wgrad(du0.view(B * 128 * 128, 64), St["a_col"], self.ws)
+        # ws rows [64][192] with k = (r*7+s)*3 + c  ->  OIHW [64][3][7][7]
+        ops.unpack_wgrad(buf, self.grads["backbone.conv1.weight"], 64, 3, 7, 7, 3, ks, kss, 147, 49, 7, 1, krow=192)
+        if self.grad_hook:
+            self.grad_hook(self, "backbone")
+        self.saved = None
+        return self.grads
+
+    def _leaky_bwd(self, g: PT, y: PT) -> PT:
+        out = ops.like(g)
+        C.gdrn_leaky_bwd(g.hi_ptr, g.lo_ptr, y.hi_ptr, out.hi_ptr, out.lo_ptr, g.numel(), _stream())
+        return out
+
+
+def out_trans_first(t):
+    return t[0]
+
+
+class _GDRNFunction(torch.autograd.Function):
+    """Autograd boundary: forward + losses and the hand-written backward are both ours; autograd only routes the
+    8 loss gradients in and the 148 parameter gradients out (so optimizers / DDP / GradScaler keep working)."""
+
+    @staticmethod
+    def forward(ctx, engine: Engine, x, aux, train_bn, *params):
+        res = engine.forward(x, aux, train_bn=train_bn, do_loss=True)
+        ctx.engine = engine
+        ctx.mark_non_differentiable(res["vis"])
+        return res["losses"], res["vis"]
+
+    @staticmethod
+    def backward(ctx, g_losses, _g_vis):
+        engine = ctx.engine
+        grads = engine.backward(g_losses)
+        return (None, None, None, None) + tuple(grads[name] for name, _ in engine.named_params)

@@ -235,9 +235,10 @@ def gemm_wgrad(dy: PT, x: PT, ws: Workspace, ksplit: int = 0):
     return buf, ks.value, _round_up(M, 128) * Ntot
 
 
-def unpack_wgrad(buf, grad: torch.Tensor, O, I, KH, KW, ipad, ksplit, ks_stride, so, si, sr, ss, flip=0, accumulate=0):
-    C.gdrn_unpack_wgrad(buf.data_ptr(), grad.data_ptr(), O, I, KH, KW, ipad, ksplit, ks_stride, so, si, sr, ss, flip, accumulate,
-                        _stream())
+def unpack_wgrad(buf, grad: torch.Tensor, O, I, KH, KW, ipad, ksplit, ks_stride, so, si, sr, ss, flip=0, accumulate=0, krow=None):
+    """krow: row length of the workspace (defaults to KH*KW*ipad)."""
+    C.gdrn_unpack_wgrad(buf.data_ptr(), grad.data_ptr(), O, I, KH, KW, ipad, krow or KH * KW * ipad, ksplit, ks_stride, so, si, sr,
+                        ss, flip, accumulate, _stream())
 
 
 # ---------------------------------------------------------------------------------------------

@@ -59,7 +59,7 @@ int gdrn_gemm_wgrad(const void* dy_hi, const void* dy_lo, const void* x_hi, cons
  * Source layouts: Conv2d OIHW, ConvTranspose2d IOHW, Linear [out][in] (state_dict of the reference). */
 int gdrn_pack_weight(const float* src, void* dst_hi, void* dst_lo, int O, int I, int KH, int KW, int opad, int ipad,
                      int krow, long so, long si, long sr, long ss, int flip, void* stream);
-int gdrn_unpack_wgrad(const float* ws, float* grad, int O, int I, int KH, int KW, int ipad, int ksplit, long ks_stride,
+int gdrn_unpack_wgrad(const float* ws, float* grad, int O, int I, int KH, int KW, int ipad, int krow, int ksplit, long ks_stride,
                       long so, long si, long sr, long ss, int flip, int accumulate, void* stream);
 /* im2col of the 7x7/2 stem: x NCHW fp32 [B,3,H,W] -> [B*H/2*W/2][192] bf16 planes, k = (r*7+s)*3 + c */
 int gdrn_stem_im2col(const float* x, void* a_hi, void* a_lo, int B, int H, int W, void* stream);
@@ -92,6 +92,9 @@ int gdrn_gn_relu_bwd(const void* g_hi, const void* g_lo, const void* y_hi, const
                      int HW, int C, int G, void* stream);
 int gdrn_add2(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* o_hi, void* o_lo, long n,
               void* stream);
+/* bias gradients (column sums of a [rows][ld] planar tensor) and LeakyReLU(0.1) backward (conv_pnp_net.py:93,152-153) */
+int gdrn_colsum(const void* x_hi, const void* x_lo, float* out, long rows, int ld, void* stream);
+int gdrn_leaky_bwd(const void* g_hi, const void* g_lo, const void* y_hi, void* o_hi, void* o_lo, long n, void* stream);
 int gdrn_f32_to_planes(const float* x, void* y_hi, void* y_lo, long n, void* stream);
 int gdrn_planes_to_f32(const void* x_hi, const void* x_lo, float* y, long n, void* stream);
 
