@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""Headline benchmark of the GDR-Net hot path (BASELINE.json configs[1]: ResNet-34 GDR-Net full fwd+bwd, batch 64 per GPU,
+256x256 synthetic crops, losses included), one process per GPU.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference algorithm on the host cores (CPU oracle), same metric
+
+One JSON line on stdout (rank 0).  `value` = crops/s of the whole job with inputs resident in HBM (device-timed, max over
+ranks); `e2e` = the same through the public module API with pinned host inputs (H2D copies + D2H loss read in the timed
+region); `roofline` = tensor-core fraction of the tcgen05 conv kernel family measured live with CUDA events;
+`cpu_baseline` = the CPU oracle timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "crops/sec (fwd+bwd, 256x256, bs64 per GPU)"
+FWD_BWD_GFLOP_PER_CROP = 68.16  # 34.08 GMAC of Conv/ConvT/Linear, x2
+BATCH_PER_GPU = 64
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_sustained=d.get("bf16_tflops_sustained", 1453.0), bf16_burst=d.get("bf16_tflops", 1718.7),
+                    hbm=d.get("hbm_gbs", 6571.6), source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_sustained=1400.0, bf16_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}",
+                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build(precision: str, device: str = "cuda"):
+    from gdr_net_b200 import GDRN as G
+    from gdr_net_b200 import synth
+    from gdr_net_b200.config import a6_config
+
+    cfg = a6_config(device=device)
+    model, opt = G.build_model_optimizer(cfg, precision=precision)
+    # seeded Kaiming-scale weights (the reference's std=1e-3 init is degenerate without ImageNet weights)
+    sd = synth.seeded_state_dict(model.state_dict(), seed=0)
+    model.load_state_dict(sd)
+    model.train()
+    return model, opt
+
+
+def device_batch(batch, dev):
+    return {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+
+
+def aux_from_batch(b):
+    return dict(roi_coord_2d=b["roi_coord_2d"], roi_cams=b["roi_cam"], roi_centers=b["roi_center"], roi_whs=b["roi_wh"],
+                roi_extents=b["roi_extent"], resize_ratios=b["resize_ratio"], gt_xyz=b["roi_xyz"],
+                gt_mask_trunc=b["roi_mask_trunc"], gt_mask_visib=b["roi_mask_visib"], gt_region=b["roi_region"],
+                gt_ego_rot=b["ego_rot"], gt_points=b["roi_points"], sym_infos=None, gt_trans=b["trans"],
+                gt_trans_ratio=b["roi_trans_ratio"])
+
+
+def run_ours(args):
+    from gdr_net_b200 import synth
+    from gdr_net_b200.capi import launch_count
+    from gdr_net_b200.dist import GradAllReducer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    B = BATCH_PER_GPU
+    peaks = load_peaks()
+
+    def one_mode(precision, steps, warmup, with_clocks):
+        model, _opt = build(precision)
+        eng = model.engine
+        reducer = GradAllReducer(eng.flat_grad, eng.named_params) if world > 1 else None
+        eng.grad_hook = reducer
+        batch = device_batch(synth.make_batch(B, seed=100 + rank), dev)
+        x = batch["roi_img"].float().contiguous()
+        aux = {k: (v.float().contiguous() if isinstance(v, torch.Tensor) and v.dtype != torch.long else v)
+               for k, v in aux_from_batch(batch).items()}
+        gl = torch.ones(8, device=dev)
+
+        def step():
+            res = eng.forward(x, aux, train_bn=True, do_loss=True)
+            eng.backward(gl)
+            if reducer is not None:
+                reducer.finish()
+            return res["losses"]
+
+        for _ in range(warmup):
+            losses = step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local) if with_clocks else None
+        if sampler:
+            sampler.start()
+        l0 = launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            losses = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        launches = (launch_count() - l0) // steps
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.barrier()
+            ms = float(t)
+        assert torch.isfinite(losses).all(), "non-finite losses"
+        return dict(model=model, eng=eng, ms=ms, launches=launches, clocks=clocks, batch=batch, losses=losses)
+
+    main = one_mode("bf16", args.steps, args.warmup, with_clocks=True)
+    ms = main["ms"]
+    value = world * B / (ms / 1e3)
+
+    out = {
+        "metric": METRIC, "value": round(value, 1), "unit": "crops/s", "per_gpu": round(value / world, 1), "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "configs[1]: ResNet-34 GDR-Net (a6_cPnP shapes) full fwd+bwd incl. all 8 losses, train-mode BN, "
+                               "batch 64/GPU, 256x256 synthetic crops, seeded Kaiming weights",
+                   "global_batch": world * B, "parallelism": f"dp{world}",
+                   "l2": "activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
+                   "grad_exchange": "bucketed NCCL all-reduce of the flat 140 MB fp32 gradient buffer, overlapped" if world > 1 else "none"},
+        "clocks": main["clocks"], "gpu_launches": int(main["launches"]),
+    }
+
+    if rank == 0 or world > 1:
+        # ---- e2e through the public module API with pinned host inputs (H2D + D2H inside the timed region)
+        model = main["model"]
+        model.engine.grad_hook = main["eng"].grad_hook
+        host = synth.make_batch(B, seed=200 + rank)
+        pinned = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
+        h2d = sum(v.numel() * v.element_size() for v in pinned.values() if isinstance(v, torch.Tensor))
+        reducer = main["eng"].grad_hook
+
+        def e2e_step():
+            b = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in pinned.items()}
+            for p in model.parameters():
+                p.grad = None
+            _, loss_dict = model(b["roi_img"], **synth.forward_kwargs(b, train=True))
+            total = sum(loss_dict.values())
+            total.backward()
+            if reducer is not None:
+                reducer.finish()
+            return float(total)  # D2H read of the step's loss
+
+        n_e2e = max(3, args.steps // 2)
+        for _ in range(max(2, args.warmup // 2)):
+            e2e_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_e2e = e0.elapsed_time(e1) / n_e2e
+        if world > 1:
+            t = torch.tensor([ms_e2e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t)
+        out["e2e"] = {"value": round(world * B / (ms_e2e / 1e3), 1), "unit": "crops/s", "ms_per_step": round(ms_e2e, 3),
+                      "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                      "api": "gdr_net_b200.GDRN.GDRN.forward(...do_loss=True) + sum(loss_dict.values()).backward()"}
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel family (tcgen05 implicit-GEMM conv: fwd + dgrad + wgrad), measured live
+        out["roofline"] = roofline_live(main, peaks)
+        if world == 1:
+            # fp32-faithful parity mode, same workload (the mode the 1e-3 parity tests run in)
+            try:
+                del main["model"], main["eng"]
+                torch.cuda.empty_cache()
+                x3 = one_mode("fp32x3", max(3, args.steps // 4), 3, with_clocks=False)
+                out["parity_mode"] = {"dtype": "bf16x3 (hi/lo planes, fp32-faithful)", "value": round(B / (x3["ms"] / 1e3), 1),
+                                      "unit": "crops/s", "ms_per_step": round(x3["ms"], 3)}
+            except Exception as e:  # pragma: no cover
+                out["parity_mode"] = {"error": str(e)[:200]}
+            out["cpu_baseline"] = cpu_baseline(sample_batch=args.cpu_batch, iters=args.cpu_iters)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def roofline_live(main, peaks):
+    """Time every tcgen05 GEMM launch of one step with CUDA events (on the launching stream) and divide the
+    algorithmic FLOPs (2*M*N*K of the convolution / linear it implements) by the summed durations."""
+    from gdr_net_b200 import ops
+
+    eng = main["eng"]
+    batch = main["batch"]
+    x = batch["roi_img"].float().contiguous()
+    aux = {k: (v.float().contiguous() if isinstance(v, torch.Tensor) and v.dtype != torch.long else v)
+           for k, v in aux_from_batch(batch).items()}
+    records = []
+    orig = {n: getattr(ops, n) for n in ("conv_fwd", "gemm_fwd", "conv_wgrad", "gemm_wgrad")}
+
+    def timed(name, fn, flops_of):
+        def wrapper(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            records.append((name, flops_of(*a, **k), e0, e1))
+            return r
+
+        return wrapper
+
+    def f_conv(x_, wp, Cout, KH, KW, stride, pad, **k):
+        N, H, W, Cin = x_.shape
+        return 2.0 * N * (H // stride) * (W // stride) * Cout * Cin * KH * KW * k.get("algo_scale", 1.0)
+
+    def f_gemm(a, wp, N, **k):
+        return 2.0 * a.shape[0] * N * a.shape[1]
+
+    def f_cw(dy, x_, ws, Cout, KH, KW, stride, pad, ksplit=0):
+        N, H, W, Cin = x_.shape
+        return 2.0 * N * (H // stride) * (W // stride) * Cout * Cin * KH * KW
+
+    def f_gw(dy, x_, ws, ksplit=0):
+        return 2.0 * dy.shape[0] * dy.shape[1] * x_.shape[1]
+
+    ops.conv_fwd = timed("conv_fwd", orig["conv_fwd"], f_conv)
+    ops.gemm_fwd = timed("gemm_fwd", orig["gemm_fwd"], f_gemm)
+    ops.conv_wgrad = timed("conv_wgrad", orig["conv_wgrad"], f_cw)
+    ops.gemm_wgrad = timed("gemm_wgrad", orig["gemm_wgrad"], f_gw)
+    try:
+        gl = torch.ones(8, device=x.device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(3):
+            records.clear()
+            e0.record()
+            eng.forward(x, aux, train_bn=True, do_loss=True)
+            eng.backward(gl)
+            e1.record()
+        torch.cuda.synchronize()
+    finally:
+        for n, f in orig.items():
+            setattr(ops, n, f)
+    step_ms = e0.elapsed_time(e1)
+    fam = {}
+    for name, fl, a, b in records:
+        d = fam.setdefault(name, [0.0, 0.0, 0])
+        d[0] += fl
+        d[1] += a.elapsed_time(b)
+        d[2] += 1
+    tot_fl = sum(v[0] for v in fam.values())
+    tot_ms = sum(v[1] for v in fam.values())
+    achieved = tot_fl / (tot_ms * 1e-3) / 1e12
+    peak = peaks["bf16_sustained"]
+    return {
+        "bound": "tensor", "kernel": "gdrn::gemm_fwd_kernel / gemm_wgrad_kernel (tcgen05 implicit-GEMM conv family)",
+        "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+        "peak_source": "bf16_tflops_sustained of " + peaks["source"], "traffic": None,
+        "launches_per_step": sum(v[2] for v in fam.values()), "avg_launch_ms": round(tot_ms / max(1, sum(v[2] for v in fam.values())), 4),
+        "algorithmic_gflop_per_step": round(tot_fl / 1e9, 1), "share_of_step": round(tot_ms / step_ms, 3),
+        "families": {k: {"tflops": round(v[0] / (v[1] * 1e-3) / 1e12, 1), "ms": round(v[1], 3), "launches": v[2]} for k, v in fam.items()},
+        "whole_step_tflops": round(FWD_BWD_GFLOP_PER_CROP * BATCH_PER_GPU / main["ms"], 1),
+        "whole_step_frac": round(FWD_BWD_GFLOP_PER_CROP * BATCH_PER_GPU / main["ms"] / peak, 4),
+    }
+
+
+def cpu_baseline(sample_batch: int = 8, iters: int = 2):
+    """The CPU oracle (port of the reference algorithm, pinned bit-exact to it: oracle/make_golden.py) timed on this
+    box's host cores: train-mode fwd + bwd of a bounded sample of the same workload."""
+    from gdr_net_b200 import synth
+    from oracle import fixtures
+    from oracle import gdrn_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.seeded_state_dict(fixtures.template_from_manifest(), 0)
+    batch = synth.make_batch(sample_batch, seed=300)
+    times = []
+    for it in range(iters + 1):
+        leaf = O.leaf_state_dict(sd)
+        t0 = time.perf_counter()
+        o = O.gdrn_forward(leaf, batch, train=True, do_loss=True)
+        sum(o["losses"].values()).backward()
+        dt = time.perf_counter() - t0
+        if it > 0:
+            times.append(dt)
+    best = sum(times) / len(times)
+    return {"value": round(sample_batch / best, 2), "unit": "crops/s", "cores": cores, "kind": "port",
+            "sample": f"train-mode fwd+bwd of {sample_batch} crops x {iters} timed iterations (1 warm-up), torch CPU fp32, "
+                      f"{cores} threads; per-crop rate of the batch-64 workload"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own algorithm on the host cores.  /root/reference does not travel to the GPU box,
+    so this times the CPU oracle port (oracle/gdrn_oracle.py, pinned bit-exact against the live reference)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    from gdr_net_b200 import synth
+    from oracle import fixtures
+    from oracle import gdrn_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.seeded_state_dict(fixtures.template_from_manifest(), 0)
+    sample = args.cpu_batch
+    batch = synth.make_batch(sample, seed=300)
+
+    def step():
+        leaf = O.leaf_state_dict(sd)
+        o = O.gdrn_forward(leaf, batch, train=True, do_loss=True)
+        sum(o["losses"].values()).backward()
+
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    value = sample / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": "crops/s", "n_gpus": world, "steps": steps,
+        "warmup": warm, "ms_per_step": round(dt * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1] (same as the CUDA arm); each step = a bounded sample of it", "parallelism": "host cpu"},
+        "cpu_baseline": {"value": round(value, 2), "unit": "crops/s", "cores": cores, "kind": "port",
+                         "sample": f"train-mode fwd+bwd of {sample} crops per step, torch CPU fp32, {cores} threads"},
+        "e2e": {"value": round(value, 2), "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--cpu-iters", type=int, default=2)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

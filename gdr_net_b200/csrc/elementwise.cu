@@ -26,10 +26,15 @@ __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
 __device__ __forceinline__ void load8(const bf16* hi, const bf16* lo, long off8, float (&f)[8]) {
     unpack8(__ldg(reinterpret_cast<const uint4*>(hi) + off8), f);
     if (lo != nullptr) {
-        float g[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(lo) + off8), g);
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(lo) + off8);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] += g[j];
+        for (int j = 0; j < 4; ++j) {
+            float a, b;
+            unpack_lo2(w[j], a, b);
+            f[2 * j] += a;
+            f[2 * j + 1] += b;
+        }
     }
 }
 __device__ __forceinline__ void store8(bf16* hi, bf16* lo, long off8, const float (&f)[8]) {
@@ -37,7 +42,7 @@ __device__ __forceinline__ void store8(bf16* hi, bf16* lo, long off8, const floa
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         h[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-        l[j] = pack_bf16x2(f[2 * j] - __uint_as_float(h[j] << 16), f[2 * j + 1] - __uint_as_float(h[j] & 0xffff0000u));
+        l[j] = pack_lo2(f[2 * j] - __uint_as_float(h[j] << 16), f[2 * j + 1] - __uint_as_float(h[j] & 0xffff0000u));
     }
     reinterpret_cast<uint4*>(hi)[off8] = make_uint4(h[0], h[1], h[2], h[3]);
     if (lo != nullptr) reinterpret_cast<uint4*>(lo)[off8] = make_uint4(l[0], l[1], l[2], l[3]);

@@ -54,7 +54,13 @@ struct GemmCfg {
     static constexpr int STAGES_RAW = (kSmemBudget - kAuxBytes - 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kAuxBytes + 1024;
-    static constexpr int TMEM_COLS = 2 * BLOCK_N;  // double-buffered accumulator
+    // tcgen05.mma accumulates into TMEM with round-toward-zero (measured: tools/exp_accum.py), so the error of a
+    // K-long chain grows ~ (K/16) * 2^-24.  The fp32-faithful mode therefore keeps the small cross terms
+    // (hi*lo + lo*hi) in their own accumulator and spreads the hi*hi k-blocks round-robin over three more; the
+    // epilogue adds the four partials with round-to-nearest fp32 adds.
+    static constexpr int NMAIN = (NSPLIT == 3) ? 3 : 1;
+    static constexpr int NACC = (NSPLIT == 3) ? 4 : 1;
+    static constexpr int TMEM_COLS = 2 * NACC * BLOCK_N;  // double-buffered accumulator set
     static_assert(STAGES >= 2, "pipeline too shallow");
     static_assert(TMEM_COLS <= 512, "TMEM overflow");
 };
@@ -178,6 +184,10 @@ __global__ void __launch_bounds__(256, 1) gemm_fwd_kernel(const __grid_constant_
         // ------------------------------------------------------------------ MMA issuer (single thread)
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+            constexpr uint32_t idesc_hl = make_idesc_f16(kBlockM, BLOCK_N, 0, 0, 1, 0);
+            constexpr uint32_t idesc_lh = make_idesc_f16(kBlockM, BLOCK_N, 0, 0, 0, 1);
+            (void)idesc_hl;
+            (void)idesc_lh;
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -186,8 +196,10 @@ __global__ void __launch_bounds__(256, 1) gemm_fwd_kernel(const __grid_constant_
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                const uint32_t d_set = tmem_base + acc * Cfg::NACC * BLOCK_N;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
+                    const uint32_t d_tmem = d_set + (NSPLIT == 3 ? (kb % Cfg::NMAIN) * BLOCK_N : 0);
+                    const uint32_t d_cross = d_set + Cfg::NMAIN * BLOCK_N;
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -196,12 +208,14 @@ __global__ void __launch_bounds__(256, 1) gemm_fwd_kernel(const __grid_constant_
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         const uint64_t da = make_smem_desc(a_hi + k * 32, 16, 1024);
                         const uint64_t db = make_smem_desc(b_hi + k * 32, 16, 1024);
-                        umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                         if (NSPLIT == 3) {
                             const uint64_t da_lo = make_smem_desc(a_hi + Cfg::A_BYTES + k * 32, 16, 1024);
                             const uint64_t db_lo = make_smem_desc(b_hi + Cfg::B_BYTES + k * 32, 16, 1024);
-                            umma_bf16(d_tmem, da, db_lo, idesc, 1u);
-                            umma_bf16(d_tmem, da_lo, db, idesc, 1u);
+                            umma_bf16(d_tmem, da, db, idesc, (kb >= Cfg::NMAIN || k != 0) ? 1u : 0u);
+                            umma_bf16(d_cross, da, db_lo, idesc, (kb | k) != 0 ? 1u : 0u);
+                            umma_bf16(d_cross, da_lo, db, idesc, 1u);
+                        } else {
+                            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                         }
                     }
                     umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above retire
@@ -231,14 +245,28 @@ __global__ void __launch_bounds__(256, 1) gemm_fwd_kernel(const __grid_constant_
             const bool row_ok = grow < p.M;
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 32; ++c) {
-                uint32_t raw[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + c * 32, raw);
-                tmem_ld_wait();
                 const int col0 = n_tile * BLOCK_N + c * 32;
                 if (col0 >= p.N) continue;  // warp-uniform
                 float f[32];
+                {
+                    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::NACC * BLOCK_N + c * 32;
+                    uint32_t raw[32];
+                    tmem_ld_32x32(t0, raw);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(raw[j]);
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(raw[j]);
+                    if (NSPLIT == 3) {
+                        const int nmain = p.num_kb < Cfg::NMAIN ? p.num_kb : Cfg::NMAIN;
+                        for (int a2 = 1; a2 <= Cfg::NMAIN; ++a2) {
+                            if (a2 < Cfg::NMAIN && a2 >= nmain) continue;  // partial never written (tiny K)
+                            tmem_ld_32x32(t0 + a2 * BLOCK_N, raw);
+                            tmem_ld_wait();
+                            const float sc = (a2 == Cfg::NMAIN) ? kLoInvScale : 1.f;  // cross terms carry the lo-plane scale
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(raw[j]), sc, f[j]);
+                        }
+                    }
+                }
                 const bool full_chunk = (col0 + 32 <= p.N);
                 if (p.bias != nullptr) {
 #pragma unroll
@@ -274,7 +302,7 @@ __global__ void __launch_bounds__(256, 1) gemm_fwd_kernel(const __grid_constant_
                             hi[j] = pack_bf16x2(a, b);
                             const float ra = a - __uint_as_float(hi[j] << 16);
                             const float rb = b - __uint_as_float(hi[j] & 0xffff0000u);
-                            lo[j] = pack_bf16x2(ra, rb);
+                            lo[j] = pack_lo2(ra, rb);
                         }
                         const int ncopy = full_chunk ? 4 : ((min(p.ldc, col0 + 32) - col0) / 8);
                         uint4* dh = reinterpret_cast<uint4*>(out_hi + grow * p.ldc + col0);
@@ -356,13 +384,13 @@ static int dispatch_gemm(const GemmParams& p, int block_n, int nsplit, cudaStrea
         if (block_n == 128) return launch_gemm<128, 1>(p, stream);
         if (block_n == 64) return launch_gemm<64, 1>(p, stream);
     } else if (nsplit == 3) {
-        if (block_n == 128) return launch_gemm<128, 3>(p, stream);
         if (block_n == 64) return launch_gemm<64, 3>(p, stream);
     }
     return set_error(GDRN_ERR_ARG, "gemm: unsupported block_n=%d nsplit=%d", block_n, nsplit);
 }
 
 static int pick_block_n(int n_pad, int nsplit) {
+    if (nsplit == 3) return (n_pad % 64 == 0) ? 64 : -1;  // 4 accumulators x 2 buffers x 64 columns = all of TMEM
     if (nsplit == 1 && n_pad % 256 == 0) return 256;
     if (n_pad % 128 == 0) return 128;
     if (n_pad % 64 == 0) return 64;

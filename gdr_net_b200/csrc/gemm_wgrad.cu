@@ -45,7 +45,11 @@ struct WgradCfg {
     static constexpr int STAGES_RAW = (227 * 1024 - 2048) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048;
-    static constexpr int TMEM_COLS = N_TILE < 32 ? 32 : N_TILE;
+    // round-toward-zero accumulation (see gemm_fwd.cu): cross terms and three round-robin hi*hi partials
+    static constexpr int NMAIN = (NSPLIT == 3) ? 3 : 1;
+    static constexpr int NACC = (NSPLIT == 3) ? 4 : 1;
+    static constexpr int TMEM_COLS = NACC * N_TILE < 32 ? 32 : NACC * N_TILE;
+    static_assert(NACC * N_TILE <= 512, "TMEM overflow");
     static_assert(STAGES >= 2, "pipeline too shallow");
 };
 
@@ -152,6 +156,10 @@ __global__ void __launch_bounds__(192, 1) gemm_wgrad_kernel(const __grid_constan
     } else if (warp == 1) {
         if (lane == 0 && nkb > 0) {
             constexpr uint32_t idesc = make_idesc_bf16(128, N_TILE, 1, 1);
+            constexpr uint32_t idesc_hl = make_idesc_f16(128, N_TILE, 1, 1, 1, 0);
+            constexpr uint32_t idesc_lh = make_idesc_f16(128, N_TILE, 1, 1, 0, 1);
+            (void)idesc_hl;
+            (void)idesc_lh;
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < nkb; ++kb) {
@@ -163,12 +171,14 @@ __global__ void __launch_bounds__(192, 1) gemm_wgrad_kernel(const __grid_constan
                 for (int k = 0; k < 4; ++k) {  // 16 pixels (= 16 rows of 128 B) per MMA
                     const uint64_t da = make_smem_desc(a_hi + k * 2048, 8192, 1024);
                     const uint64_t db = make_smem_desc(b_hi + k * 2048, 8192, 1024);
-                    umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                     if (NSPLIT == 3) {
                         const uint64_t da_lo = make_smem_desc(a_hi + Cfg::A_BYTES + k * 2048, 8192, 1024);
                         const uint64_t db_lo = make_smem_desc(b_hi + Cfg::B_BYTES + k * 2048, 8192, 1024);
-                        umma_bf16(tmem_base, da, db_lo, idesc, 1u);
-                        umma_bf16(tmem_base, da_lo, db, idesc, 1u);
+                        umma_bf16(tmem_base + (kb % Cfg::NMAIN) * N_TILE, da, db, idesc, (kb >= Cfg::NMAIN || k != 0) ? 1u : 0u);
+                        umma_bf16(tmem_base + Cfg::NMAIN * N_TILE, da, db_lo, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_bf16(tmem_base + Cfg::NMAIN * N_TILE, da_lo, db, idesc, 1u);
+                    } else {
+                        umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                 }
                 umma_commit(&empty_bar[stage]);
@@ -194,8 +204,21 @@ __global__ void __launch_bounds__(192, 1) gemm_wgrad_kernel(const __grid_constan
         for (int c = 0; c < N_TILE / 32; ++c) {
             uint32_t raw[32];
             if (nkb > 0) {
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, raw);
+                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + c * 32;
+                tmem_ld_32x32(t0, raw);
                 tmem_ld_wait();
+                if (NSPLIT == 3) {
+                    const int nmain = nkb < Cfg::NMAIN ? nkb : Cfg::NMAIN;
+                    for (int a2 = 1; a2 <= Cfg::NMAIN; ++a2) {
+                        if (a2 < Cfg::NMAIN && a2 >= nmain) continue;
+                        uint32_t r2[32];
+                        tmem_ld_32x32(t0 + a2 * N_TILE, r2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            raw[j] = __float_as_uint(fmaf(__uint_as_float(r2[j]), a2 == Cfg::NMAIN ? kLoInvScale : 1.f, __uint_as_float(raw[j])));
+                    }
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) raw[j] = 0u;

@@ -27,7 +27,7 @@ __device__ __forceinline__ void store_row_bf16(bf16* hi, bf16* lo, long row, int
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             h[q] = pack_bf16x2(v[j + 2 * q], v[j + 2 * q + 1]);
-            l[q] = pack_bf16x2(v[j + 2 * q] - __uint_as_float(h[q] << 16), v[j + 2 * q + 1] - __uint_as_float(h[q] & 0xffff0000u));
+            l[q] = pack_lo2(v[j + 2 * q] - __uint_as_float(h[q] << 16), v[j + 2 * q + 1] - __uint_as_float(h[q] & 0xffff0000u));
         }
         *reinterpret_cast<uint4*>(hi + row * ld + j) = make_uint4(h[0], h[1], h[2], h[3]);
         if (lo != nullptr) *reinterpret_cast<uint4*>(lo + row * ld + j) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -168,8 +168,10 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__
                     const uint32_t w2[4] = {q2.x, q2.y, q2.z, q2.w};
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
-                        gin[j + 2 * t] += __uint_as_float(w2[t] << 16);
-                        gin[j + 2 * t + 1] += __uint_as_float(w2[t] & 0xffff0000u);
+                        float ra, rb;
+                        unpack_lo2(w2[t], ra, rb);
+                        gin[j + 2 * t] += ra;
+                        gin[j + 2 * t + 1] += rb;
                     }
                 }
             }
@@ -547,7 +549,7 @@ __global__ void __launch_bounds__(128) pose_loss_kernel(const PoseParams p) {
             *reinterpret_cast<uint32_t*>(p.dy_hi + (long)b * 64 + k) = h;
             if (p.dy_lo != nullptr)
                 *reinterpret_cast<uint32_t*>(p.dy_lo + (long)b * 64 + k) =
-                    pack_bf16x2(a - __uint_as_float(h << 16), c - __uint_as_float(h & 0xffff0000u));
+                    pack_lo2(a - __uint_as_float(h << 16), c - __uint_as_float(h & 0xffff0000u));
         }
     }
 }

@@ -5,6 +5,8 @@
 // Parameter layouts follow the reference state_dict: Conv2d OIHW, ConvTranspose2d
 // IOHW (cdpn_rot_head_region.py:82-91), Linear [out][in] with fc1's input flattened from NCHW
 // (conv_pnp_net.py:145).
+#include <cuda_fp16.h>
+
 #include "gdrn_internal.h"
 #include "ptx.cuh"
 
@@ -90,7 +92,7 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* _
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-            lo[j] = pack_bf16x2(v[2 * j] - __uint_as_float(hi[j] << 16), v[2 * j + 1] - __uint_as_float(hi[j] & 0xffff0000u));
+            lo[j] = pack_lo2(v[2 * j] - __uint_as_float(hi[j] << 16), v[2 * j + 1] - __uint_as_float(hi[j] & 0xffff0000u));
         }
         reinterpret_cast<uint4*>(a_hi)[idx] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         if (a_lo != nullptr) reinterpret_cast<uint4*>(a_lo)[idx] = make_uint4(lo[0], lo[1], lo[2], lo[3]);

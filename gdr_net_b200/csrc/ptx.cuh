@@ -128,6 +128,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with explicit operand formats (0 = F16, 1 = BF16): the cross terms multiply a bf16 hi plane by an fp16 lo plane
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major, int a_fmt, int b_fmt) {
+    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn_major << 15) |
+           ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -139,6 +144,19 @@ __device__ __forceinline__ float bf16_round(float x) {  // round-to-nearest-even
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.0f), "f"(x));
     return __uint_as_float(r << 16);
+}
+// ---- lo plane of the (hi, lo) pair: lo = bf16(x - bf16(x)) (16-bit operands).  NOTE: a scaled fp16 residual
+// (19 bits) was tried; tcgen05.mma kind::f16 rejects mixed bf16 x fp16 operands (illegal instruction), so both
+// planes share one format.
+constexpr float kLoInvScale = 1.f;
+__device__ __forceinline__ uint32_t pack_lo2(float ra, float rb) {  // residuals of (low half, high half)
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(rb), "f"(ra));
+    return r;
+}
+__device__ __forceinline__ void unpack_lo2(uint32_t w, float& a, float& b) {
+    a = __uint_as_float(w << 16);
+    b = __uint_as_float(w & 0xffff0000u);
 }
 __device__ __forceinline__ float bf16_bits_to_f32(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
 

@@ -139,7 +139,7 @@ class Engine:
         stats = st.stats if train_bn else None
         k, stride, pad = conv.kernel_size[0], conv.stride[0], conv.padding[0]
         if kind == "deconv":
-            u = ops.conv_fwd(x, self.wf["deconv"], conv.out_channels, 3, 3, 1, 1, stats=stats)
+            u = ops.conv_fwd(x, self.wf["deconv"], conv.out_channels, 3, 3, 1, 1, stats=stats, algo_scale=0.25)
         else:
             u = ops.conv_fwd(x, self.wf[wkey or ckey], conv.out_channels, k, k, stride, pad, stats=stats)
         y = self._bn_fwd(bkey, u, relu, train_bn, res)
@@ -316,7 +316,7 @@ class Engine:
     def _dgrad_conv(self, du: PT, conv, wkey: str) -> PT:
         k, stride, pad = conv.kernel_size[0], conv.stride[0], conv.padding[0]
         z = ops.zero_insert(du) if stride == 2 else du
-        return ops.conv_fwd(z, self.wd[wkey], conv.in_channels, k, k, 1, k - 1 - pad)
+        return ops.conv_fwd(z, self.wd[wkey], conv.in_channels, k, k, 1, k - 1 - pad, algo_scale=0.25 if stride == 2 else 1.0)
 
     def _bn_bwd(self, bkey: str, ga: PT, gb: Optional[PT], y: Optional[PT], u: PT, want_gout=False):
         mod, st = self._bn_mods[bkey], self.bn[bkey]
@@ -414,6 +414,8 @@ class Engine:
                 ga, gb = dx_main, dx_ds
             else:
                 ga, gb = dx_main, gout
+            if self.grad_hook and p.endswith(".0") and not p.startswith("backbone.layer1"):
+                self.grad_hook(self, p[:-2])  # all gradients of backbone.layerN are final
         g_pool = ops.add2(ga, gb)
         St = S["stem"]
         g_a0 = ops.maxpool_bwd(St["a0"], g_pool)
@@ -422,7 +424,7 @@ class Engine:
         # ws rows [64][192] with k = (r*7+s)*3 + c  ->  OIHW [64][3][7][7]
         ops.unpack_wgrad(buf, self.grads["backbone.conv1.weight"], 64, 3, 7, 7, 3, ks, kss, 147, 49, 7, 1, krow=192)
         if self.grad_hook:
-            self.grad_hook(self, "backbone")
+            self.grad_hook(self, "backbone.stem")  # layer1 + bn1 + conv1
         self.saved = None
         return self.grads
 

@@ -170,7 +170,8 @@ def pack_linear(w: torch.Tensor, planes: int, out: PT | None = None, nhwc_from: 
 # ---------------------------------------------------------------------------------------------
 def conv_fwd(x: PT, wp: PT, Cout: int, KH: int, KW: int, stride: int, pad: int, *, out: PT | None = None,
              out_f32: torch.Tensor | None = None, bias=None, stats=None, act: int = 0, ldc: int | None = None,
-             want_planes: bool = True) -> PT | None:
+             want_planes: bool = True, algo_scale: float = 1.0) -> PT | None:
+    """algo_scale: fraction of the launched MACs that are algorithmic (0.25 for zero-inserted inputs); bookkeeping only."""
     N, H, W, Cin = x.shape
     Ho, Wo = H // stride, W // stride
     ldc = ldc or _round_up(Cout, 64)
