@@ -271,6 +271,7 @@ def roofline_live(main, peaks):
     from gdr_net_b200 import ops
 
     eng = main["eng"]
+    eng.grad_hook = None  # rank-0-only instrumentation pass: no collectives
     batch = main["batch"]
     x = batch["roi_img"].float().contiguous()
     aux = {k: (v.float().contiguous() if isinstance(v, torch.Tensor) and v.dtype != torch.long else v)
