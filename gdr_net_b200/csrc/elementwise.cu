@@ -89,33 +89,123 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
     }
 }
 
-// y = [relu](x * scale[c] + shift[c] [+ res])
-__global__ void bn_act_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo, const bf16* __restrict__ r_hi,
-                              const bf16* __restrict__ r_lo, bf16* __restrict__ y_hi, bf16* __restrict__ y_lo,
-                              const float* __restrict__ scale, const float* __restrict__ shift, long rows, int C, int relu) {
+// y = [relu](x * scale[c] + shift[c] [+ res]).  blockDim (256) is a multiple of C/8, so a thread always sees the same
+// 8 channels: coefficients live in registers; two independent 16-byte loads per tensor are kept in flight.
+__global__ void __launch_bounds__(256) bn_act_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo,
+                                                     const bf16* __restrict__ r_hi, const bf16* __restrict__ r_lo,
+                                                     bf16* __restrict__ y_hi, bf16* __restrict__ y_lo,
+                                                     const float* __restrict__ scale, const float* __restrict__ shift, long rows,
+                                                     int C, int relu) {
     const int cg = C / 8;
     const long total = rows * cg;
-    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int c0 = (int)(idx % cg) * 8;
-        float v[8];
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long first = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    const int c0 = (int)(first % cg) * 8;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = __ldg(scale + c0 + j);
+        sh[j] = __ldg(shift + c0 + j);
+    }
+    for (long idx = first; idx < total; idx += 2 * stride) {
+        const long idx2 = idx + stride;
+        const bool two = idx2 < total;
+        float v[8], w[8], r[8], q[8];
         load8(x_hi, x_lo, idx, v);
-        const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c0)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c0 + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + c0)), b1 = __ldg(reinterpret_cast<const float4*>(shift + c0 + 4));
-        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-        const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+        if (two) load8(x_hi, x_lo, idx2, w);
         if (r_hi != nullptr) {
-            float r[8];
             load8(r_hi, r_lo, idx, r);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += r[j];
+            if (two) load8(r_hi, r_lo, idx2, q);
         }
-        if (relu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        for (int j = 0; j < 8; ++j) {
+            v[j] = fmaf(v[j], sc[j], sh[j]);
+            w[j] = fmaf(w[j], sc[j], sh[j]);
+            if (r_hi != nullptr) {
+                v[j] += r[j];
+                w[j] += q[j];
+            }
+            if (relu) {
+                v[j] = fmaxf(v[j], 0.f);
+                w[j] = fmaxf(w[j], 0.f);
+            }
         }
         store8(y_hi, y_lo, idx, v);
+        if (two) store8(y_hi, y_lo, idx2, w);
+    }
+}
+
+// BatchNorm forward in ONE kernel: every thread derives scale/shift of its 8 channels from the conv epilogue's
+// (sum, sum^2) statistics (train) or the running statistics (eval); block 0 also stores mean/invstd for the backward
+// pass and updates the running statistics (momentum, unbiased variance) like nn.BatchNorm2d.
+__global__ void __launch_bounds__(256) bn_fwd_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo,
+                                                     const bf16* __restrict__ r_hi, const bf16* __restrict__ r_lo,
+                                                     bf16* __restrict__ y_hi, bf16* __restrict__ y_lo,
+                                                     const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float* running_mean, float* running_var,
+                                                     float* __restrict__ mean_out, float* __restrict__ invstd_out, long rows, int C,
+                                                     float eps, float momentum, int train, int relu) {
+    const int cg = C / 8;
+    const long total = rows * cg;
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long first = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    const int c0 = (int)(first % cg) * 8;
+    const float count = (float)rows;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        float mean, var;
+        if (train) {
+            const double m = (double)stats[c] / count;
+            double v = (double)stats[C + c] / count - m * m;
+            if (v < 0) v = 0;
+            mean = (float)m;
+            var = (float)v;
+        } else {
+            mean = running_mean[c];
+            var = running_var[c];
+        }
+        const float invstd = rsqrtf(var + eps);
+        sc[j] = gamma[c] * invstd;
+        sh[j] = beta[c] - mean * sc[j];
+        if (blockIdx.x == 0 && threadIdx.x < cg) {
+            if (mean_out != nullptr) {
+                mean_out[c] = mean;
+                invstd_out[c] = invstd;
+            }
+            if (train && running_mean != nullptr) {
+                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+                const float unbiased = count > 1.f ? var * (count / (count - 1.f)) : var;
+                running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+            }
+        }
+    }
+    for (long idx = first; idx < total; idx += 2 * stride) {
+        const long idx2 = idx + stride;
+        const bool two = idx2 < total;
+        float v[8], w[8], r[8], q[8];
+        load8(x_hi, x_lo, idx, v);
+        if (two) load8(x_hi, x_lo, idx2, w);
+        if (r_hi != nullptr) {
+            load8(r_hi, r_lo, idx, r);
+            if (two) load8(r_hi, r_lo, idx2, q);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v[j] = fmaf(v[j], sc[j], sh[j]);
+            w[j] = fmaf(w[j], sc[j], sh[j]);
+            if (r_hi != nullptr) {
+                v[j] += r[j];
+                w[j] += q[j];
+            }
+            if (relu) {
+                v[j] = fmaxf(v[j], 0.f);
+                w[j] = fmaxf(w[j], 0.f);
+            }
+        }
+        store8(y_hi, y_lo, idx, v);
+        if (two) store8(y_hi, y_lo, idx2, w);
     }
 }
 
@@ -123,7 +213,7 @@ __global__ void bn_act_kernel(const bf16* __restrict__ x_hi, const bf16* __restr
 // MaxPool 3x3 s2 p1 (first maximum in row-major window order wins, like ATen)
 // ------------------------------------------------------------------------------------------------
 __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo, bf16* __restrict__ y_hi,
-                                   bf16* __restrict__ y_lo, int B, int H, int W, int C) {
+                                   bf16* __restrict__ y_lo, uint8_t* __restrict__ arg_out, int B, int H, int W, int C) {
     const int cg = C / 8, Ho = H / 2, Wo = W / 2;
     const long total = (long)B * Ho * Wo * cg;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -134,28 +224,44 @@ __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x_hi, const bf16* __
         const int oy = (int)(t % Ho);
         const int b = (int)(t / Ho);
         float m[8];
+        uint32_t arg[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+        for (int j = 0; j < 8; ++j) {
+            m[j] = -INFINITY;
+            arg[j] = 0;
+        }
+#pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
             const int iy = oy * 2 + dy - 1;
             if (iy < 0 || iy >= H) continue;
+#pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
                 const int ix = ox * 2 + dx - 1;
                 if (ix < 0 || ix >= W) continue;
                 float v[8];
                 load8(x_hi, x_lo, (((long)b * H + iy) * W + ix) * cg + g, v);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) m[j] = v[j] > m[j] ? v[j] : m[j];
+                for (int j = 0; j < 8; ++j)
+                    if (v[j] > m[j]) {
+                        m[j] = v[j];
+                        arg[j] = dy * 3 + dx;
+                    }
             }
         }
         store8(y_hi, y_lo, idx, m);
+        if (arg_out != nullptr) {
+            uint2 packed;
+            packed.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+            packed.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+            reinterpret_cast<uint2*>(arg_out)[idx] = packed;
+        }
     }
 }
 
-// dx[iy,ix] = sum over the (<=4) windows containing it whose first-max position is (iy,ix)
-__global__ void maxpool_bwd_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo,
-                                   const bf16* __restrict__ g_hi, const bf16* __restrict__ g_lo, bf16* __restrict__ dx_hi,
-                                   bf16* __restrict__ dx_lo, int B, int H, int W, int C) {
+// dx[iy,ix] = sum of g over the (<=4) windows whose saved arg-max (window-local code dy*3+dx, first maximum) is (iy,ix)
+__global__ void maxpool_bwd_kernel(const uint8_t* __restrict__ arg_in, const bf16* __restrict__ g_hi,
+                                   const bf16* __restrict__ g_lo, bf16* __restrict__ dx_hi, bf16* __restrict__ dx_lo, int B, int H,
+                                   int W, int C) {
     const int cg = C / 8, Ho = H / 2, Wo = W / 2;
     const long total = (long)B * H * W * cg;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -168,39 +274,20 @@ __global__ void maxpool_bwd_kernel(const bf16* __restrict__ x_hi, const bf16* __
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        // windows oy with oy*2-1 <= iy <= oy*2+1  <=>  oy in [iy/2, (iy+1)/2]
-        for (int oy = iy / 2; oy <= (iy + 1) / 2; ++oy) {
-            if (oy < 0 || oy >= Ho) continue;
+        for (int oy = iy / 2; oy <= (iy + 1) / 2; ++oy) {  // windows with oy*2-1 <= iy <= oy*2+1
+            if (oy >= Ho) continue;
             for (int ox = ix / 2; ox <= (ix + 1) / 2; ++ox) {
-                if (ox < 0 || ox >= Wo) continue;
-                float m[8];
-                int arg[8];
+                if (ox >= Wo) continue;
+                const uint32_t code = (uint32_t)((iy - (oy * 2 - 1)) * 3 + (ix - (ox * 2 - 1)));
+                const long o = (((long)b * Ho + oy) * Wo + ox) * cg + g;
+                const uint2 a = __ldg(reinterpret_cast<const uint2*>(arg_in) + o);
+                float gv[8];
+                load8(g_hi, g_lo, o, gv);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    m[j] = -INFINITY;
-                    arg[j] = -1;
+                    const uint32_t aj = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xffu;
+                    if (aj == code) acc[j] += gv[j];
                 }
-                for (int dy = 0; dy < 3; ++dy) {
-                    const int yy = oy * 2 + dy - 1;
-                    if (yy < 0 || yy >= H) continue;
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const int xx = ox * 2 + dx - 1;
-                        if (xx < 0 || xx >= W) continue;
-                        float v[8];
-                        load8(x_hi, x_lo, (((long)b * H + yy) * W + xx) * cg + g, v);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (v[j] > m[j]) {
-                                m[j] = v[j];
-                                arg[j] = yy * W + xx;
-                            }
-                    }
-                }
-                float gv[8];
-                load8(g_hi, g_lo, (((long)b * Ho + oy) * Wo + ox) * cg + g, gv);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (arg[j] == iy * W + ix) acc[j] += gv[j];
             }
         }
         store8(dx_hi, dx_lo, idx, acc);
@@ -343,27 +430,36 @@ __global__ void __launch_bounds__(kBnBwdThreads) bn_bwd_reduce_kernel(
         mu[j] = mean[g * 8 + j];
         is[j] = invstd[g * 8 + j];
     }
-    for (long r = (long)blockIdx.x * rpb + rl; r < rows; r += (long)gridDim.x * rpb) {
-        const long off = r * cg + g;
-        float gv[8], u[8];
-        load8(ga_hi, ga_lo, off, gv);
-        if (gb_hi != nullptr) {
-            float t[8];
-            load8(gb_hi, gb_lo, off, t);
+    const long rstride = (long)gridDim.x * rpb;
+    for (long r0 = (long)blockIdx.x * rpb + rl; r0 < rows; r0 += 4 * rstride) {
+        float gv[4][8], u[4][8], y[4][8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) gv[j] += t[j];
+        for (int t = 0; t < 4; ++t) {  // all loads first (memory-level parallelism), then the math
+            const long r = r0 + t * rstride;
+            if (r < rows) {
+                const long off = r * cg + g;
+                load8(ga_hi, ga_lo, off, gv[t]);
+                load8(u_hi, u_lo, off, u[t]);
+                if (y_hi != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(y_hi) + off), y[t]);
+            }
         }
-        if (y_hi != nullptr) {
-            float y[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(y_hi) + off), y);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) gv[j] = y[j] > 0.f ? gv[j] : 0.f;
-        }
-        load8(u_hi, u_lo, off, u);
+        for (int t = 0; t < 4; ++t) {
+            const long r = r0 + t * rstride;
+            if (r < rows) {
+                if (gb_hi != nullptr) {
+                    float tb[8];
+                    load8(gb_hi, gb_lo, r * cg + g, tb);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            s0[j] += gv[j];
-            s1[j] = fmaf(gv[j], (u[j] - mu[j]) * is[j], s1[j]);
+                    for (int j = 0; j < 8; ++j) gv[t][j] += tb[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float gg = (y_hi == nullptr || y[t][j] > 0.f) ? gv[t][j] : 0.f;
+                    s0[j] += gg;
+                    s1[j] = fmaf(gg, (u[t][j] - mu[j]) * is[j], s1[j]);
+                }
+            }
         }
     }
     __shared__ float red[2][kBnBwdThreads][8 + 1];
@@ -383,14 +479,13 @@ __global__ void __launch_bounds__(kBnBwdThreads) bn_bwd_reduce_kernel(
     }
 }
 
-__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ ga_hi, const bf16* __restrict__ ga_lo,
-                                    const bf16* __restrict__ gb_hi, const bf16* __restrict__ gb_lo,
-                                    const bf16* __restrict__ y_hi, const bf16* __restrict__ u_hi,
-                                    const bf16* __restrict__ u_lo, const float* __restrict__ mean,
-                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                    const float* __restrict__ sums, bf16* __restrict__ du_hi, bf16* __restrict__ du_lo,
-                                    bf16* __restrict__ gout_hi, bf16* __restrict__ gout_lo, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta, long rows, int C, int train) {
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
+    const bf16* __restrict__ ga_hi, const bf16* __restrict__ ga_lo, const bf16* __restrict__ gb_hi,
+    const bf16* __restrict__ gb_lo, const bf16* __restrict__ y_hi, const bf16* __restrict__ u_hi,
+    const bf16* __restrict__ u_lo, const float* __restrict__ mean, const float* __restrict__ invstd,
+    const float* __restrict__ gamma, const float* __restrict__ sums, bf16* __restrict__ du_hi, bf16* __restrict__ du_lo,
+    bf16* __restrict__ gout_hi, bf16* __restrict__ gout_lo, float* __restrict__ dgamma, float* __restrict__ dbeta, long rows,
+    int C, int train) {
     const int cg = C / 8;
     const long total = rows * cg;
     const float inv_n = 1.f / (float)rows;
@@ -400,36 +495,63 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ ga_hi, const bf16* 
             dgamma[c] = sums[C + c];
         }
     }
-    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int c0 = (int)(idx % cg) * 8;
-        float gv[8], u[8], o[8];
-        load8(ga_hi, ga_lo, idx, gv);
-        if (gb_hi != nullptr) {
-            float t[8];
-            load8(gb_hi, gb_lo, idx, t);
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long first = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    const int c0 = (int)(first % cg) * 8;
+    // du = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) = k1*g + k2*u + k3 with per-channel constants
+    float k1[8], k2[8], k3[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) gv[j] += t[j];
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        const float is = invstd[c];
+        k1[j] = gamma[c] * is;
+        if (train) {
+            const float m0 = sums[c] * inv_n, m1 = sums[C + c] * inv_n;
+            k2[j] = -k1[j] * is * m1;
+            k3[j] = k1[j] * (mean[c] * is * m1 - m0);
+        } else {
+            k2[j] = 0.f;
+            k3[j] = 0.f;
         }
+    }
+    for (long idx = first; idx < total; idx += 2 * stride) {
+        const long idx2 = idx + stride;
+        const bool two = idx2 < total;
+        float g1[8], g2[8], u1[8], u2[8], y1[8], y2[8];
+        load8(ga_hi, ga_lo, idx, g1);
+        if (two) load8(ga_hi, ga_lo, idx2, g2);
+        load8(u_hi, u_lo, idx, u1);
+        if (two) load8(u_hi, u_lo, idx2, u2);
         if (y_hi != nullptr) {
-            float y[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(y_hi) + idx), y);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) gv[j] = y[j] > 0.f ? gv[j] : 0.f;
+            unpack8(__ldg(reinterpret_cast<const uint4*>(y_hi) + idx), y1);
+            if (two) unpack8(__ldg(reinterpret_cast<const uint4*>(y_hi) + idx2), y2);
         }
-        load8(u_hi, u_lo, idx, u);
+        if (gb_hi != nullptr) {
+            float t1[8], t2[8];
+            load8(gb_hi, gb_lo, idx, t1);
+            if (two) load8(gb_hi, gb_lo, idx2, t2);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = c0 + j;
-            const float is = invstd[c];
-            if (train) {
-                const float xh = (u[j] - mean[c]) * is;
-                o[j] = gamma[c] * is * (gv[j] - sums[c] * inv_n - xh * sums[C + c] * inv_n);
-            } else {
-                o[j] = gamma[c] * is * gv[j];
+            for (int j = 0; j < 8; ++j) {
+                g1[j] += t1[j];
+                g2[j] += t2[j];
             }
         }
-        store8(du_hi, du_lo, idx, o);
-        if (gout_hi != nullptr) store8(gout_hi, gout_lo, idx, gv);
+        float o1[8], o2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (y_hi != nullptr) {
+                g1[j] = y1[j] > 0.f ? g1[j] : 0.f;
+                g2[j] = y2[j] > 0.f ? g2[j] : 0.f;
+            }
+            o1[j] = fmaf(k1[j], g1[j], fmaf(k2[j], u1[j], k3[j]));
+            o2[j] = fmaf(k1[j], g2[j], fmaf(k2[j], u2[j], k3[j]));
+        }
+        store8(du_hi, du_lo, idx, o1);
+        if (gout_hi != nullptr) store8(gout_hi, gout_lo, idx, g1);
+        if (two) {
+            store8(du_hi, du_lo, idx2, o2);
+            if (gout_hi != nullptr) store8(gout_hi, gout_lo, idx2, g2);
+        }
     }
 }
 
@@ -699,18 +821,18 @@ extern "C" int gdrn_bn_act(const void* x_hi, const void* x_lo, const void* r_hi,
     LAUNCH_DONE();
 }
 
-extern "C" int gdrn_maxpool_fwd(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int B, int H, int W, int C,
-                                void* stream_) {
+extern "C" int gdrn_maxpool_fwd(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, void* arg_out, int B, int H,
+                                int W, int C, void* stream_) {
     STREAM;
-    maxpool_fwd_kernel<<<ew_grid((long)B * (H / 2) * (W / 2) * (C / 8), 256), 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), BF(y_hi),
-                                                                                              BF(y_lo), B, H, W, C);
+    maxpool_fwd_kernel<<<ew_grid((long)B * (H / 2) * (W / 2) * (C / 8), 256), 256, 0, stream>>>(
+        CBF(x_hi), CBF(x_lo), BF(y_hi), BF(y_lo), reinterpret_cast<uint8_t*>(arg_out), B, H, W, C);
     LAUNCH_DONE();
 }
-extern "C" int gdrn_maxpool_bwd(const void* x_hi, const void* x_lo, const void* g_hi, const void* g_lo, void* dx_hi,
-                                void* dx_lo, int B, int H, int W, int C, void* stream_) {
+extern "C" int gdrn_maxpool_bwd(const void* arg_in, const void* g_hi, const void* g_lo, void* dx_hi, void* dx_lo, int B,
+                                int H, int W, int C, void* stream_) {
     STREAM;
-    maxpool_bwd_kernel<<<ew_grid((long)B * H * W * (C / 8), 256), 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), CBF(g_hi), CBF(g_lo),
-                                                                                    BF(dx_hi), BF(dx_lo), B, H, W, C);
+    maxpool_bwd_kernel<<<ew_grid((long)B * H * W * (C / 8), 256), 256, 0, stream>>>(
+        reinterpret_cast<const uint8_t*>(arg_in), CBF(g_hi), CBF(g_lo), BF(dx_hi), BF(dx_lo), B, H, W, C);
     LAUNCH_DONE();
 }
 extern "C" int gdrn_upsample2x_fwd(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int B, int H, int W, int C,
@@ -808,5 +930,18 @@ extern "C" int gdrn_leaky_bwd(const void* g_hi, const void* g_lo, const void* y_
                               void* stream_) {
     STREAM;
     leaky_bwd_kernel<<<ew_grid(n / 8, 256), 256, 0, stream>>>(CBF(g_hi), CBF(g_lo), CBF(y_hi), BF(o_hi), BF(o_lo), n / 8);
+    LAUNCH_DONE();
+}
+
+extern "C" int gdrn_bn_fwd(const void* x_hi, const void* x_lo, const void* r_hi, const void* r_lo, void* y_hi, void* y_lo,
+                           const float* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                           float* mean_out, float* invstd_out, long rows, int C, float eps, float momentum, int train, int relu,
+                           void* stream_) {
+    STREAM;
+    if (C % 8 || 256 % (C / 8)) return set_error(GDRN_ERR_ARG, "bn_fwd: unsupported C=%d", C);
+    if (train && stats == nullptr) return set_error(GDRN_ERR_ARG, "bn_fwd: batch statistics missing");
+    bn_fwd_kernel<<<ew_grid(rows * (C / 8), 256), 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), CBF(r_hi), CBF(r_lo), BF(y_hi), BF(y_lo),
+                                                                    stats, gamma, beta, running_mean, running_var, mean_out,
+                                                                    invstd_out, rows, C, eps, momentum, train, relu);
     LAUNCH_DONE();
 }

@@ -389,9 +389,14 @@ static int dispatch_gemm(const GemmParams& p, int block_n, int nsplit, cudaStrea
     return set_error(GDRN_ERR_ARG, "gemm: unsupported block_n=%d nsplit=%d", block_n, nsplit);
 }
 
-static int pick_block_n(int n_pad, int nsplit) {
+// Tile width: the widest BLOCK_N (fewest A re-reads, best smem-bandwidth ratio) that still yields >= ~0.75 waves of
+// CTAs on the 148 SMs; small-M layers (layer4, FC) fall back to narrower tiles instead of leaving SMs idle.
+static int pick_block_n(int n_pad, int nsplit, int num_m_tiles) {
     if (nsplit == 3) return (n_pad % 64 == 0) ? 64 : -1;  // 4 accumulators x 2 buffers x 64 columns = all of TMEM
-    if (nsplit == 1 && n_pad % 256 == 0) return 256;
+    const int want = (num_sms() * 3) / 4;
+    if (n_pad % 256 == 0 && num_m_tiles * (n_pad / 256) >= want) return 256;
+    if (n_pad % 128 == 0 && num_m_tiles * (n_pad / 128) >= want) return 128;
+    if (n_pad % 64 == 0 && num_m_tiles * (n_pad / 128) < num_sms() / 2) return 64;
     if (n_pad % 128 == 0) return 128;
     if (n_pad % 64 == 0) return 64;
     return -1;
@@ -418,7 +423,7 @@ extern "C" int gdrn_conv_fwd(const void* x_hi, const void* x_lo, const void* w_h
     if (TH > Ho) TH = Ho;
     const int TN = 128 / (Wo * TH);
     if (Ho % TH != 0) return set_error(GDRN_ERR_ARG, "conv_fwd: Ho=%d not divisible by tile rows %d", Ho, TH);
-    const int block_n = pick_block_n(Cout_pad, nsplit);
+    const int block_n = pick_block_n(Cout_pad, nsplit, (N * Ho * Wo + 127) / 128);
     if (block_n < 0) return set_error(GDRN_ERR_ARG, "conv_fwd: Cout_pad=%d must be a multiple of 64", Cout_pad);
 
     GemmParams p;
@@ -473,7 +478,7 @@ extern "C" int gdrn_gemm_fwd(const void* a_hi, const void* a_lo, const void* w_h
     if (nsplit == 3 && (a_lo == nullptr || w_lo == nullptr)) return set_error(GDRN_ERR_ARG, "gemm_fwd: lo planes missing");
     if (K % 64 != 0) return set_error(GDRN_ERR_ARG, "gemm_fwd: K=%d must be a multiple of 64", K);
     if (ldc % 8 != 0 || ldc < N) return set_error(GDRN_ERR_ARG, "gemm_fwd: bad ldc=%d", ldc);
-    const int block_n = pick_block_n(N_pad, nsplit);
+    const int block_n = pick_block_n(N_pad, nsplit, (M + 127) / 128);
     if (block_n < 0) return set_error(GDRN_ERR_ARG, "gemm_fwd: N_pad=%d must be a multiple of 64", N_pad);
     GemmParams p;
     memset(&p, 0, sizeof(p));

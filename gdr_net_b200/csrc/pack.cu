@@ -37,6 +37,54 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, __nv_bfloat16*
     }
 }
 
+// All per-step weight re-packs of the network in ONE launch: a device-resident job table (built once by the host,
+// pointers are stable) replaces ~100 tiny launches.  Jobs are padded to multiples of 256 elements so that each block
+// belongs to exactly one job (one binary search per block).
+struct PackJob {
+    const float* src;
+    __nv_bfloat16* dst_hi;
+    __nv_bfloat16* dst_lo;
+    long so, si, sr, ss;
+    long elem_begin;  // prefix sum of ceil256(opad * krow)
+    int O, I, KH, KW, opad, ipad, krow, flip;
+};
+
+__global__ void __launch_bounds__(256) pack_weight_batched_kernel(const PackJob* __restrict__ jobs, int njobs, long total_blocks) {
+    __shared__ PackJob job;
+    for (long blk = blockIdx.x; blk < total_blocks; blk += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const long e = blk * 256;
+            int lo = 0, hi = njobs - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (jobs[mid].elem_begin <= e) lo = mid; else hi = mid - 1;
+            }
+            job = jobs[lo];
+        }
+        __syncthreads();
+        const long idx = blk * 256 + threadIdx.x - job.elem_begin;
+        const long total = (long)job.opad * job.krow;
+        if (idx >= total) continue;
+        const int o = (int)(idx / job.krow);
+        const int col = (int)(idx - (long)o * job.krow);
+        const int tap = col / job.ipad;
+        const int i = col - tap * job.ipad;
+        float v = 0.f;
+        if (o < job.O && i < job.I && tap < job.KH * job.KW) {
+            int r = tap / job.KW, s2 = tap - (tap / job.KW) * job.KW;
+            if (job.flip) {
+                r = job.KH - 1 - r;
+                s2 = job.KW - 1 - s2;
+            }
+            v = __ldg(job.src + o * job.so + i * job.si + r * job.sr + s2 * job.ss);
+        }
+        const float h = bf16_round(v);
+        job.dst_hi[idx] = __float2bfloat16(h);
+        if (job.dst_lo != nullptr) job.dst_lo[idx] = __float2bfloat16(v - h);
+    }
+}
+
 // grad[o*so + i*si + r'*sr + s'*ss] (+)= sum_ks ws[ks][o*krow + tap*ipad + i]
 __global__ void unpack_wgrad_kernel(const float* __restrict__ ws, float* __restrict__ grad, int O, int I, int KH, int KW,
                                     int ipad, int krow_, int ksplit, long ks_stride, long so, long si, long sr, long ss, int flip,
@@ -138,6 +186,19 @@ extern "C" int gdrn_stem_im2col(const float* x, void* a_hi, void* a_lo, int B, i
     if (H % 2 || W % 2) return set_error(GDRN_ERR_ARG, "stem_im2col: H, W must be even");
     const long total = (long)B * (H / 2) * (W / 2) * 24;
     stem_im2col_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo, B, H, W);
+    GDRN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int gdrn_pack_weight_batched(const void* jobs_dev, int njobs, long total_blocks, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    static_assert(sizeof(PackJob) == 96, "PackJob layout is mirrored by the host (gdr_net_b200/engine.py)");
+    if (njobs <= 0) return 0;
+    long grid = total_blocks;
+    const long cap = (long)num_sms() * 16;
+    if (grid > cap) grid = cap;
+    pack_weight_batched_kernel<<<(int)grid, 256, 0, stream>>>(reinterpret_cast<const PackJob*>(jobs_dev), njobs, total_blocks);
     GDRN_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;

@@ -90,7 +90,38 @@ class Engine:
         return out
 
     def prepare_weights(self, need_dgrad: bool):
-        """fp32 parameters -> K-major bf16 (hi, lo) GEMM operands (re-done every step: weights change)."""
+        """fp32 parameters -> K-major bf16 (hi, lo) GEMM operands, re-done every step (weights change) by ONE batched
+        launch over a device-resident job table (rebuilt only if a parameter / buffer pointer moved)."""
+        import numpy as np
+
+        key = (need_dgrad, tuple(p.data_ptr() for _, p in self.named_params))
+        if getattr(self, "_pack_key", None) != key:
+            ops._pack_recorder = []
+            try:
+                self._prepare_weights_calls(need_dgrad)
+                self._pack_stem()
+                jobs = ops._pack_recorder
+            finally:
+                ops._pack_recorder = None
+            dt = np.dtype([("src", "<u8"), ("hi", "<u8"), ("lo", "<u8"), ("so", "<i8"), ("si", "<i8"), ("sr", "<i8"), ("ss", "<i8"),
+                           ("begin", "<i8"), ("O", "<i4"), ("I", "<i4"), ("KH", "<i4"), ("KW", "<i4"), ("opad", "<i4"),
+                           ("ipad", "<i4"), ("krow", "<i4"), ("flip", "<i4")])
+            assert dt.itemsize == 96
+            arr = np.zeros(len(jobs), dtype=dt)
+            begin = 0
+            for n, (src, out, O, I, KH, KW, opad, ipad, krow, so, si, sr, ss, flip) in enumerate(jobs):
+                arr[n] = (src.data_ptr(), out.hi_ptr, out.lo_ptr or 0, so, si, sr, ss, begin, O, I, KH, KW, opad, ipad, krow, flip)
+                begin += (opad * krow + 255) // 256 * 256
+            self._pack_jobs = torch.from_numpy(arr.view(np.uint8).copy()).to(self.dev)
+            self._pack_njobs, self._pack_blocks = len(jobs), begin // 256
+            self._pack_srcs = [j[0] for j in jobs]  # keep the sources alive
+            self._pack_key = key
+        with torch.no_grad():
+            torch.cat([self.model.pnp_net.fc_r.weight, self.model.pnp_net.fc_t.weight], 0, out=self.w_rt)
+            torch.cat([self.model.pnp_net.fc_r.bias, self.model.pnp_net.fc_t.bias], 0, out=self.b_rt)
+        C.gdrn_pack_weight_batched(self._pack_jobs.data_ptr(), self._pack_njobs, self._pack_blocks, _stream())
+
+    def _prepare_weights_calls(self, need_dgrad: bool):
         m, pl = self.model, self.planes
         wf, wd = self.wf, self.wd
         for key, conv in self._conv_modules():
@@ -106,8 +137,9 @@ class Engine:
         pn = m.pnp_net
         wf["fc1"] = ops.pack_linear(pn.fc1.weight, pl, out=wf.get("fc1"), nhwc_from=(128, 8, 8))
         wf["fc2"] = ops.pack_linear(pn.fc2.weight, pl, out=wf.get("fc2"))
-        self.w_rt = torch.cat([pn.fc_r.weight, pn.fc_t.weight], 0).contiguous()
-        self.b_rt = torch.cat([pn.fc_r.bias, pn.fc_t.bias], 0).contiguous()
+        if not hasattr(self, "w_rt"):
+            self.w_rt = torch.empty(pn.fc_r.out_features + 3, pn.fc_r.in_features, device=self.dev)
+            self.b_rt = torch.empty(pn.fc_r.out_features + 3, device=self.dev)
         wf["fc_rt"] = ops.pack_linear(self.w_rt, pl, out=wf.get("fc_rt"))
         if need_dgrad:
             wd["fc1"] = ops.pack_linear(pn.fc1.weight, pl, out=wd.get("fc1"), nhwc_from=(128, 8, 8), transpose=True)
@@ -118,7 +150,7 @@ class Engine:
         """7x7 stem weight [64][3][7][7] -> [64][192] with k = (r*7+s)*3 + c (matches gdrn_stem_im2col)."""
         w = self.model.backbone.conv1.weight
         out = self.wf.get("stem") or PT((64, 192), self.planes, device=self.dev)
-        C.gdrn_pack_weight(w.data_ptr(), out.hi_ptr, out.lo_ptr, 64, 3, 7, 7, 64, 3, 192, 147, 49, 7, 1, 0, _stream())
+        ops._pack(w, out, 64, 3, 7, 7, 64, 3, 192, 147, 49, 7, 1, 0)
         self.wf["stem"] = out
 
     # ------------------------------------------------------------------------------------------ building blocks
@@ -127,11 +159,14 @@ class Engine:
         Cc = mod.num_features
         count = u.numel() // Cc
         mom = mod.momentum if mod.momentum is not None else 0.1
-        ops.bn_finalize(st.stats if train_bn else None, mod.weight, mod.bias, mod.running_mean, mod.running_var, st.scale,
-                        st.shift, st.mean, st.invstd, Cc, count, mod.eps, mom, train_bn)
         if train_bn and mod.num_batches_tracked is not None:
-            mod.num_batches_tracked += 1
-        return ops.bn_act(u, st.scale, st.shift, relu, res=res)
+            self._nbt.append(mod.num_batches_tracked)
+        y = ops.like(u)
+        C.gdrn_bn_fwd(u.hi_ptr, u.lo_ptr, res.hi_ptr if res else None, res.lo_ptr if res else None, y.hi_ptr, y.lo_ptr,
+                      ops.ptr(st.stats) if train_bn else None, mod.weight.data_ptr(), mod.bias.data_ptr(),
+                      mod.running_mean.data_ptr(), mod.running_var.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), count, Cc,
+                      float(mod.eps), float(mom), int(train_bn), int(relu), _stream())
+        return y
 
     def _conv_bn(self, x: PT, ckey: str, conv, bkey: str, relu: bool, train_bn: bool, res: Optional[PT] = None,
                  wkey: Optional[str] = None, kind: str = "conv"):
@@ -172,7 +207,7 @@ class Engine:
         B = x.shape[0]
         assert x.shape[1:] == (3, 256, 256), x.shape
         self.prepare_weights(need_dgrad=do_loss)
-        self._pack_stem()
+        self._nbt = []
         if train_bn:
             self.stats_all.zero_()
         S = dict(B=B, train_bn=train_bn) if do_loss else None
@@ -183,10 +218,12 @@ class Engine:
         st0 = self.bn["backbone.bn1"]
         u0 = ops.gemm_fwd(a_col, self.wf["stem"], 64, stats=st0.stats if train_bn else None).view(B, 128, 128, 64)
         a0 = self._bn_fwd("backbone.bn1", u0, True, train_bn)
-        cur = ops.maxpool_fwd(a0)
         if S is not None:
-            S["stem"] = dict(a_col=a_col, u0=u0, a0=a0)
+            cur, pool_arg = ops.maxpool_fwd(a0, want_arg=True)
+            S["stem"] = dict(a_col=a_col, u0=u0, a0=a0, pool_arg=pool_arg)
             S["blocks"] = []
+        else:
+            cur = ops.maxpool_fwd(a0)
         for li in range(1, 5):
             for bi, blk in enumerate(getattr(m.backbone, f"layer{li}")):
                 p = f"backbone.layer{li}.{bi}"
@@ -218,6 +255,8 @@ class Engine:
                 S["head"].append(dict(ci=ci, bi=bi, up=up, x_in=cur, u=u, y=y))
             cur = y
         head_in = cur  # [B,64,64,256]
+        if self._nbt:
+            torch._foreach_add_(self._nbt, 1)  # all BatchNorm num_batches_tracked counters in one launch
         logits = torch.empty(B * 4096, 72, device=dev)
         ops.conv_fwd(head_in, self.wf["rot_head_net.features.23"], 69, 1, 1, 1, 0, out_f32=logits, bias=hf[23].bias, ldc=72,
                      want_planes=False)
@@ -418,7 +457,7 @@ class Engine:
                 self.grad_hook(self, p[:-2])  # all gradients of backbone.layerN are final
         g_pool = ops.add2(ga, gb)
         St = S["stem"]
-        g_a0 = ops.maxpool_bwd(St["a0"], g_pool)
+        g_a0 = ops.maxpool_bwd(St["pool_arg"], g_pool)
         du0, _ = self._bn_bwd("backbone.bn1", g_a0, None, St["a0"], St["u0"])
         buf, ks, kss = ops.gemm_wgrad(du0.view(B * 128 * 128, 64), St["a_col"], self.ws)
         # ws rows [64][192] with k = (r*7+s)*3 + c  ->  OIHW [64][3][7][7]

@@ -83,6 +83,16 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
+_pack_recorder = None  # when a list: pack calls are recorded as job tuples instead of launched (Engine batches them)
+
+
+def _pack(src: torch.Tensor, out: "PT", O, I, KH, KW, opad, ipad, krow, so, si, sr, ss, flip):
+    if _pack_recorder is not None:
+        _pack_recorder.append((src, out, O, I, KH, KW, opad, ipad, krow, so, si, sr, ss, flip))
+        return
+    C.gdrn_pack_weight(src.data_ptr(), out.hi_ptr, out.lo_ptr, O, I, KH, KW, opad, ipad, krow, so, si, sr, ss, flip, _stream())
+
+
 # ---------------------------------------------------------------------------------------------
 # weight packing
 # ---------------------------------------------------------------------------------------------
@@ -93,8 +103,7 @@ def pack_conv_fwd(w: torch.Tensor, planes: int, out: PT | None = None, ipad: int
     opad = _round_up(O, 64)
     krow = KH * KW * ipad
     out = out or PT((opad, krow), planes, device=w.device)
-    C.gdrn_pack_weight(w.data_ptr(), out.hi_ptr, out.lo_ptr, O, I, KH, KW, opad, ipad, krow, I * KH * KW, KH * KW, KW, 1, 0,
-                       _stream())
+    _pack(w, out, O, I, KH, KW, opad, ipad, krow, I * KH * KW, KH * KW, KW, 1, 0)
     return out
 
 
@@ -105,8 +114,7 @@ def pack_conv_dgrad(w: torch.Tensor, planes: int, out: PT | None = None) -> PT:
     krow = KH * KW * ipad
     out = out or PT((opad, krow), planes, device=w.device)
     # rows = input channels (stride KH*KW), cols = output channels (stride I*KH*KW)
-    C.gdrn_pack_weight(w.data_ptr(), out.hi_ptr, out.lo_ptr, I, O, KH, KW, opad, ipad, krow, KH * KW, I * KH * KW, KW, 1, 1,
-                       _stream())
+    _pack(w, out, I, O, KH, KW, opad, ipad, krow, KH * KW, I * KH * KW, KW, 1, 1)
     return out
 
 
@@ -117,8 +125,7 @@ def pack_deconv_fwd(wt: torch.Tensor, planes: int, out: PT | None = None) -> PT:
     opad, ipad = _round_up(O, 64), _round_up(I, 64)
     krow = KH * KW * ipad
     out = out or PT((opad, krow), planes, device=wt.device)
-    C.gdrn_pack_weight(wt.data_ptr(), out.hi_ptr, out.lo_ptr, O, I, KH, KW, opad, ipad, krow, KH * KW, O * KH * KW, KW, 1, 1,
-                       _stream())
+    _pack(wt, out, O, I, KH, KW, opad, ipad, krow, KH * KW, O * KH * KW, KW, 1, 1)
     return out
 
 
@@ -128,8 +135,7 @@ def pack_deconv_dgrad(wt: torch.Tensor, planes: int, out: PT | None = None) -> P
     opad, ipad = _round_up(I, 64), _round_up(O, 64)
     krow = KH * KW * ipad
     out = out or PT((opad, krow), planes, device=wt.device)
-    C.gdrn_pack_weight(wt.data_ptr(), out.hi_ptr, out.lo_ptr, I, O, KH, KW, opad, ipad, krow, O * KH * KW, KH * KW, KW, 1, 0,
-                       _stream())
+    _pack(wt, out, I, O, KH, KW, opad, ipad, krow, O * KH * KW, KH * KW, KW, 1, 0)
     return out
 
 
@@ -145,23 +151,23 @@ def pack_linear(w: torch.Tensor, planes: int, out: PT | None = None, nhwc_from: 
             # view as OIHW [N][C][H][W] -> rows N, cols (h, w, c)
             opad = _round_up(N, 64)
             out = out or PT((opad, K), planes, device=w.device)
-            C.gdrn_pack_weight(w.data_ptr(), out.hi_ptr, out.lo_ptr, N, Cc, H, W, opad, Cc, K, K, H * W, W, 1, 0, _stream())
+            _pack(w, out, N, Cc, H, W, opad, Cc, K, K, H * W, W, 1, 0)
             return out
         # dgrad operand [K' = (h, w, c)][N]: dst viewed as [tap = h*W+w][c][n] == pack with O = taps, "taps" = C, I = N
         taps = H * W
         npad = _round_up(N, 64)
         assert npad == N
         out = out or PT((K, N), planes, device=w.device)
-        C.gdrn_pack_weight(w.data_ptr(), out.hi_ptr, out.lo_ptr, taps, N, Cc, 1, taps, N, Cc * N, 1, K, taps, 0, 0, _stream())
+        _pack(w, out, taps, N, Cc, 1, taps, N, Cc * N, 1, K, taps, 0, 0)
         return out
     if not transpose:
         opad = _round_up(N, 64)
         out = out or PT((opad, K), planes, device=w.device)
-        C.gdrn_pack_weight(w.data_ptr(), out.hi_ptr, out.lo_ptr, N, K, 1, 1, opad, K, K, K, 1, 0, 0, 0, _stream())
+        _pack(w, out, N, K, 1, 1, opad, K, K, K, 1, 0, 0, 0)
     else:
         opad, ipad = _round_up(K, 64), _round_up(N, 64)
         out = out or PT((opad, ipad), planes, device=w.device)
-        C.gdrn_pack_weight(w.data_ptr(), out.hi_ptr, out.lo_ptr, K, N, 1, 1, opad, ipad, ipad, 1, K, 0, 0, 0, _stream())
+        _pack(w, out, K, N, 1, 1, opad, ipad, ipad, 1, K, 0, 0, 0)
     return out
 
 
@@ -276,17 +282,18 @@ def bn_bwd(ga: PT, gb: PT | None, y: PT | None, u: PT, mean, invstd, gamma, sums
     return du, gout
 
 
-def maxpool_fwd(x: PT) -> PT:
+def maxpool_fwd(x: PT, want_arg: bool = False):
     B, H, W, Cc = x.shape
     out = like(x, (B, H // 2, W // 2, Cc))
-    C.gdrn_maxpool_fwd(x.hi_ptr, x.lo_ptr, out.hi_ptr, out.lo_ptr, B, H, W, Cc, _stream())
-    return out
+    arg = torch.empty((B, H // 2, W // 2, Cc), dtype=torch.uint8, device=x.buf.device) if want_arg else None
+    C.gdrn_maxpool_fwd(x.hi_ptr, x.lo_ptr, out.hi_ptr, out.lo_ptr, ptr(arg), B, H, W, Cc, _stream())
+    return (out, arg) if want_arg else out
 
 
-def maxpool_bwd(x: PT, g: PT) -> PT:
-    B, H, W, Cc = x.shape
-    out = like(x)
-    C.gdrn_maxpool_bwd(x.hi_ptr, x.lo_ptr, g.hi_ptr, g.lo_ptr, out.hi_ptr, out.lo_ptr, B, H, W, Cc, _stream())
+def maxpool_bwd(arg: torch.Tensor, g: PT) -> PT:
+    B, Ho, Wo, Cc = g.shape
+    out = like(g, (B, 2 * Ho, 2 * Wo, Cc))
+    C.gdrn_maxpool_bwd(arg.data_ptr(), g.hi_ptr, g.lo_ptr, out.hi_ptr, out.lo_ptr, B, 2 * Ho, 2 * Wo, Cc, _stream())
     return out
 
 

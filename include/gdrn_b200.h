@@ -59,6 +59,8 @@ int gdrn_gemm_wgrad(const void* dy_hi, const void* dy_lo, const void* x_hi, cons
  * Source layouts: Conv2d OIHW, ConvTranspose2d IOHW, Linear [out][in] (state_dict of the reference). */
 int gdrn_pack_weight(const float* src, void* dst_hi, void* dst_lo, int O, int I, int KH, int KW, int opad, int ipad,
                      int krow, long so, long si, long sr, long ss, int flip, void* stream);
+/* all per-step re-packs in one launch; jobs_dev = device array of 96-byte PackJob records (csrc/pack.cu) */
+int gdrn_pack_weight_batched(const void* jobs_dev, int njobs, long total_blocks, void* stream);
 int gdrn_unpack_wgrad(const float* ws, float* grad, int O, int I, int KH, int KW, int ipad, int krow, int ksplit, long ks_stride,
                       long so, long si, long sr, long ss, int flip, int accumulate, void* stream);
 /* im2col of the 7x7/2 stem: x NCHW fp32 [B,3,H,W] -> [B*H/2*W/2][192] bf16 planes, k = (r*7+s)*3 + c */
@@ -69,6 +71,11 @@ int gdrn_stem_im2col(const float* x, void* a_hi, void* a_lo, int B, int H, int W
 int gdrn_bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
                      float* scale, float* shift, float* mean_out, float* invstd_out, int C, float count, float eps,
                      float momentum, int train, void* stream);
+/* finalize + apply in one kernel (what the engine uses): batch statistics from the conv epilogue -> y, running stats */
+int gdrn_bn_fwd(const void* x_hi, const void* x_lo, const void* r_hi, const void* r_lo, void* y_hi, void* y_lo,
+                const float* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                float* mean_out, float* invstd_out, long rows, int C, float eps, float momentum, int train, int relu,
+                void* stream);
 int gdrn_bn_act(const void* x_hi, const void* x_lo, const void* r_hi, const void* r_lo, void* y_hi, void* y_lo,
                 const float* scale, const float* shift, long rows, int C, int relu, void* stream);
 int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_hi, const void* gb_lo, const void* y_hi,
@@ -78,9 +85,11 @@ int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_hi, const v
 
 /* ---- MaxPool2d(3,2,1) resnet_backbone.py:72; UpsamplingBilinear2d(x2) cdpn_rot_head_region.py:102;
  * zero insertion (stride-2 transposed convs); GroupNorm(32)+ReLU conv_pnp_net.py:76-80 */
-int gdrn_maxpool_fwd(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int B, int H, int W, int C, void* stream);
-int gdrn_maxpool_bwd(const void* x_hi, const void* x_lo, const void* g_hi, const void* g_lo, void* dx_hi, void* dx_lo,
-                     int B, int H, int W, int C, void* stream);
+/* arg_out / arg_in: uint8 [B,H/2,W/2,C] window-local arg-max codes (first maximum, like ATen's saved indices) */
+int gdrn_maxpool_fwd(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, void* arg_out, int B, int H, int W, int C,
+                     void* stream);
+int gdrn_maxpool_bwd(const void* arg_in, const void* g_hi, const void* g_lo, void* dx_hi, void* dx_lo, int B, int H, int W,
+                     int C, void* stream);
 int gdrn_upsample2x_fwd(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int B, int H, int W, int C, void* stream);
 int gdrn_upsample2x_bwd(const void* g_hi, const void* g_lo, void* dx_hi, void* dx_lo, int B, int H, int W, int C, void* stream);
 int gdrn_zero_insert(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int B, int H, int W, int C, int mode,

@@ -249,12 +249,12 @@ def test_maxpool_upsample_zero_insert(planes):
     tol = 8e-3 if planes == 1 else 3e-5
     # maxpool
     y_ref = F.max_pool2d(xf, 3, 2, 1)
-    Y = ops.maxpool_fwd(X)
+    Y, ARG = ops.maxpool_fwd(X, want_arg=True)
     assert _rel(Y.float().permute(0, 3, 1, 2), y_ref) < tol
     gy = torch.randn_like(y_ref)
     GY = _nhwc(gy, planes)
     (gx_ref,) = torch.autograd.grad(y_ref, xf, GY.float().permute(0, 3, 1, 2))
-    GX = ops.maxpool_bwd(X, GY)
+    GX = ops.maxpool_bwd(ARG, GY)
     assert _rel(GX.float().permute(0, 3, 1, 2), gx_ref) < tol
     # bilinear x2, align_corners=True
     xf2 = X.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
