@@ -477,6 +477,49 @@ def out_trans_first(t):
     return t[0]
 
 
+class GraphedTrainStep:
+    """One CUDA graph for the whole train step (forward + losses + backward [+ bucketed all-reduce]): ~560 kernel
+    launches are replayed with a single cudaGraphLaunch, removing the per-launch host cost of the Python/ctypes
+    orchestration.  Inputs live in static buffers; call with new tensors to copy them in (device-side copies)."""
+
+    def __init__(self, engine: "Engine", x: torch.Tensor, aux: dict, train_bn: bool = True, warmup: int = 2, after_backward=None):
+        self.engine = engine
+        self.x = x.clone()
+        self.aux = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in aux.items()}
+        if self.aux.get("sym_infos") is not None:
+            raise NotImplementedError("graphed step: symmetric PM loss (host-side symmetry packing) is not capturable yet")
+        self.gw = torch.ones(8, device=x.device)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):  # also sizes the split-K workspace and uploads the pack job table
+                engine.forward(self.x, self.aux, train_bn=train_bn, do_loss=True)
+                engine.backward(self.gw)
+                if after_backward is not None:
+                    after_backward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            res = engine.forward(self.x, self.aux, train_bn=train_bn, do_loss=True)
+            engine.backward(self.gw)
+            if after_backward is not None:
+                after_backward()
+        self.losses, self.vis, self.rot, self.trans = res["losses"], res["vis"], res["rot"], res["trans"]
+
+    def __call__(self, x: Optional[torch.Tensor] = None, aux: Optional[dict] = None, grad_losses: Optional[torch.Tensor] = None):
+        if x is not None:
+            self.x.copy_(x, non_blocking=True)
+        if aux is not None:
+            for k, v in aux.items():
+                if isinstance(v, torch.Tensor):
+                    self.aux[k].copy_(v, non_blocking=True)
+        if grad_losses is not None:
+            self.gw.copy_(grad_losses)
+        self.graph.replay()
+        return self.losses
+
+
 class _GDRNFunction(torch.autograd.Function):
     """Autograd boundary: forward + losses and the hand-written backward are both ours; autograd only routes the
     8 loss gradients in and the 148 parameter gradients out (so optimizers / DDP / GradScaler keep working)."""
