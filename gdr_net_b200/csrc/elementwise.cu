@@ -53,6 +53,13 @@ static inline int ew_grid(long total, int block) {
     const long cap = (long)num_sms() * 8;
     return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
+// for kernels with a per-thread prologue (per-channel coefficients): at least `per_thread` items per thread so the
+// prologue is amortised on small tensors (a 4 MB layer4 tensor must not pay 300K threads x 16 coefficient loads)
+static inline int ew_grid_amortised(long total, int block, int per_thread) {
+    long g = (total + (long)block * per_thread - 1) / ((long)block * per_thread);
+    const long cap = (long)num_sms() * 8;
+    return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
 
 // ------------------------------------------------------------------------------------------------
 // BatchNorm statistics -> per-channel scale/shift (+ running-stat update)
@@ -89,72 +96,101 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
     }
 }
 
-// y = [relu](x * scale[c] + shift[c] [+ res]).  blockDim (256) is a multiple of C/8, so a thread always sees the same
-// 8 channels: coefficients live in registers; two independent 16-byte loads per tensor are kept in flight.
-__global__ void __launch_bounds__(256) bn_act_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo,
-                                                     const bf16* __restrict__ r_hi, const bf16* __restrict__ r_lo,
-                                                     bf16* __restrict__ y_hi, bf16* __restrict__ y_lo,
-                                                     const float* __restrict__ scale, const float* __restrict__ shift, long rows,
-                                                     int C, int relu) {
-    const int cg = C / 8;
-    const long total = rows * cg;
-    const long stride = (long)gridDim.x * blockDim.x;
-    const long first = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    const int c0 = (int)(first % cg) * 8;
-    float sc[8], sh[8];
+// ------------------------------------------------------------------------------------------------
+// BatchNorm forward.  Design notes (ncu, profiles/r1_bn_kernels.txt): the first version kept unpacked fp32 arrays live
+// across the loads (115 registers -> 2 blocks/SM -> 24 % warps active -> 29 % of DRAM peak).  Now the 16-byte loads
+// stay PACKED in registers while in flight (4 per tensor), per-channel coefficients live in shared memory, and the
+// kernels are templated on "has lo plane" / "has residual" so unused operands cost nothing.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld16(const bf16* p, long off8) { return __ldg(reinterpret_cast<const uint4*>(p) + off8); }
+__device__ __forceinline__ void unpack8_lo(const uint4& q, float (&f)[8]) {  // adds the lo plane
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        sc[j] = __ldg(scale + c0 + j);
-        sh[j] = __ldg(shift + c0 + j);
-    }
-    for (long idx = first; idx < total; idx += 2 * stride) {
-        const long idx2 = idx + stride;
-        const bool two = idx2 < total;
-        float v[8], w[8], r[8], q[8];
-        load8(x_hi, x_lo, idx, v);
-        if (two) load8(x_hi, x_lo, idx2, w);
-        if (r_hi != nullptr) {
-            load8(r_hi, r_lo, idx, r);
-            if (two) load8(r_hi, r_lo, idx2, q);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            v[j] = fmaf(v[j], sc[j], sh[j]);
-            w[j] = fmaf(w[j], sc[j], sh[j]);
-            if (r_hi != nullptr) {
-                v[j] += r[j];
-                w[j] += q[j];
-            }
-            if (relu) {
-                v[j] = fmaxf(v[j], 0.f);
-                w[j] = fmaxf(w[j], 0.f);
-            }
-        }
-        store8(y_hi, y_lo, idx, v);
-        if (two) store8(y_hi, y_lo, idx2, w);
+    for (int j = 0; j < 4; ++j) {
+        float a, b;
+        unpack_lo2(w[j], a, b);
+        f[2 * j] += a;
+        f[2 * j + 1] += b;
     }
 }
 
-// BatchNorm forward in ONE kernel: every thread derives scale/shift of its 8 channels from the conv epilogue's
-// (sum, sum^2) statistics (train) or the running statistics (eval); block 0 also stores mean/invstd for the backward
-// pass and updates the running statistics (momentum, unbiased variance) like nn.BatchNorm2d.
-__global__ void __launch_bounds__(256) bn_fwd_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo,
-                                                     const bf16* __restrict__ r_hi, const bf16* __restrict__ r_lo,
-                                                     bf16* __restrict__ y_hi, bf16* __restrict__ y_lo,
-                                                     const float* __restrict__ stats, const float* __restrict__ gamma,
-                                                     const float* __restrict__ beta, float* running_mean, float* running_var,
-                                                     float* __restrict__ mean_out, float* __restrict__ invstd_out, long rows, int C,
-                                                     float eps, float momentum, int train, int relu) {
-    const int cg = C / 8;
-    const long total = rows * cg;
+// y = [relu](x * sc[c] + sh[c] [+ res]);  s_sc / s_sh: shared memory [C]
+template <bool LO, bool RES>
+__device__ __forceinline__ void bn_apply_loop(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo,
+                                              const bf16* __restrict__ r_hi, const bf16* __restrict__ r_lo,
+                                              bf16* __restrict__ y_hi, bf16* __restrict__ y_lo, const float* s_sc,
+                                              const float* s_sh, long total, int cg, int relu) {
     const long stride = (long)gridDim.x * blockDim.x;
     const long first = blockIdx.x * (long)blockDim.x + threadIdx.x;
     const int c0 = (int)(first % cg) * 8;
-    const float count = (float)rows;
-    float sc[8], sh[8];
+    for (long idx = first; idx < total; idx += 4 * stride) {
+        uint4 xr[4], xl[4], rr[4], rl[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = c0 + j;
+        for (int t = 0; t < 4; ++t) {
+            const long it = idx + t * stride;
+            if (it < total) {
+                xr[t] = ld16(x_hi, it);
+                if (LO) xl[t] = ld16(x_lo, it);
+                if (RES) {
+                    rr[t] = ld16(r_hi, it);
+                    if (LO) rl[t] = ld16(r_lo, it);
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const long it = idx + t * stride;
+            if (it < total) {
+                float v[8];
+                unpack8(xr[t], v);
+                if (LO) unpack8_lo(xl[t], v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], s_sc[c0 + j], s_sh[c0 + j]);
+                if (RES) {
+                    float r[8];
+                    unpack8(rr[t], r);
+                    if (LO) unpack8_lo(rl[t], r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] += r[j];
+                }
+                if (relu) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                store8(y_hi, LO ? y_lo : nullptr, it, v);
+            }
+        }
+    }
+}
+
+template <bool LO, bool RES>
+__global__ void __launch_bounds__(256, 4) bn_act_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo,
+                                                        const bf16* __restrict__ r_hi, const bf16* __restrict__ r_lo,
+                                                        bf16* __restrict__ y_hi, bf16* __restrict__ y_lo,
+                                                        const float* __restrict__ scale, const float* __restrict__ shift,
+                                                        long rows, int C, int relu) {
+    __shared__ float s_sc[512], s_sh[512];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        s_sc[c] = scale[c];
+        s_sh[c] = shift[c];
+    }
+    __syncthreads();
+    bn_apply_loop<LO, RES>(x_hi, x_lo, r_hi, r_lo, y_hi, y_lo, s_sc, s_sh, rows * (C / 8), C / 8, relu);
+}
+
+// finalize + apply in one kernel: scale/shift from the conv epilogue's (sum, sum^2) (train) or the running statistics
+// (eval); block 0 stores mean/invstd for backward and updates the running statistics like nn.BatchNorm2d.
+template <bool LO, bool RES>
+__global__ void __launch_bounds__(256, 4) bn_fwd_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo,
+                                                        const bf16* __restrict__ r_hi, const bf16* __restrict__ r_lo,
+                                                        bf16* __restrict__ y_hi, bf16* __restrict__ y_lo,
+                                                        const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float* running_mean, float* running_var,
+                                                        float* __restrict__ mean_out, float* __restrict__ invstd_out, long rows,
+                                                        int C, float eps, float momentum, int train, int relu) {
+    __shared__ float s_sc[512], s_sh[512];
+    const float count = (float)rows;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float mean, var;
         if (train) {
             const double m = (double)stats[c] / count;
@@ -167,9 +203,10 @@ __global__ void __launch_bounds__(256) bn_fwd_kernel(const bf16* __restrict__ x_
             var = running_var[c];
         }
         const float invstd = rsqrtf(var + eps);
-        sc[j] = gamma[c] * invstd;
-        sh[j] = beta[c] - mean * sc[j];
-        if (blockIdx.x == 0 && threadIdx.x < cg) {
+        const float sc = gamma[c] * invstd;
+        s_sc[c] = sc;
+        s_sh[c] = beta[c] - mean * sc;
+        if (blockIdx.x == 0) {
             if (mean_out != nullptr) {
                 mean_out[c] = mean;
                 invstd_out[c] = invstd;
@@ -181,32 +218,8 @@ __global__ void __launch_bounds__(256) bn_fwd_kernel(const bf16* __restrict__ x_
             }
         }
     }
-    for (long idx = first; idx < total; idx += 2 * stride) {
-        const long idx2 = idx + stride;
-        const bool two = idx2 < total;
-        float v[8], w[8], r[8], q[8];
-        load8(x_hi, x_lo, idx, v);
-        if (two) load8(x_hi, x_lo, idx2, w);
-        if (r_hi != nullptr) {
-            load8(r_hi, r_lo, idx, r);
-            if (two) load8(r_hi, r_lo, idx2, q);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            v[j] = fmaf(v[j], sc[j], sh[j]);
-            w[j] = fmaf(w[j], sc[j], sh[j]);
-            if (r_hi != nullptr) {
-                v[j] += r[j];
-                w[j] += q[j];
-            }
-            if (relu) {
-                v[j] = fmaxf(v[j], 0.f);
-                w[j] = fmaxf(w[j], 0.f);
-            }
-        }
-        store8(y_hi, y_lo, idx, v);
-        if (two) store8(y_hi, y_lo, idx2, w);
-    }
+    __syncthreads();
+    bn_apply_loop<LO, RES>(x_hi, x_lo, r_hi, r_lo, y_hi, y_lo, s_sc, s_sh, rows * (C / 8), C / 8, relu);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -412,7 +425,29 @@ __global__ void zero_insert_kernel(const bf16* __restrict__ x_hi, const bf16* __
 // ------------------------------------------------------------------------------------------------
 constexpr int kBnBwdThreads = 256;
 
-__global__ void __launch_bounds__(kBnBwdThreads) bn_bwd_reduce_kernel(
+// masked gradient of one 8-channel group: g = (ga [+ gb]) * [y > 0]
+template <bool LO>
+__device__ __forceinline__ void masked_grad(const uint4& gah, const uint4& gal, const uint4& gbh, const uint4& gbl, const uint4& yh,
+                                            bool has_gb, bool has_y, float (&g)[8]) {
+    unpack8(gah, g);
+    if (LO) unpack8_lo(gal, g);
+    if (has_gb) {
+        float t[8];
+        unpack8(gbh, t);
+        if (LO) unpack8_lo(gbl, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] += t[j];
+    }
+    if (has_y) {
+        float y[8];
+        unpack8(yh, y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = y[j] > 0.f ? g[j] : 0.f;
+    }
+}
+
+template <bool LO>
+__global__ void __launch_bounds__(kBnBwdThreads, 3) bn_bwd_reduce_kernel(
     const bf16* __restrict__ ga_hi, const bf16* __restrict__ ga_lo, const bf16* __restrict__ gb_hi,
     const bf16* __restrict__ gb_lo, const bf16* __restrict__ y_hi, const bf16* __restrict__ u_hi,
     const bf16* __restrict__ u_lo, const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -422,54 +457,58 @@ __global__ void __launch_bounds__(kBnBwdThreads) bn_bwd_reduce_kernel(
     const int rpb = kBnBwdThreads / cg;  // cg in {8,16,32,64}: always divides 256
     const int g = threadIdx.x % cg;
     const int rl = threadIdx.x / cg;
-    float s0[8], s1[8], mu[8], is[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        s0[j] = 0.f;
-        s1[j] = 0.f;
-        mu[j] = mean[g * 8 + j];
-        is[j] = invstd[g * 8 + j];
+    __shared__ float s_mu[512], s_is[512];
+    __shared__ float red[2][kBnBwdThreads][8 + 1];
+    for (int c = threadIdx.x; c < C; c += kBnBwdThreads) {
+        s_mu[c] = mean[c];
+        s_is[c] = invstd[c];
     }
-    const long rstride = (long)gridDim.x * rpb;
-    for (long r0 = (long)blockIdx.x * rpb + rl; r0 < rows; r0 += 4 * rstride) {
-        float gv[4][8], u[4][8], y[4][8];
+    __syncthreads();
+    const bool has_gb = gb_hi != nullptr, has_y = y_hi != nullptr;
+    float s0[8], s1[8];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {  // all loads first (memory-level parallelism), then the math
+    for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
+    const long rstride = (long)gridDim.x * rpb;
+    for (long r0 = (long)blockIdx.x * rpb + rl; r0 < rows; r0 += 2 * rstride) {
+        uint4 gah[2], gal[2], gbh[2], gbl[2], yh[2], uh[2], ul[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
             const long r = r0 + t * rstride;
             if (r < rows) {
                 const long off = r * cg + g;
-                load8(ga_hi, ga_lo, off, gv[t]);
-                load8(u_hi, u_lo, off, u[t]);
-                if (y_hi != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(y_hi) + off), y[t]);
+                gah[t] = ld16(ga_hi, off);
+                uh[t] = ld16(u_hi, off);
+                if (has_y) yh[t] = ld16(y_hi, off);
+                if (has_gb) gbh[t] = ld16(gb_hi, off);
+                if (LO) {
+                    gal[t] = ld16(ga_lo, off);
+                    ul[t] = ld16(u_lo, off);
+                    if (has_gb) gbl[t] = ld16(gb_lo, off);
+                }
             }
         }
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
+        for (int t = 0; t < 2; ++t) {
             const long r = r0 + t * rstride;
             if (r < rows) {
-                if (gb_hi != nullptr) {
-                    float tb[8];
-                    load8(gb_hi, gb_lo, r * cg + g, tb);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) gv[t][j] += tb[j];
-                }
+                float gv[8], u[8];
+                masked_grad<LO>(gah[t], gal[t], gbh[t], gbl[t], yh[t], has_gb, has_y, gv);
+                unpack8(uh[t], u);
+                if (LO) unpack8_lo(ul[t], u);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float gg = (y_hi == nullptr || y[t][j] > 0.f) ? gv[t][j] : 0.f;
-                    s0[j] += gg;
-                    s1[j] = fmaf(gg, (u[t][j] - mu[j]) * is[j], s1[j]);
+                    s0[j] += gv[j];
+                    s1[j] = fmaf(gv[j], (u[j] - s_mu[g * 8 + j]) * s_is[g * 8 + j], s1[j]);
                 }
             }
         }
     }
-    __shared__ float red[2][kBnBwdThreads][8 + 1];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         red[0][threadIdx.x][j] = s0[j];
         red[1][threadIdx.x][j] = s1[j];
     }
     __syncthreads();
-    // thread t < 2*C: which = t / C, channel = t % C
     for (int t = threadIdx.x; t < 2 * C; t += kBnBwdThreads) {
         const int which = t / C, c = t % C;
         const int gg = c / 8, j = c % 8;
@@ -479,78 +518,71 @@ __global__ void __launch_bounds__(kBnBwdThreads) bn_bwd_reduce_kernel(
     }
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
+// du = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) = k1*g + k2*u + k3 with per-channel constants (shared memory)
+template <bool LO>
+__global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(
     const bf16* __restrict__ ga_hi, const bf16* __restrict__ ga_lo, const bf16* __restrict__ gb_hi,
     const bf16* __restrict__ gb_lo, const bf16* __restrict__ y_hi, const bf16* __restrict__ u_hi,
     const bf16* __restrict__ u_lo, const float* __restrict__ mean, const float* __restrict__ invstd,
     const float* __restrict__ gamma, const float* __restrict__ sums, bf16* __restrict__ du_hi, bf16* __restrict__ du_lo,
     bf16* __restrict__ gout_hi, bf16* __restrict__ gout_lo, float* __restrict__ dgamma, float* __restrict__ dbeta, long rows,
     int C, int train) {
+    __shared__ float s_k1[512], s_k2[512], s_k3[512];
     const int cg = C / 8;
     const long total = rows * cg;
     const float inv_n = 1.f / (float)rows;
-    if (blockIdx.x == 0 && dgamma != nullptr) {
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float is = invstd[c];
+        const float k1 = gamma[c] * is;
+        float k2 = 0.f, k3 = 0.f;
+        if (train) {
+            const float m0 = sums[c] * inv_n, m1 = sums[C + c] * inv_n;
+            k2 = -k1 * is * m1;
+            k3 = k1 * (mean[c] * is * m1 - m0);
+        }
+        s_k1[c] = k1;
+        s_k2[c] = k2;
+        s_k3[c] = k3;
+        if (blockIdx.x == 0 && dgamma != nullptr) {
             dbeta[c] = sums[c];
             dgamma[c] = sums[C + c];
         }
     }
+    __syncthreads();
+    const bool has_gb = gb_hi != nullptr, has_y = y_hi != nullptr, has_gout = gout_hi != nullptr;
     const long stride = (long)gridDim.x * blockDim.x;
     const long first = blockIdx.x * (long)blockDim.x + threadIdx.x;
     const int c0 = (int)(first % cg) * 8;
-    // du = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) = k1*g + k2*u + k3 with per-channel constants
-    float k1[8], k2[8], k3[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = c0 + j;
-        const float is = invstd[c];
-        k1[j] = gamma[c] * is;
-        if (train) {
-            const float m0 = sums[c] * inv_n, m1 = sums[C + c] * inv_n;
-            k2[j] = -k1[j] * is * m1;
-            k3[j] = k1[j] * (mean[c] * is * m1 - m0);
-        } else {
-            k2[j] = 0.f;
-            k3[j] = 0.f;
-        }
-    }
     for (long idx = first; idx < total; idx += 2 * stride) {
-        const long idx2 = idx + stride;
-        const bool two = idx2 < total;
-        float g1[8], g2[8], u1[8], u2[8], y1[8], y2[8];
-        load8(ga_hi, ga_lo, idx, g1);
-        if (two) load8(ga_hi, ga_lo, idx2, g2);
-        load8(u_hi, u_lo, idx, u1);
-        if (two) load8(u_hi, u_lo, idx2, u2);
-        if (y_hi != nullptr) {
-            unpack8(__ldg(reinterpret_cast<const uint4*>(y_hi) + idx), y1);
-            if (two) unpack8(__ldg(reinterpret_cast<const uint4*>(y_hi) + idx2), y2);
-        }
-        if (gb_hi != nullptr) {
-            float t1[8], t2[8];
-            load8(gb_hi, gb_lo, idx, t1);
-            if (two) load8(gb_hi, gb_lo, idx2, t2);
+        uint4 gah[2], gal[2], gbh[2], gbl[2], yh[2], uh[2], ul[2];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                g1[j] += t1[j];
-                g2[j] += t2[j];
+        for (int t = 0; t < 2; ++t) {
+            const long it = idx + t * stride;
+            if (it < total) {
+                gah[t] = ld16(ga_hi, it);
+                uh[t] = ld16(u_hi, it);
+                if (has_y) yh[t] = ld16(y_hi, it);
+                if (has_gb) gbh[t] = ld16(gb_hi, it);
+                if (LO) {
+                    gal[t] = ld16(ga_lo, it);
+                    ul[t] = ld16(u_lo, it);
+                    if (has_gb) gbl[t] = ld16(gb_lo, it);
+                }
             }
         }
-        float o1[8], o2[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (y_hi != nullptr) {
-                g1[j] = y1[j] > 0.f ? g1[j] : 0.f;
-                g2[j] = y2[j] > 0.f ? g2[j] : 0.f;
+        for (int t = 0; t < 2; ++t) {
+            const long it = idx + t * stride;
+            if (it < total) {
+                float gv[8], u[8], o[8];
+                masked_grad<LO>(gah[t], gal[t], gbh[t], gbl[t], yh[t], has_gb, has_y, gv);
+                unpack8(uh[t], u);
+                if (LO) unpack8_lo(ul[t], u);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = fmaf(s_k1[c0 + j], gv[j], fmaf(s_k2[c0 + j], u[j], s_k3[c0 + j]));
+                store8(du_hi, LO ? du_lo : nullptr, it, o);
+                if (has_gout) store8(gout_hi, LO ? gout_lo : nullptr, it, gv);
             }
-            o1[j] = fmaf(k1[j], g1[j], fmaf(k2[j], u1[j], k3[j]));
-            o2[j] = fmaf(k1[j], g2[j], fmaf(k2[j], u2[j], k3[j]));
-        }
-        store8(du_hi, du_lo, idx, o1);
-        if (gout_hi != nullptr) store8(gout_hi, gout_lo, idx, g1);
-        if (two) {
-            store8(du_hi, du_lo, idx2, o2);
-            if (gout_hi != nullptr) store8(gout_hi, gout_lo, idx2, g2);
         }
     }
 }
@@ -816,8 +848,16 @@ extern "C" int gdrn_bn_act(const void* x_hi, const void* x_lo, const void* r_hi,
                            const float* scale, const float* shift, long rows, int C, int relu, void* stream_) {
     STREAM;
     if (C % 8) return set_error(GDRN_ERR_ARG, "bn_act: C %% 8 != 0");
-    bn_act_kernel<<<ew_grid(rows * (C / 8), 256), 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), CBF(r_hi), CBF(r_lo), BF(y_hi),
-                                                                    BF(y_lo), scale, shift, rows, C, relu);
+    if (C > 512 || 256 % (C / 8)) return set_error(GDRN_ERR_ARG, "bn_act: unsupported C=%d", C);
+    const int grid = ew_grid_amortised(rows * (C / 8), 256, 4);
+#define GDRN_BN_ACT(LO, RES) \
+    bn_act_kernel<LO, RES><<<grid, 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), CBF(r_hi), CBF(r_lo), BF(y_hi), BF(y_lo), scale, shift, rows, C, relu)
+    if (x_lo != nullptr) {
+        if (r_hi != nullptr) GDRN_BN_ACT(true, true); else GDRN_BN_ACT(true, false);
+    } else {
+        if (r_hi != nullptr) GDRN_BN_ACT(false, true); else GDRN_BN_ACT(false, false);
+    }
+#undef GDRN_BN_ACT
     LAUNCH_DONE();
 }
 
@@ -866,18 +906,28 @@ extern "C" int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_
     {  // the reductions also provide dgamma / dbeta when BN runs on frozen (eval) statistics
         GDRN_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream));
         const int rpb = kBnBwdThreads / (C / 8);
-        long blocks = (rows + rpb - 1) / rpb;
-        const long cap = (long)num_sms() * 4;
+        long blocks = (rows + (long)rpb * 16 - 1) / ((long)rpb * 16);  // >= 16 rows per thread: few atomics, amortised prologue
+        const long cap = (long)num_sms() * 2;
         if (blocks > cap) blocks = cap;
-        bn_bwd_reduce_kernel<<<(int)blocks, kBnBwdThreads, 0, stream>>>(CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo),
-                                                                        CBF(y_hi), CBF(u_hi), CBF(u_lo), mean, invstd, sums,
-                                                                        rows, C);
+        if (blocks < 1) blocks = 1;
+        if (u_lo != nullptr)
+            bn_bwd_reduce_kernel<true><<<(int)blocks, kBnBwdThreads, 0, stream>>>(CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo), CBF(y_hi),
+                                                                                  CBF(u_hi), CBF(u_lo), mean, invstd, sums, rows, C);
+        else
+            bn_bwd_reduce_kernel<false><<<(int)blocks, kBnBwdThreads, 0, stream>>>(CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo), CBF(y_hi),
+                                                                                   CBF(u_hi), CBF(u_lo), mean, invstd, sums, rows, C);
         GDRN_CUDA_OK(cudaGetLastError());
         count_launch();
     }
-    bn_bwd_apply_kernel<<<ew_grid(rows * (C / 8), 256), 256, 0, stream>>>(
-        CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo), CBF(y_hi), CBF(u_hi), CBF(u_lo), mean, invstd, gamma, sums,
-        BF(du_hi), BF(du_lo), BF(gout_hi), BF(gout_lo), dgamma, dbeta, rows, C, train);
+    const int agrid = ew_grid_amortised(rows * (C / 8), 256, 4);
+    if (u_lo != nullptr)
+        bn_bwd_apply_kernel<true><<<agrid, 256, 0, stream>>>(CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo), CBF(y_hi), CBF(u_hi), CBF(u_lo),
+                                                             mean, invstd, gamma, sums, BF(du_hi), BF(du_lo), BF(gout_hi), BF(gout_lo),
+                                                             dgamma, dbeta, rows, C, train);
+    else
+        bn_bwd_apply_kernel<false><<<agrid, 256, 0, stream>>>(CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo), CBF(y_hi), CBF(u_hi), CBF(u_lo),
+                                                              mean, invstd, gamma, sums, BF(du_hi), BF(du_lo), BF(gout_hi), BF(gout_lo),
+                                                              dgamma, dbeta, rows, C, train);
     LAUNCH_DONE();
 }
 
@@ -938,10 +988,17 @@ extern "C" int gdrn_bn_fwd(const void* x_hi, const void* x_lo, const void* r_hi,
                            float* mean_out, float* invstd_out, long rows, int C, float eps, float momentum, int train, int relu,
                            void* stream_) {
     STREAM;
-    if (C % 8 || 256 % (C / 8)) return set_error(GDRN_ERR_ARG, "bn_fwd: unsupported C=%d", C);
+    if (C % 8 || C > 512 || 256 % (C / 8)) return set_error(GDRN_ERR_ARG, "bn_fwd: unsupported C=%d", C);
     if (train && stats == nullptr) return set_error(GDRN_ERR_ARG, "bn_fwd: batch statistics missing");
-    bn_fwd_kernel<<<ew_grid(rows * (C / 8), 256), 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), CBF(r_hi), CBF(r_lo), BF(y_hi), BF(y_lo),
-                                                                    stats, gamma, beta, running_mean, running_var, mean_out,
-                                                                    invstd_out, rows, C, eps, momentum, train, relu);
+    const int grid = ew_grid_amortised(rows * (C / 8), 256, 4);
+#define GDRN_BN_FWD(LO, RES)                                                                                                  \
+    bn_fwd_kernel<LO, RES><<<grid, 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), CBF(r_hi), CBF(r_lo), BF(y_hi), BF(y_lo), stats, gamma, beta, \
+                                                     running_mean, running_var, mean_out, invstd_out, rows, C, eps, momentum, train, relu)
+    if (x_lo != nullptr) {
+        if (r_hi != nullptr) GDRN_BN_FWD(true, true); else GDRN_BN_FWD(true, false);
+    } else {
+        if (r_hi != nullptr) GDRN_BN_FWD(false, true); else GDRN_BN_FWD(false, false);
+    }
+#undef GDRN_BN_FWD
     LAUNCH_DONE();
 }
