@@ -43,7 +43,9 @@ struct GemmParams {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kAuxBytes = 4096;
+constexpr int kEpiWarps = 8;                    // two epilogue warpgroups, one per TMEM accumulator buffer
+constexpr int kTrBytes = kEpiWarps * 32 * 17 * 4;  // per-warp 32x16 (+1 pad) fp32 transpose buffers for the BN statistics
+constexpr int kAuxBytes = 4096 + kTrBytes;
 
 template <int BLOCK_N, int NSPLIT>
 struct GemmCfg {
@@ -81,7 +83,7 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
 }
 
 template <int BLOCK_N, int NSPLIT>
-__global__ void __launch_bounds__(256, 1) gemm_fwd_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<BLOCK_N, NSPLIT>;
     constexpr int NPL = Cfg::NPL;
     constexpr int STAGES = Cfg::STAGES;
@@ -95,6 +97,7 @@ __global__ void __launch_bounds__(256, 1) gemm_fwd_kernel(const __grid_constant_
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     float* s_stats = reinterpret_cast<float*>(aux + 512);  // [2][BLOCK_N]
+    float* s_tr = reinterpret_cast<float*>(aux + 4096);    // [kEpiWarps][32][17]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -228,13 +231,16 @@ __global__ void __launch_bounds__(256, 1) gemm_fwd_kernel(const __grid_constant_
             }
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue (128 threads)
+        // ------------------------------------------------------------------ epilogue: 2 warpgroups x 128 threads.
+        // Group g drains TMEM accumulator buffer g, i.e. every other tile of this CTA: two tile epilogues are in flight
+        // (needed for small-K layers such as 64->64 3x3, whose 9 k-blocks of MMA are shorter than one epilogue).
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        const int grp = (warp - 4) >> 2;
         const int row = q * 32 + lane;
+        float* tr = s_tr + (warp - 4) * (32 * 17);
         __nv_bfloat16* out_hi = reinterpret_cast<__nv_bfloat16*>(p.out_hi);
         __nv_bfloat16* out_lo = reinterpret_cast<__nv_bfloat16*>(p.out_lo);
-        int it = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        for (int t = blockIdx.x + grp * gridDim.x, it = grp; t < num_tiles; t += 2 * gridDim.x, it += 2) {
             const int n_tile = t % p.num_n_tiles;
             const int m_tile = t / p.num_n_tiles;
             const int acc = it & 1;
@@ -319,16 +325,30 @@ __global__ void __launch_bounds__(256, 1) gemm_fwd_kernel(const __grid_constant_
                     }
                 }
                 if (p.stats != nullptr) {
-                    float sq[32];
+                    // per-channel sum / sum of squares over this warp's 32 rows: transpose 16 columns at a time through a
+                    // padded smem tile (conflict-free), lane l then adds column (l & 15) over row half (l >> 4).
+                    // (A shuffle butterfly was latency-bound: ~60 dependent shuffles per chunk.)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (!row_ok) f[j] = 0.f;
-                        sq[j] = f[j] * f[j];
+                    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) tr[lane * 17 + j] = row_ok ? f[h * 16 + j] : 0.f;
+                        __syncwarp();
+                        float s1 = 0.f, s2 = 0.f;
+                        const int col = lane & 15, r0 = (lane >> 4) * 16;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float v = tr[(r0 + i) * 17 + col];
+                            s1 += v;
+                            s2 = fmaf(v, v, s2);
+                        }
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                        s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+                        __syncwarp();
+                        if (lane < 16) {
+                            atomicAdd(&s_stats[c * 32 + h * 16 + lane], s1);
+                            atomicAdd(&s_stats[BLOCK_N + c * 32 + h * 16 + lane], s2);
+                        }
                     }
-                    const float s1 = warp_transpose_reduce(f, lane);
-                    const float s2 = warp_transpose_reduce(sq, lane);
-                    atomicAdd(&s_stats[c * 32 + lane], s1);
-                    atomicAdd(&s_stats[BLOCK_N + c * 32 + lane], s2);
                 }
             }
             tc_fence_before();
@@ -336,9 +356,9 @@ __global__ void __launch_bounds__(256, 1) gemm_fwd_kernel(const __grid_constant_
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
         if (p.stats != nullptr && blockIdx.x < num_tiles) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
             const int n_tile = blockIdx.x % p.num_n_tiles;   // fixed per CTA (grid % num_n_tiles == 0)
-            for (int i = threadIdx.x - 128; i < BLOCK_N; i += 128) {
+            for (int i = threadIdx.x - 128; i < BLOCK_N; i += 256) {
                 const int col = n_tile * BLOCK_N + i;
                 if (col < p.N) {
                     atomicAdd(p.stats + col, s_stats[i]);
@@ -372,7 +392,7 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
     int grid = tiles < num_sms() ? tiles : num_sms();
     grid -= grid % p.num_n_tiles;  // every CTA keeps one n_tile => per-CTA BatchNorm partial sums
     if (grid <= 0) grid = p.num_n_tiles;
-    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(p);
+    kern<<<grid, 128 + 32 * kEpiWarps, Cfg::SMEM_BYTES, stream>>>(p);
     GDRN_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;

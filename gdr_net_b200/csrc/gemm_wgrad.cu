@@ -280,8 +280,10 @@ using namespace gdrn;
 // Workspace size query + K-split choice shared by conv and gemm wgrad.
 static int choose_ksplit(int base_items, int kb_total, int requested) {
     if (requested > 0) return requested < kb_total ? requested : kb_total;
-    int ks = (2 * num_sms() + base_items - 1) / base_items;  // aim at ~2 waves of work items
-    int max_ks = kb_total / 4;                               // keep >= 4 k-blocks per split
+    // one full wave of CTAs (each CTA is one (tile, tap, K-split) work item and owns an SM: 1 CTA/SM by smem), with at
+    // least 8 k-blocks per split so the pipeline fill / TMEM drain is amortised
+    int ks = num_sms() / base_items;
+    int max_ks = kb_total / 8;
     if (max_ks < 1) max_ks = 1;
     if (ks > max_ks) ks = max_ks;
     if (ks < 1) ks = 1;
