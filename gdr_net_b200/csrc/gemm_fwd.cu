@@ -18,6 +18,8 @@
 //     TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   * NSPLIT = 3 is the fp32-faithful mode: operands are (hi, lo) bf16 planes and each k-step issues
 //     hi*hi + hi*lo + lo*hi (the lo*lo term, 2^-18 relative, is dropped).
+#include <stdlib.h>
+
 #include "gdrn_internal.h"
 #include "ptx.cuh"
 
@@ -38,6 +40,7 @@ struct GemmParams {
     const float* bias;
     int act;       // 0 none, 1 LeakyReLU(0.1)
     float* stats;  // [2][N]: sum, sum of squares (accumulated with atomics) or nullptr
+    int cluster;   // 1, or 2: CTA pairs share one n_tile and each TMA-multicasts half of the weight tile to both
 };
 
 constexpr int kBlockM = 128;
@@ -60,8 +63,10 @@ struct GemmCfg {
     // K-long chain grows ~ (K/16) * 2^-24.  The fp32-faithful mode therefore keeps the small cross terms
     // (hi*lo + lo*hi) in their own accumulator and spreads the hi*hi k-blocks round-robin over three more; the
     // epilogue adds the four partials with round-to-nearest fp32 adds.
-    static constexpr int NMAIN = (NSPLIT == 3) ? 3 : 1;
-    static constexpr int NACC = (NSPLIT == 3) ? 4 : 1;
+    // (Splitting the hi*hi chain over several accumulators was measured to change nothing at these K: the 16-bit
+    // operand planes dominate the error, so one main + one cross accumulator is used and BLOCK_N can be 128.)
+    static constexpr int NMAIN = 1;
+    static constexpr int NACC = (NSPLIT == 3) ? 2 : 1;
     static constexpr int TMEM_COLS = 2 * NACC * BLOCK_N;  // double-buffered accumulator set
     static_assert(STAGES >= 2, "pipeline too shallow");
     static_assert(TMEM_COLS <= 512, "TMEM overflow");
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], p.cluster);  // every CTA of the cluster must have consumed the stage (multicast writes all)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
@@ -129,15 +134,22 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // cluster geometry: clusters stride over "tile groups" = (n_tile, group of `cl` consecutive m_tiles)
+    const int cl = p.cluster;
+    const uint32_t crank = cl > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << cl) - 1u);
+    const int my_cluster = blockIdx.x / cl, num_clusters = gridDim.x / cl;
+    const int num_groups = num_tiles / cl;
+    if (cl > 1) cluster_sync_all();  // peers' barriers are initialised before any remote arrive / multicast write
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int n_tile = t % p.num_n_tiles;
-                const int m_tile = t / p.num_n_tiles;
+            for (int grp = my_cluster; grp < num_groups; grp += num_clusters) {
+                const int n_tile = grp % p.num_n_tiles;
+                const int m_tile = (grp / p.num_n_tiles) * cl + (int)crank;
                 int n0 = 0, h0 = 0;
                 if (p.mode == 1) {
                     if (p.TN == 1) {
@@ -172,10 +184,20 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
                             tma_load_2d(st + pl * Cfg::A_BYTES, &p.tmA[pl][0], &full_bar[stage], kb * kBlockK,
                                         m_tile * kBlockM);
                     }
+                    if (cl == 1) {
 #pragma unroll
-                    for (int pl = 0; pl < NPL; ++pl)
-                        tma_load_2d(st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES, &p.tmB[pl], &full_bar[stage],
-                                    kb * kBlockK, n_tile * BLOCK_N);
+                        for (int pl = 0; pl < NPL; ++pl)
+                            tma_load_2d(st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES, &p.tmB[pl], &full_bar[stage],
+                                        kb * kBlockK, n_tile * BLOCK_N);
+                    } else {
+                        // this CTA fetches rows [crank * BLOCK_N/cl, +BLOCK_N/cl) of the weight tile and multicasts them to
+                        // the same smem offset of every CTA in the cluster: L2 -> SM weight traffic drops by cl
+                        const int rows = BLOCK_N / cl;
+#pragma unroll
+                        for (int pl = 0; pl < NPL; ++pl)
+                            tma_load_2d_mcast(st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES + crank * rows * 128, &p.tmB[pl],
+                                              &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N + crank * rows, cmask);
+                    }
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -194,7 +216,7 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            for (int grp = my_cluster; grp < num_groups; grp += num_clusters, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -221,7 +243,8 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
                             umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                         }
                     }
-                    umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above retire
+                    // frees this smem stage (in every CTA of the cluster: their multicasts write our smem) when the MMAs retire
+                    if (cl == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], cmask);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -240,9 +263,9 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
         float* tr = s_tr + (warp - 4) * (32 * 17);
         __nv_bfloat16* out_hi = reinterpret_cast<__nv_bfloat16*>(p.out_hi);
         __nv_bfloat16* out_lo = reinterpret_cast<__nv_bfloat16*>(p.out_lo);
-        for (int t = blockIdx.x + grp * gridDim.x, it = grp; t < num_tiles; t += 2 * gridDim.x, it += 2) {
-            const int n_tile = t % p.num_n_tiles;
-            const int m_tile = t / p.num_n_tiles;
+        for (int tg = my_cluster + grp * num_clusters, it = grp; tg < num_groups; tg += 2 * num_clusters, it += 2) {
+            const int n_tile = tg % p.num_n_tiles;
+            const int m_tile = (tg / p.num_n_tiles) * cl + (int)crank;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tfull_bar[acc], acc_phase);
@@ -355,9 +378,9 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
-        if (p.stats != nullptr && blockIdx.x < num_tiles) {
+        if (p.stats != nullptr) {
             asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
-            const int n_tile = blockIdx.x % p.num_n_tiles;   // fixed per CTA (grid % num_n_tiles == 0)
+            const int n_tile = my_cluster % p.num_n_tiles;   // fixed per CTA (num_clusters % num_n_tiles == 0)
             for (int i = threadIdx.x - 128; i < BLOCK_N; i += 256) {
                 const int col = n_tile * BLOCK_N + i;
                 if (col < p.N) {
@@ -370,6 +393,7 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
 
     tc_fence_before();
     __syncthreads();
+    if (cl > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into its smem / arrive on its barriers
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -388,12 +412,25 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
         GDRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    const int tiles = p.num_m_tiles * p.num_n_tiles;
-    int grid = tiles < num_sms() ? tiles : num_sms();
-    grid -= grid % p.num_n_tiles;  // every CTA keeps one n_tile => per-CTA BatchNorm partial sums
-    if (grid <= 0) grid = p.num_n_tiles;
-    kern<<<grid, 128 + 32 * kEpiWarps, Cfg::SMEM_BYTES, stream>>>(p);
-    GDRN_CUDA_OK(cudaGetLastError());
+    const int cl = p.cluster;
+    const int groups = p.num_m_tiles * p.num_n_tiles / cl;
+    int clusters = groups < num_sms() / cl ? groups : num_sms() / cl;
+    clusters -= clusters % p.num_n_tiles;  // every CTA keeps one n_tile => per-CTA BatchNorm partial sums
+    if (clusters <= 0) clusters = p.num_n_tiles;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(clusters * cl);
+    cfg.blockDim = dim3(128 + 32 * kEpiWarps);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GDRN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
     count_launch();
     return 0;
 }
@@ -404,6 +441,7 @@ static int dispatch_gemm(const GemmParams& p, int block_n, int nsplit, cudaStrea
         if (block_n == 128) return launch_gemm<128, 1>(p, stream);
         if (block_n == 64) return launch_gemm<64, 1>(p, stream);
     } else if (nsplit == 3) {
+        if (block_n == 128) return launch_gemm<128, 3>(p, stream);
         if (block_n == 64) return launch_gemm<64, 3>(p, stream);
     }
     return set_error(GDRN_ERR_ARG, "gemm: unsupported block_n=%d nsplit=%d", block_n, nsplit);
@@ -412,14 +450,27 @@ static int dispatch_gemm(const GemmParams& p, int block_n, int nsplit, cudaStrea
 // Tile width: the widest BLOCK_N (fewest A re-reads, best smem-bandwidth ratio) that still yields >= ~0.75 waves of
 // CTAs on the 148 SMs; small-M layers (layer4, FC) fall back to narrower tiles instead of leaving SMs idle.
 static int pick_block_n(int n_pad, int nsplit, int num_m_tiles) {
-    if (nsplit == 3) return (n_pad % 64 == 0) ? 64 : -1;  // 4 accumulators x 2 buffers x 64 columns = all of TMEM
     const int want = (num_sms() * 3) / 4;
-    if (n_pad % 256 == 0 && num_m_tiles * (n_pad / 256) >= want) return 256;
+    // fp32x3: (main + cross) x 2 buffers x 128 columns = all 512 TMEM columns, so 128 is the widest tile
+    if (nsplit == 1 && n_pad % 256 == 0 && num_m_tiles * (n_pad / 256) >= want) return 256;
     if (n_pad % 128 == 0 && num_m_tiles * (n_pad / 128) >= want) return 128;
     if (n_pad % 64 == 0 && num_m_tiles * (n_pad / 128) < num_sms() / 2) return 64;
     if (n_pad % 128 == 0) return 128;
     if (n_pad % 64 == 0) return 64;
     return -1;
+}
+
+// Optional CTA pairs (cluster of 2) that TMA-multicast the weight tile.  MEASURED SLOWER on B200 (64x64 256->256 conv:
+// 1250 -> 1066 TFLOP/s; whole step 12.36 -> 12.75 ms): the two CTAs' stage rings become coupled and the halved TMA boxes
+// cost more than the saved L2 traffic, so it is off unless GDRN_CLUSTER=2 is set (kept for round-2 experiments).
+static int pick_cluster(int num_m_tiles) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("GDRN_CLUSTER");
+        forced = e ? atoi(e) : 1;
+    }
+    if (forced != 2) return 1;
+    return (num_m_tiles % 2 == 0 && num_m_tiles >= 2) ? 2 : 1;
 }
 
 }  // namespace gdrn
@@ -448,6 +499,7 @@ extern "C" int gdrn_conv_fwd(const void* x_hi, const void* x_lo, const void* w_h
 
     GemmParams p;
     memset(&p, 0, sizeof(p));
+    const int cluster = pick_cluster((N * Ho * Wo + 127) / 128);
     const int npl = nsplit == 1 ? 1 : 2;
     const void* xs[2] = {x_hi, x_lo};
     const void* ws[2] = {w_hi, w_lo};
@@ -464,9 +516,10 @@ extern "C" int gdrn_conv_fwd(const void* x_hi, const void* x_lo, const void* w_h
         }
         uint64_t wdims[2] = {(uint64_t)K, (uint64_t)Cout_pad};
         uint64_t wstr[1] = {(uint64_t)K * 2};
-        uint32_t wbox[2] = {64, (uint32_t)block_n};
+        uint32_t wbox[2] = {64, (uint32_t)(block_n / cluster)};
         if (make_tmap(&p.tmB[pl], ws[pl], 2, wdims, wstr, wbox)) return GDRN_ERR_CUDA;
     }
+    p.cluster = cluster;
     p.mode = 1;
     p.M = N * Ho * Wo;
     p.N = Cout;
@@ -502,6 +555,7 @@ extern "C" int gdrn_gemm_fwd(const void* a_hi, const void* a_lo, const void* w_h
     if (block_n < 0) return set_error(GDRN_ERR_ARG, "gemm_fwd: N_pad=%d must be a multiple of 64", N_pad);
     GemmParams p;
     memset(&p, 0, sizeof(p));
+    const int cluster = pick_cluster((M + 127) / 128);
     const int npl = nsplit == 1 ? 1 : 2;
     const void* as[2] = {a_hi, a_lo};
     const void* ws[2] = {w_hi, w_lo};
@@ -511,9 +565,10 @@ extern "C" int gdrn_gemm_fwd(const void* a_hi, const void* a_lo, const void* w_h
         uint32_t abox[2] = {64, 128};
         if (make_tmap(&p.tmA[pl][0], as[pl], 2, adims, astr, abox)) return GDRN_ERR_CUDA;
         uint64_t wdims[2] = {(uint64_t)K, (uint64_t)N_pad};
-        uint32_t wbox[2] = {64, (uint32_t)block_n};
+        uint32_t wbox[2] = {64, (uint32_t)(block_n / cluster)};
         if (make_tmap(&p.tmB[pl], ws[pl], 2, wdims, astr, wbox)) return GDRN_ERR_CUDA;
     }
+    p.cluster = cluster;
     p.mode = 0;
     p.M = M;
     p.N = N;

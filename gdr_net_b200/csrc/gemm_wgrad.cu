@@ -31,6 +31,9 @@ struct WgradParams {
     int KW, pad, stride;
     int blocks_per_img, THk, TNk;
     float* ws;              // [ksplit][num_m_tiles*128][taps*Ntot]
+    int tap_pack;           // 1: Cin == 64, stride 1: one work item covers a whole filter ROW, its KW taps packed along N
+    int items;              // work items per (m_tile, n_tile, ksplit): taps, or KH when tap_pack
+    int ws_ld;              // workspace row length in floats (= KH*KW*Cin)
 };
 
 constexpr int kWgStageA = 2 * 8192;
@@ -48,7 +51,8 @@ struct WgradCfg {
     // round-toward-zero accumulation (see gemm_fwd.cu): cross terms and three round-robin hi*hi partials
     static constexpr int NMAIN = (NSPLIT == 3) ? 3 : 1;
     static constexpr int NACC = (NSPLIT == 3) ? 4 : 1;
-    static constexpr int TMEM_COLS = NACC * N_TILE < 32 ? 32 : NACC * N_TILE;
+    static constexpr int TMEM_RAW = NACC * N_TILE;
+    static constexpr int TMEM_COLS = TMEM_RAW <= 32 ? 32 : TMEM_RAW <= 64 ? 64 : TMEM_RAW <= 128 ? 128 : TMEM_RAW <= 256 ? 256 : 512;
     static_assert(NACC * N_TILE <= 512, "TMEM overflow");
     static_assert(STAGES >= 2, "pipeline too shallow");
 };
@@ -77,8 +81,8 @@ __global__ void __launch_bounds__(192, 1) gemm_wgrad_kernel(const __grid_constan
     item /= p.num_m_tiles;
     const int n_tile = item % p.num_n_tiles;
     item /= p.num_n_tiles;
-    const int tap = item % p.taps;
-    const int ks = item / p.taps;
+    const int tap = item % p.items;  // filter tap, or filter row when tap_pack
+    const int ks = item / p.items;
     const int kb_per = (p.kb_total + p.ksplit - 1) / p.ksplit;
     const int kb_begin = ks * kb_per;
     const int kb_end = min(p.kb_total, kb_begin + kb_per);
@@ -104,7 +108,9 @@ __global__ void __launch_bounds__(192, 1) gemm_wgrad_kernel(const __grid_constan
     if (warp == 0) {
         if (lane == 0 && nkb > 0) {
             int dh = 0, dw = 0, map = 0;
-            if (p.mode == 1) {
+            if (p.mode == 1 && p.tap_pack) {
+                dh = tap - p.pad;  // `tap` is the filter row; the column shift varies per 64-channel chunk below
+            } else if (p.mode == 1) {
                 const int r = tap / p.KW;
                 const int s = tap - r * p.KW;
                 dh = r - p.pad;
@@ -136,10 +142,16 @@ __global__ void __launch_bounds__(192, 1) gemm_wgrad_kernel(const __grid_constan
                             n0 = kb * p.TNk;
                             h0 = 0;
                         }
+                        if (p.tap_pack) {
 #pragma unroll
-                        for (int c = 0; c < NCH; ++c)
-                            tma_load_4d(b_dst + c * 8192, &p.tmB[pl][map], &full_bar[stage], n_tile * N_TILE + c * 64, dw,
-                                        h0 + dh, n0);
+                            for (int c = 0; c < NCH; ++c)  // chunk c = filter column c (all 64 input channels)
+                                tma_load_4d(b_dst + c * 8192, &p.tmB[pl][0], &full_bar[stage], 0, c - p.pad, h0 + dh, n0);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < NCH; ++c)
+                                tma_load_4d(b_dst + c * 8192, &p.tmB[pl][map], &full_bar[stage], n_tile * N_TILE + c * 64, dw,
+                                            h0 + dh, n0);
+                        }
                     } else {
 #pragma unroll
                         for (int c = 0; c < NCH; ++c)
@@ -198,8 +210,10 @@ __global__ void __launch_bounds__(192, 1) gemm_wgrad_kernel(const __grid_constan
             mbar_wait(done_bar, 0);
             tc_fence_after();
         }
-        const size_t ld = (size_t)p.taps * p.Ntot;
-        float* dst_row = p.ws + ((size_t)ks * p.num_m_tiles * 128 + co) * ld + (size_t)tap * p.Ntot + n_tile * N_TILE;
+        const size_t ld = (size_t)p.ws_ld;
+        // tap_pack: columns (filter column, ci) of filter row `tap` are contiguous in the [co][tap][ci] workspace row
+        const size_t col0 = p.tap_pack ? (size_t)tap * N_TILE : (size_t)tap * p.Ntot + (size_t)n_tile * N_TILE;
+        float* dst_row = p.ws + ((size_t)ks * p.num_m_tiles * 128 + co) * ld + col0;
 #pragma unroll 1
         for (int c = 0; c < N_TILE / 32; ++c) {
             uint32_t raw[32];
@@ -223,7 +237,7 @@ __global__ void __launch_bounds__(192, 1) gemm_wgrad_kernel(const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 32; ++j) raw[j] = 0u;
             }
-            if (n_tile * N_TILE + c * 32 < p.Ntot) {
+            if (p.tap_pack || n_tile * N_TILE + c * 32 < p.Ntot) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<uint4*>(dst_row + c * 32 + j) = make_uint4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
@@ -247,7 +261,7 @@ static int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
         GDRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    const int grid = p.num_m_tiles * p.num_n_tiles * p.taps * p.ksplit;
+    const int grid = p.num_m_tiles * p.num_n_tiles * p.items * p.ksplit;
     kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(p);
     GDRN_CUDA_OK(cudaGetLastError());
     count_launch();
@@ -257,6 +271,7 @@ static int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
 static int dispatch_wgrad(const WgradParams& p, int n_tile, int nsplit, cudaStream_t stream) {
     if (nsplit == 1) {
         if (n_tile == 256) return launch_wgrad<256, 1>(p, stream);
+        if (n_tile == 192) return launch_wgrad<192, 1>(p, stream);
         if (n_tile == 128) return launch_wgrad<128, 1>(p, stream);
         if (n_tile == 64) return launch_wgrad<64, 1>(p, stream);
     } else if (nsplit == 3) {
@@ -306,17 +321,23 @@ extern "C" int gdrn_conv_wgrad(const void* dy_hi, const void* dy_lo, const void*
     if (Ho % THk != 0 || (N % TNk) != 0) return set_error(GDRN_ERR_ARG, "conv_wgrad: shape not tileable by 64 pixels");
     const long P = (long)N * Ho * Wo;
     if (P % 64 != 0) return set_error(GDRN_ERR_ARG, "conv_wgrad: N*Ho*Wo must be a multiple of 64");
-    const int n_tile = pick_n_tile(Cin, nsplit);
+    // Cin == 64 (layer1): a 64-wide N tile leaves the tensor core smem/ingress-bound; pack the KW taps of a filter row
+    // along N instead (N = 192): one dY tile load feeds three taps, 3x fewer MMAs / A loads per FLOP
+    const int tap_pack = (nsplit == 1 && Cin == 64 && stride == 1 && KW == 3) ? 1 : 0;
+    const int n_tile = tap_pack ? 192 : pick_n_tile(Cin, nsplit);
     WgradParams p;
     memset(&p, 0, sizeof(p));
     p.mode = 1;
+    p.tap_pack = tap_pack;
+    p.items = tap_pack ? KH : KH * KW;
+    p.ws_ld = KH * KW * Cin;
     p.Mvalid = Cout;
     p.Ntot = Cin;
     p.num_m_tiles = (Cout + 127) / 128;
-    p.num_n_tiles = Cin / n_tile;
+    p.num_n_tiles = tap_pack ? 1 : Cin / n_tile;
     p.taps = KH * KW;
     p.kb_total = (int)(P / 64);
-    p.ksplit = choose_ksplit(p.num_m_tiles * p.num_n_tiles * p.taps, p.kb_total, ksplit);
+    p.ksplit = choose_ksplit(p.num_m_tiles * p.num_n_tiles * p.items, p.kb_total, ksplit);
     p.KW = KW;
     p.pad = pad;
     p.stride = stride;
@@ -366,6 +387,8 @@ extern "C" int gdrn_gemm_wgrad(const void* dy_hi, const void* dy_lo, const void*
     p.num_m_tiles = (M + 127) / 128;
     p.num_n_tiles = Ntot / n_tile;
     p.taps = 1;
+    p.items = 1;
+    p.ws_ld = Ntot;
     p.kb_total = (int)((P + 63) / 64);
     p.ksplit = choose_ksplit(p.num_m_tiles * p.num_n_tiles, p.kb_total, ksplit);
     p.ws = ws;

@@ -45,11 +45,14 @@ struct PackJob {
     __nv_bfloat16* dst_hi;
     __nv_bfloat16* dst_lo;
     long so, si, sr, ss;
-    long elem_begin;  // prefix sum of ceil256(opad * krow)
+    long elem_begin;  // prefix sum of ceil256(opad * ipad): (dst row, dst channel) work items
     int O, I, KH, KW, opad, ipad, krow, flip;
 };
 
 __global__ void __launch_bounds__(256) pack_weight_batched_kernel(const PackJob* __restrict__ jobs, int njobs, long total_blocks) {
+    // One thread = one (dst row o, dst channel i) pair, looping over the taps: a warp reads 32 short contiguous runs of
+    // the fp32 source (the taps of OIHW / IOHW are innermost: >= 50 % sector efficiency) and writes 64 contiguous bytes
+    // per tap and plane.  (The first version mapped threads to dst elements: 2-byte gathers with a 36-byte stride.)
     __shared__ PackJob job;
     for (long blk = blockIdx.x; blk < total_blocks; blk += gridDim.x) {
         __syncthreads();
@@ -63,25 +66,29 @@ __global__ void __launch_bounds__(256) pack_weight_batched_kernel(const PackJob*
             job = jobs[lo];
         }
         __syncthreads();
-        const long idx = blk * 256 + threadIdx.x - job.elem_begin;
-        const long total = (long)job.opad * job.krow;
-        if (idx >= total) continue;
-        const int o = (int)(idx / job.krow);
-        const int col = (int)(idx - (long)o * job.krow);
-        const int tap = col / job.ipad;
-        const int i = col - tap * job.ipad;
-        float v = 0.f;
-        if (o < job.O && i < job.I && tap < job.KH * job.KW) {
-            int r = tap / job.KW, s2 = tap - (tap / job.KW) * job.KW;
-            if (job.flip) {
-                r = job.KH - 1 - r;
-                s2 = job.KW - 1 - s2;
+        const long item = blk * 256 + threadIdx.x - job.elem_begin;  // elem_begin counts (o, i) ITEMS here
+        if (item >= (long)job.opad * job.ipad) continue;
+        const int o = (int)(item / job.ipad);
+        const int i = (int)(item - (long)o * job.ipad);
+        const int taps = job.KH * job.KW;
+        const bool valid = (o < job.O) && (i < job.I);
+        const float* sp = job.src + o * job.so + i * job.si;
+        __nv_bfloat16* dh = job.dst_hi + (long)o * job.krow + i;
+        __nv_bfloat16* dl = job.dst_lo != nullptr ? job.dst_lo + (long)o * job.krow + i : nullptr;
+        for (int tap = 0; tap < taps; ++tap) {
+            float v = 0.f;
+            if (valid) {
+                int r = tap / job.KW, s2 = tap - (tap / job.KW) * job.KW;
+                if (job.flip) {
+                    r = job.KH - 1 - r;
+                    s2 = job.KW - 1 - s2;
+                }
+                v = __ldg(sp + r * job.sr + s2 * job.ss);
             }
-            v = __ldg(job.src + o * job.so + i * job.si + r * job.sr + s2 * job.ss);
+            const float h = bf16_round(v);
+            dh[(long)tap * job.ipad] = __float2bfloat16(h);
+            if (dl != nullptr) dl[(long)tap * job.ipad] = __float2bfloat16(v - h);
         }
-        const float h = bf16_round(v);
-        job.dst_hi[idx] = __float2bfloat16(h);
-        if (job.dst_lo != nullptr) job.dst_lo[idx] = __float2bfloat16(v - h);
     }
 }
 
@@ -89,40 +96,54 @@ __global__ void __launch_bounds__(256) pack_weight_batched_kernel(const PackJob*
 __global__ void unpack_wgrad_kernel(const float* __restrict__ ws, float* __restrict__ grad, int O, int I, int KH, int KW,
                                     int ipad, int krow_, int ksplit, long ks_stride, long so, long si, long sr, long ss, int flip,
                                     int accumulate) {
+    // thread = (o, i): reads are coalesced over i for every (split, tap); the taps of one (o, i) are written back to back
+    // (contiguous 36-byte runs in OIHW, so a warp covers one contiguous 1152-byte range).
     const int taps = KH * KW;
     const long krow = krow_;
-    const long total = (long)O * taps * I;
+    const long total = (long)O * I;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        // read-coalesced order: (o, tap, i)
         const int i = (int)(idx % I);
-        const long t2 = idx / I;
-        const int tap = (int)(t2 % taps);
-        const int o = (int)(t2 / taps);
-        const float* src = ws + (long)o * krow + (long)tap * ipad + i;
-        float acc = 0.f;
-        for (int ks = 0; ks < ksplit; ++ks) acc += src[ks * ks_stride];
-        int r = tap / KW, s = tap - (tap / KW) * KW;
-        if (flip) {
-            r = KH - 1 - r;
-            s = KW - 1 - s;
+        const int o = (int)(idx / I);
+        const float* src = ws + (long)o * krow + i;
+        float* d = grad + o * so + i * si;
+        for (int tap = 0; tap < taps; ++tap) {
+            float acc = 0.f;
+            for (int ks = 0; ks < ksplit; ++ks) acc += src[ks * ks_stride + (long)tap * ipad];
+            int r = tap / KW, s = tap - (tap / KW) * KW;
+            if (flip) {
+                r = KH - 1 - r;
+                s = KW - 1 - s;
+            }
+            float* dd = d + r * sr + s * ss;
+            *dd = accumulate ? (*dd + acc) : acc;
         }
-        float* d = grad + o * so + i * si + r * sr + s * ss;
-        *d = accumulate ? (*d + acc) : acc;
     }
 }
 
 // Stem im2col: x NCHW fp32 [B,3,H,W] -> A[(b,oh,ow)][192] with k = (r*7+s)*3 + c (147 valid), conv 7x7 s2 p3.
-// One thread produces 8 consecutive k (one 16-byte store per plane).
-__global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a_hi,
-                                   __nv_bfloat16* __restrict__ a_lo, int B, int H, int W) {
+// One block per (image, output row): the 7 x 3 input rows it needs are staged in shared memory with a zero halo
+// (coalesced fp32 loads), then every thread emits 16-byte groups of 8 consecutive k for consecutive positions
+// (coalesced stores; the matrix is 403 MB per plane at B=64, so the stores are what matters).
+template <int W>
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a_hi,
+                                                          __nv_bfloat16* __restrict__ a_lo, int B, int H) {
+    constexpr int WP = W + 6;  // 3-pixel zero halo left and right
+    __shared__ float tile[3][7][WP];
     const int Ho = H / 2, Wo = W / 2;
-    const long total = (long)B * Ho * Wo * 24;  // 24 groups of 8 columns
-    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int g = (int)(idx % 24);
-        const long pix = idx / 24;
-        const int ow = (int)(pix % Wo);
-        const int oh = (int)((pix / Wo) % Ho);
-        const int b = (int)(pix / ((long)Wo * Ho));
+    const int b = blockIdx.x / Ho, oh = blockIdx.x - b * Ho;
+    for (int e = threadIdx.x; e < 3 * 7 * WP; e += 256) {
+        const int col = e % WP;
+        const int r = (e / WP) % 7;
+        const int c = e / (WP * 7);
+        const int ih = oh * 2 + r - 3, iw = col - 3;
+        float v = 0.f;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(x + (((long)b * 3 + c) * H + ih) * W + iw);
+        tile[c][r][col] = v;
+    }
+    __syncthreads();
+    const long row0 = ((long)b * Ho + oh) * Wo;
+    for (int item = threadIdx.x; item < Wo * 24; item += 256) {
+        const int ow = item / 24, g = item - ow * 24;
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -130,9 +151,8 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* _
             float val = 0.f;
             if (k < 147) {
                 const int tap = k / 3, c = k - tap * 3;
-                const int r = tap / 7, s = tap - r * 7;
-                const int ih = oh * 2 + r - 3, iw = ow * 2 + s - 3;
-                if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = __ldg(x + (((long)b * 3 + c) * H + ih) * W + iw);
+                const int r = tap / 7, s2 = tap - r * 7;
+                val = tile[c][r][2 * ow + s2];
             }
             v[j] = val;
         }
@@ -142,6 +162,7 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* _
             hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
             lo[j] = pack_lo2(v[2 * j] - __uint_as_float(hi[j] << 16), v[2 * j + 1] - __uint_as_float(hi[j] & 0xffff0000u));
         }
+        const long idx = (row0 + ow) * 24 + g;
         reinterpret_cast<uint4*>(a_hi)[idx] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         if (a_lo != nullptr) reinterpret_cast<uint4*>(a_lo)[idx] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
@@ -173,8 +194,8 @@ extern "C" int gdrn_unpack_wgrad(const float* ws, float* grad, int O, int I, int
                                  long ks_stride, long so, long si, long sr, long ss, int flip, int accumulate,
                                  void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    const long total = (long)O * KH * KW * I;
-    unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, stream>>>(ws, grad, O, I, KH, KW, ipad, krow, ksplit, ks_stride, so, si,
+    const long total = (long)O * I;
+    unpack_wgrad_kernel<<<grid_for(total, 128), 128, 0, stream>>>(ws, grad, O, I, KH, KW, ipad, krow, ksplit, ks_stride, so, si,
                                                                  sr, ss, flip, accumulate);
     GDRN_CUDA_OK(cudaGetLastError());
     count_launch();
@@ -183,9 +204,8 @@ extern "C" int gdrn_unpack_wgrad(const float* ws, float* grad, int O, int I, int
 
 extern "C" int gdrn_stem_im2col(const float* x, void* a_hi, void* a_lo, int B, int H, int W, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    if (H % 2 || W % 2) return set_error(GDRN_ERR_ARG, "stem_im2col: H, W must be even");
-    const long total = (long)B * (H / 2) * (W / 2) * 24;
-    stem_im2col_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo, B, H, W);
+    if (H % 2 || W != 256) return set_error(GDRN_ERR_ARG, "stem_im2col: expects 256-wide crops (INPUT_RES=256), even height");
+    stem_im2col_kernel<256><<<B * (H / 2), 256, 0, stream>>>(x, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo, B, H);
     GDRN_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;

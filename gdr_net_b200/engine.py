@@ -111,7 +111,7 @@ class Engine:
             begin = 0
             for n, (src, out, O, I, KH, KW, opad, ipad, krow, so, si, sr, ss, flip) in enumerate(jobs):
                 arr[n] = (src.data_ptr(), out.hi_ptr, out.lo_ptr or 0, so, si, sr, ss, begin, O, I, KH, KW, opad, ipad, krow, flip)
-                begin += (opad * krow + 255) // 256 * 256
+                begin += (opad * ipad + 255) // 256 * 256  # work items = (dst row, dst channel) pairs
             self._pack_jobs = torch.from_numpy(arr.view(np.uint8).copy()).to(self.dev)
             self._pack_njobs, self._pack_blocks = len(jobs), begin // 256
             self._pack_srcs = [j[0] for j in jobs]  # keep the sources alive
@@ -149,7 +149,7 @@ class Engine:
     def _pack_stem(self):
         """7x7 stem weight [64][3][7][7] -> [64][192] with k = (r*7+s)*3 + c (matches gdrn_stem_im2col)."""
         w = self.model.backbone.conv1.weight
-        out = self.wf.get("stem") or PT((64, 192), self.planes, device=self.dev)
+        out = self.wf.get("stem") or PT((64, 192), self.planes, device=self.dev, zero=True)  # cols 147..191 stay zero
         ops._pack(w, out, 64, 3, 7, 7, 64, 3, 192, 147, 49, 7, 1, 0)
         self.wf["stem"] = out
 
