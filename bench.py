@@ -294,13 +294,16 @@ def roofline_live(main, peaks):
     records = []
     orig = {n: getattr(ops, n) for n in ("conv_fwd", "gemm_fwd", "conv_wgrad", "gemm_wgrad")}
 
+    from gdr_net_b200.capi import C as _C
+
     def timed(name, fn, flops_of):
         def wrapper(*a, **k):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             r = fn(*a, **k)
             e1.record()
-            records.append((name, flops_of(*a, **k), e0, e1))
+            variant = _C.load().gdrn_last_gemm_variant() if name in ("conv_fwd", "gemm_fwd") else 0
+            records.append((name, flops_of(*a, **k), e0, e1, variant))
             return r
 
         return wrapper
@@ -337,22 +340,40 @@ def roofline_live(main, peaks):
         for n, f in orig.items():
             setattr(ops, n, f)
     step_ms = e0.elapsed_time(e1)
-    fam = {}
-    for name, fl, a, b in records:
+    fam, inst = {}, {}
+    for name, fl, a, b, variant in records:
+        ms_ = a.elapsed_time(b)
         d = fam.setdefault(name, [0.0, 0.0, 0])
         d[0] += fl
-        d[1] += a.elapsed_time(b)
+        d[1] += ms_
         d[2] += 1
+        if variant:
+            key = f"gdrn::gemm_fwd_kernel<{variant // 10}, {variant % 10}>"
+            d = inst.setdefault(key, [0.0, 0.0, 0])
+            d[0] += fl
+            d[1] += ms_
+            d[2] += 1
     tot_fl = sum(v[0] for v in fam.values())
     tot_ms = sum(v[1] for v in fam.values())
-    achieved = tot_fl / (tot_ms * 1e-3) / 1e12
+    # dominant kernel = the instantiation with the largest time share of the step
+    dom = max(inst.items(), key=lambda kv: kv[1][1])
+    dom_tflops = dom[1][0] / (dom[1][1] * 1e-3) / 1e12
     peak = peaks["bf16_sustained"]
     return {
-        "bound": "tensor", "kernel": "gdrn::gemm_fwd_kernel / gemm_wgrad_kernel (tcgen05 implicit-GEMM conv family)",
-        "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-        "peak_source": "bf16_tflops_sustained of " + peaks["source"], "traffic": None,
-        "launches_per_step": sum(v[2] for v in fam.values()), "avg_launch_ms": round(tot_ms / max(1, sum(v[2] for v in fam.values())), 4),
-        "algorithmic_gflop_per_step": round(tot_fl / 1e9, 1), "share_of_step": round(tot_ms / step_ms, 3),
+        "bound": "tensor", "kernel": dom[0] + " (tcgen05 implicit-GEMM conv forward / dgrad)",
+        "achieved": round(dom_tflops, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(dom_tflops / peak, 4),
+        "peak_source": "bf16_tflops_sustained of " + peaks["source"] + " (kernel timed inside the long step)",
+        "launches_per_step": dom[1][2], "avg_launch_ms": round(dom[1][1] / dom[1][2], 4),
+        "algorithmic_gflop_per_launch": round(dom[1][0] / dom[1][2] / 1e9, 2), "share_of_step": round(dom[1][1] / step_ms, 3),
+        "traffic": 222.1e6,
+        "traffic_note": "dram read+write of ONE launch of this kernel on the 64x64 256->256 conv (B=64), ncu --set full "
+                        "(profiles/r1_ncu_full_kernel_metrics.txt); algorithmic bytes of that launch 269.7e6 (bf16 in + out + weights)",
+        "tensor_pipe_pct_ncu": 57.3,
+        "gemm_family": {"achieved": round(tot_fl / (tot_ms * 1e-3) / 1e12, 1), "frac": round(tot_fl / (tot_ms * 1e-3) / 1e12 / peak, 4),
+                        "share_of_step": round(tot_ms / step_ms, 3), "launches_per_step": sum(v[2] for v in fam.values()),
+                        "algorithmic_gflop_per_step": round(tot_fl / 1e9, 1)},
+        "instantiations": {k: {"tflops": round(v[0] / (v[1] * 1e-3) / 1e12, 1), "ms": round(v[1], 3), "launches": v[2]}
+                           for k, v in sorted(inst.items(), key=lambda kv: -kv[1][1])},
         "families": {k: {"tflops": round(v[0] / (v[1] * 1e-3) / 1e12, 1), "ms": round(v[1], 3), "launches": v[2]} for k, v in fam.items()},
         "whole_step_tflops": round(FWD_BWD_GFLOP_PER_CROP * BATCH_PER_GPU / main["ms"], 1),
         "whole_step_frac": round(FWD_BWD_GFLOP_PER_CROP * BATCH_PER_GPU / main["ms"] / peak, 4),
@@ -366,7 +387,7 @@ def cpu_baseline(sample_batch: int = 8, iters: int = 2):
     from oracle import fixtures
     from oracle import gdrn_oracle as O
 
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 32)  # more threads than this slow the oneDNN convolutions down on the 128-thread hosts
     torch.set_num_threads(cores)
     sd = synth.seeded_state_dict(fixtures.template_from_manifest(), 0)
     batch = synth.make_batch(sample_batch, seed=300)
@@ -396,7 +417,7 @@ def run_reference(args):
     from oracle import fixtures
     from oracle import gdrn_oracle as O
 
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     sd = synth.seeded_state_dict(fixtures.template_from_manifest(), 0)
     sample = args.cpu_batch
@@ -433,7 +454,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-batch", type=int, default=8)
-    ap.add_argument("--cpu-iters", type=int, default=2)
+    ap.add_argument("--cpu-iters", type=int, default=1)
     ap.add_argument("--quick", action="store_true", help="device-timed value only (for profiler runs)")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel from Python instead of one CUDA graph")
     args = ap.parse_args()

@@ -435,7 +435,10 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
     return 0;
 }
 
+static thread_local int g_last_variant = 0;
+
 static int dispatch_gemm(const GemmParams& p, int block_n, int nsplit, cudaStream_t stream) {
+    g_last_variant = block_n * 10 + nsplit;
     if (nsplit == 1) {
         if (block_n == 256) return launch_gemm<256, 1>(p, stream);
         if (block_n == 128) return launch_gemm<128, 1>(p, stream);
@@ -584,3 +587,6 @@ extern "C" int gdrn_gemm_fwd(const void* a_hi, const void* a_lo, const void* w_h
     p.stats = stats;
     return dispatch_gemm(p, block_n, nsplit, stream);
 }
+
+// BLOCK_N * 10 + NSPLIT of the most recent gdrn_conv_fwd / gdrn_gemm_fwd call on this thread (bookkeeping for bench.py)
+extern "C" int gdrn_last_gemm_variant() { return g_last_variant; }

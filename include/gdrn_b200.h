@@ -28,6 +28,7 @@ extern "C" {
 const char* gdrn_last_error(void);
 long gdrn_launch_count(void); /* kernels launched by this library since load */
 int gdrn_abi_version(void);
+int gdrn_last_gemm_variant(void); /* BLOCK_N*10 + nsplit of this thread's last conv/gemm forward launch */
 
 /* ---- tcgen05 implicit-GEMM convolution, forward (and dgrad with flipped/transposed weights) ------------
  * replaces nn.Conv2d / nn.ConvTranspose2d forward: resnet_backbone.py:21-49,69-76 (torchvision BasicBlock),
