@@ -199,7 +199,7 @@ def _check_supported(cfg):
 
 
 class GDRN(nn.Module):
-    def __init__(self, cfg, backbone, rot_head_net, trans_head_net=None, pnp_net=None, precision: str = "bf16"):
+    def __init__(self, cfg, backbone, rot_head_net, trans_head_net=None, pnp_net=None, precision: str = "half"):
         super().__init__()
         assert cfg.MODEL.CDPN.NAME == "GDRN", cfg.MODEL.CDPN.NAME
         _check_supported(cfg)
@@ -211,7 +211,7 @@ class GDRN(nn.Module):
         self.concat = cfg.MODEL.CDPN.ROT_HEAD.ROT_CONCAT
         self.r_out_dim, self.mask_out_dim, self.region_out_dim = get_xyz_mask_region_out_dim(cfg)
         self._engine: Optional[Engine] = None
-        self.precision = precision  # "bf16" (1 tcgen05 pass) | "fp32x3" (hi/lo planes, 3 passes, fp32-faithful)
+        self.precision = {"bf16": "half", "fp16": "half"}.get(precision, precision)  # "half" (1 pass) | "fp32x3" (hi/lo planes)
 
     @property
     def engine(self) -> Engine:
@@ -279,7 +279,7 @@ def _get_event_storage():
         return None
 
 
-def build_model_optimizer(cfg, precision: str = "bf16"):
+def build_model_optimizer(cfg, precision: str = "half"):
     """reference GDRN.py:550-724"""
     backbone_cfg = cfg.MODEL.CDPN.BACKBONE
     r_head_cfg = cfg.MODEL.CDPN.ROT_HEAD

@@ -23,6 +23,9 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
     "-diag-suppress", "550",
+    # 16-bit storage format of the activation / weight planes: 1 = fp16 (11-bit mantissa, TF32-equivalent; default),
+    # 0 = bf16.  See csrc/ptx.cuh.
+    "-DGDRN_STORE_F16=" + os.environ.get("GDRN_STORE_F16", "1"),
 ]
 
 

@@ -4,6 +4,7 @@
 #include <atomic>
 
 #include "gdrn_internal.h"
+#include "ptx.cuh"
 
 namespace gdrn {
 
@@ -64,7 +65,7 @@ int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims
         es[i] = 1;
     }
     for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, es,
+    CUresult r = fn(out, GDRN_STORE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -82,3 +83,7 @@ int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims
 extern "C" const char* gdrn_last_error() { return gdrn::g_err; }
 extern "C" long gdrn_launch_count() { return gdrn::g_launches.load(); }
 extern "C" int gdrn_abi_version() { return 1; }
+
+// 0 = bf16 planes, 1 = fp16 planes (compile-time GDRN_STORE_F16); the host side mirrors dtype and lo-plane scale
+extern "C" int gdrn_storage_format() { return GDRN_STORE_F16; }
+extern "C" float gdrn_lo_scale() { return gdrn::kLoScale; }

@@ -18,8 +18,7 @@ __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        f[2 * j] = __uint_as_float(w[j] << 16);
-        f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+        unpack_hi2(w[j], f[2 * j], f[2 * j + 1]);
     }
 }
 // value = hi (+ lo)
@@ -41,8 +40,7 @@ __device__ __forceinline__ void store8(bf16* hi, bf16* lo, long off8, const floa
     uint32_t h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        h[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-        l[j] = pack_lo2(f[2 * j] - __uint_as_float(h[j] << 16), f[2 * j + 1] - __uint_as_float(h[j] & 0xffff0000u));
+        split2(f[2 * j], f[2 * j + 1], h[j], l[j]);
     }
     reinterpret_cast<uint4*>(hi)[off8] = make_uint4(h[0], h[1], h[2], h[3]);
     if (lo != nullptr) reinterpret_cast<uint4*>(lo)[off8] = make_uint4(l[0], l[1], l[2], l[3]);

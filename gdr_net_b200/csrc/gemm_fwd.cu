@@ -208,11 +208,7 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (single thread)
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
-            constexpr uint32_t idesc_hl = make_idesc_f16(kBlockM, BLOCK_N, 0, 0, 1, 0);
-            constexpr uint32_t idesc_lh = make_idesc_f16(kBlockM, BLOCK_N, 0, 0, 0, 1);
-            (void)idesc_hl;
-            (void)idesc_lh;
+            constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -328,10 +324,7 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
                                 if (col0 + 2 * j >= p.N) a = 0.f;
                                 if (col0 + 2 * j + 1 >= p.N) b = 0.f;
                             }
-                            hi[j] = pack_bf16x2(a, b);
-                            const float ra = a - __uint_as_float(hi[j] << 16);
-                            const float rb = b - __uint_as_float(hi[j] & 0xffff0000u);
-                            lo[j] = pack_lo2(ra, rb);
+                            split2(a, b, hi[j], lo[j]);
                         }
                         const int ncopy = full_chunk ? 4 : ((min(p.ldc, col0 + 32) - col0) / 8);
                         uint4* dh = reinterpret_cast<uint4*>(out_hi + grow * p.ldc + col0);

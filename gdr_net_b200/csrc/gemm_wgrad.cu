@@ -167,11 +167,7 @@ __global__ void __launch_bounds__(192, 1) gemm_wgrad_kernel(const __grid_constan
         }
     } else if (warp == 1) {
         if (lane == 0 && nkb > 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, N_TILE, 1, 1);
-            constexpr uint32_t idesc_hl = make_idesc_f16(128, N_TILE, 1, 1, 1, 0);
-            constexpr uint32_t idesc_lh = make_idesc_f16(128, N_TILE, 1, 1, 0, 1);
-            (void)idesc_hl;
-            (void)idesc_lh;
+            constexpr uint32_t idesc = make_idesc(128, N_TILE, 1, 1);
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < nkb; ++kb) {

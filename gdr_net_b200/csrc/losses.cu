@@ -26,8 +26,7 @@ __device__ __forceinline__ void store_row_bf16(bf16* hi, bf16* lo, long row, int
         uint32_t h[4], l[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            h[q] = pack_bf16x2(v[j + 2 * q], v[j + 2 * q + 1]);
-            l[q] = pack_lo2(v[j + 2 * q] - __uint_as_float(h[q] << 16), v[j + 2 * q + 1] - __uint_as_float(h[q] & 0xffff0000u));
+            split2(v[j + 2 * q], v[j + 2 * q + 1], h[q], l[q]);
         }
         *reinterpret_cast<uint4*>(hi + row * ld + j) = make_uint4(h[0], h[1], h[2], h[3]);
         if (lo != nullptr) *reinterpret_cast<uint4*>(lo + row * ld + j) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -160,8 +159,7 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__
                 const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    gin[j + 2 * t] = __uint_as_float(w[t] << 16);
-                    gin[j + 2 * t + 1] = __uint_as_float(w[t] & 0xffff0000u);
+                    unpack_hi2(w[t], gin[j + 2 * t], gin[j + 2 * t + 1]);
                 }
                 if (din_lo != nullptr) {
                     const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(din_lo + pix * kPnpLd + j));
@@ -545,11 +543,10 @@ __global__ void __launch_bounds__(128) pose_loss_kernel(const PoseParams p) {
         for (int k = 9; k < 16; ++k) g[k] = 0.f;
         for (int k = 0; k < 64; k += 2) {
             const float a = k < 16 ? g[k] : 0.f, c = k + 1 < 16 ? g[k + 1] : 0.f;
-            const uint32_t h = pack_bf16x2(a, c);
+            uint32_t h, l;
+            split2(a, c, h, l);
             *reinterpret_cast<uint32_t*>(p.dy_hi + (long)b * 64 + k) = h;
-            if (p.dy_lo != nullptr)
-                *reinterpret_cast<uint32_t*>(p.dy_lo + (long)b * 64 + k) =
-                    pack_lo2(a - __uint_as_float(h << 16), c - __uint_as_float(h & 0xffff0000u));
+            if (p.dy_lo != nullptr) *reinterpret_cast<uint32_t*>(p.dy_lo + (long)b * 64 + k) = l;
         }
     }
 }

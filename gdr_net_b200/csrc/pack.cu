@@ -31,9 +31,10 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, __nv_bfloat16*
             }
             v = __ldg(src + o * so + i * si + r * sr + s * ss);
         }
-        const float h = bf16_round(v);
-        dst_hi[idx] = __float2bfloat16(h);
-        if (dst_lo != nullptr) dst_lo[idx] = __float2bfloat16(v - h);
+        uint16_t h, l;
+        split1(v, h, l);
+        reinterpret_cast<uint16_t*>(dst_hi)[idx] = h;
+        if (dst_lo != nullptr) reinterpret_cast<uint16_t*>(dst_lo)[idx] = l;
     }
 }
 
@@ -85,9 +86,10 @@ __global__ void __launch_bounds__(256) pack_weight_batched_kernel(const PackJob*
                 }
                 v = __ldg(sp + r * job.sr + s2 * job.ss);
             }
-            const float h = bf16_round(v);
-            dh[(long)tap * job.ipad] = __float2bfloat16(h);
-            if (dl != nullptr) dl[(long)tap * job.ipad] = __float2bfloat16(v - h);
+            uint16_t h, l;
+            split1(v, h, l);
+            reinterpret_cast<uint16_t*>(dh)[(long)tap * job.ipad] = h;
+            if (dl != nullptr) reinterpret_cast<uint16_t*>(dl)[(long)tap * job.ipad] = l;
         }
     }
 }
@@ -158,8 +160,7 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-            lo[j] = pack_lo2(v[2 * j] - __uint_as_float(hi[j] << 16), v[2 * j + 1] - __uint_as_float(hi[j] & 0xffff0000u));
+            split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
         }
         const long idx = (row0 + ow) * 24 + g;
         reinterpret_cast<uint4*>(a_hi)[idx] = make_uint4(hi[0], hi[1], hi[2], hi[3]);

@@ -161,30 +161,66 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_maj
            ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// ---------------------------------------------------------------- misc
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+// ---------------------------------------------------------------- 16-bit storage format of the (hi, lo) planes
+// GDRN_STORE_F16 = 0: hi = bf16(x),  lo = bf16(x - hi)               (8 + 8 bits; fp32 exponent range)
+// GDRN_STORE_F16 = 1: hi = fp16(x),  lo = fp16((x - hi) * 2^11)       (11 + 11 bits: the single-plane mode has the
+//     mantissa of TF32 -- what cuDNN uses for the reference's fp32 convolutions -- and the two-plane mode 22 bits.
+//     The scaled residual has the magnitude of x itself, so it needs no extra exponent range; the scale is divided
+//     out exactly in the GEMM epilogues (cross-term accumulator) and in load8().  Gradients are kept in range by a
+//     static loss scale applied by the engine (Engine.grad_scale), like AMP's GradScaler in the reference's configs.)
+// Both planes must share one format: tcgen05.mma kind::f16 rejects mixed bf16 x fp16 operands (illegal instruction).
+#ifndef GDRN_STORE_F16
+#define GDRN_STORE_F16 0
+#endif
+#if GDRN_STORE_F16
+constexpr int kOperandFmt = 0;  // instruction-descriptor a/b format: F16
+constexpr float kLoScale = 2048.f;
+constexpr float kLoInvScale = 1.f / 2048.f;
+__device__ __forceinline__ uint32_t pack_hi2(float a, float b) {  // a -> low half, b -> high half
     uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
     return r;
 }
-__device__ __forceinline__ float bf16_round(float x) {  // round-to-nearest-even bf16, returned as fp32
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.0f), "f"(x));
-    return __uint_as_float(r << 16);
+__device__ __forceinline__ void unpack_hi2(uint32_t w, float& a, float& b) {
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(a), "=f"(b) : "r"(w));
 }
-// ---- lo plane of the (hi, lo) pair: lo = bf16(x - bf16(x)) (16-bit operands).  NOTE: a scaled fp16 residual
-// (19 bits) was tried; tcgen05.mma kind::f16 rejects mixed bf16 x fp16 operands (illegal instruction), so both
-// planes share one format.
+#else
+constexpr int kOperandFmt = 1;  // BF16
+constexpr float kLoScale = 1.f;
 constexpr float kLoInvScale = 1.f;
-__device__ __forceinline__ uint32_t pack_lo2(float ra, float rb) {  // residuals of (low half, high half)
+__device__ __forceinline__ uint32_t pack_hi2(float a, float b) {
     uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(rb), "f"(ra));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
     return r;
 }
-__device__ __forceinline__ void unpack_lo2(uint32_t w, float& a, float& b) {
+__device__ __forceinline__ void unpack_hi2(uint32_t w, float& a, float& b) {
     a = __uint_as_float(w << 16);
     b = __uint_as_float(w & 0xffff0000u);
 }
-__device__ __forceinline__ float bf16_bits_to_f32(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
+#endif
+__device__ __forceinline__ uint32_t pack_lo2(float ra, float rb) { return pack_hi2(ra * kLoScale, rb * kLoScale); }
+__device__ __forceinline__ void unpack_lo2(uint32_t w, float& a, float& b) {
+    unpack_hi2(w, a, b);
+    a *= kLoInvScale;
+    b *= kLoInvScale;
+}
+// (a, b) -> packed hi pair and packed lo pair (residuals after rounding to the hi format)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& h, uint32_t& l) {
+    h = pack_hi2(a, b);
+    float ha, hb;
+    unpack_hi2(h, ha, hb);
+    l = pack_lo2(a - ha, b - hb);
+}
+// scalar versions (weight packing): 16-bit patterns
+__device__ __forceinline__ void split1(float x, uint16_t& h, uint16_t& l) {
+    uint32_t hh, ll;
+    split2(x, 0.f, hh, ll);
+    h = (uint16_t)(hh & 0xffffu);
+    l = (uint16_t)(ll & 0xffffu);
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | ((uint32_t)kOperandFmt << 7) | ((uint32_t)kOperandFmt << 10) | ((uint32_t)a_mn_major << 15) |
+           ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 }  // namespace gdrn

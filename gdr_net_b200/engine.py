@@ -4,8 +4,9 @@ Mirrors reference `GDRN.forward` (core/gdrn_modeling/models/GDRN.py:83-306), `gd
 autograd backward of both, but every tensor op is one of our sm_100a kernels (gdr_net_b200/csrc).  PyTorch is
 used for device memory, streams and the autograd/DDP boundary only.
 
-precision = "bf16"   : activations/gradients are bf16 NHWC tensors, one tcgen05 pass per k-step
-precision = "fp32x3" : (hi, lo) bf16 planes, three tcgen05 passes (fp32-faithful; the 1e-3 parity mode)
+precision = "half"   : activations / gradients are 16-bit NHWC tensors (fp16 by default, bf16 if the library is built with
+                       GDRN_STORE_F16=0), one tcgen05 pass per k-step.  "fp16" / "bf16" are accepted as aliases.
+precision = "fp32x3" : (hi, lo) 16-bit planes (22-bit operands with fp16), three tcgen05 passes: the 1e-3 parity mode
 """
 from __future__ import annotations
 
@@ -34,12 +35,13 @@ class _BN:
 
 
 class Engine:
-    def __init__(self, model, precision: str = "bf16"):
-        assert precision in ("bf16", "fp32x3")
+    def __init__(self, model, precision: str = "half"):
+        precision = {"bf16": "half", "fp16": "half"}.get(precision, precision)
+        assert precision in ("half", "fp32x3"), precision
         C.load()  # fail loudly if the CUDA library is missing
         self.model = model
         self.precision = precision
-        self.planes = 1 if precision == "bf16" else 2
+        self.planes = 1 if precision == "half" else 2
         self.dev = next(model.parameters()).device
         if self.dev.type != "cuda":
             raise RuntimeError("gdr_net_b200 engine needs CUDA parameters (model.to('cuda')); no CPU fallback exists")
@@ -70,6 +72,13 @@ class Engine:
         self.wf: Dict[str, PT] = {}
         self.wd: Dict[str, PT] = {}
         self.grad_hook = None  # optional callable(engine) invoked at bucket boundaries during backward (DDP overlap)
+        # fp16 planes: activation gradients are carried with a static power-of-two loss scale (exactly removed from the
+        # fp32 parameter gradients at the end of backward), like the GradScaler of the reference's AMP configs
+        self.storage_name = ops.storage_format()[2]
+        self.grad_scale = 1024.0 if self.storage_name == "fp16" else 1.0
+        from .dist import SEGMENTS, segment_bounds
+
+        self._seg = segment_bounds(self.named_params, SEGMENTS)
 
     # ------------------------------------------------------------------------------------------ weights
     def _conv_modules(self):
@@ -369,6 +378,8 @@ class Engine:
         B, aux, pn = S["B"], S["aux"], m.pnp_net
         self.flat_grad.zero_()
         gw = grad_losses.float().contiguous()
+        if self.grad_scale != 1.0:
+            gw = gw * self.grad_scale  # the whole backward is linear in the loss gradients
         self._pose(S, gw=gw[5:8].contiguous())
         dy9 = S["dy9"]
         tmp = torch.empty(1024, device=dev)
@@ -401,8 +412,7 @@ class Engine:
             self._wgrad_conv(du, L["x_in"], pf[ci], f"pnp_net.features.{ci}.weight")
             g = self._dgrad_conv(du, pf[ci], f"pnp_net.features.{ci}")
         d_pnp_in = g  # [B,64,64,128]
-        if self.grad_hook:
-            self.grad_hook(self, "pnp_net")
+        self._segment_done("pnp_net")
 
         # ---- glue + per-pixel losses backward (one fused pass over the logits)
         dlog = PT((B * 4096, 128), self.planes, device=dev)
@@ -433,8 +443,7 @@ class Engine:
         # ConvTranspose2d weight is IOHW [512][256][3][3] with flipped taps relative to the equivalent conv
         ops.unpack_wgrad(buf, self.grads["rot_head_net.features.0.weight"], 256, 512, 3, 3, 512, ks, kss, 9, 256 * 9, 3, 1, flip=1)
         g = ops.conv_fwd(du, self.wd["deconv"], 512, 3, 3, 2, 1)  # [B,8,8,512]
-        if self.grad_hook:
-            self.grad_hook(self, "rot_head_net")
+        self._segment_done("rot_head_net")
 
         # ---- backbone (torchvision BasicBlock backward)
         ga, gb = g, None
@@ -453,8 +462,8 @@ class Engine:
                 ga, gb = dx_main, dx_ds
             else:
                 ga, gb = dx_main, gout
-            if self.grad_hook and p.endswith(".0") and not p.startswith("backbone.layer1"):
-                self.grad_hook(self, p[:-2])  # all gradients of backbone.layerN are final
+            if p.endswith(".0") and not p.startswith("backbone.layer1"):
+                self._segment_done(p[:-2])  # all gradients of backbone.layerN are final
         g_pool = ops.add2(ga, gb)
         St = S["stem"]
         g_a0 = ops.maxpool_bwd(St["pool_arg"], g_pool)
@@ -462,10 +471,21 @@ class Engine:
         buf, ks, kss = ops.gemm_wgrad(du0.view(B * 128 * 128, 64), St["a_col"], self.ws)
         # ws rows [64][192] with k = (r*7+s)*3 + c  ->  OIHW [64][3][7][7]
         ops.unpack_wgrad(buf, self.grads["backbone.conv1.weight"], 64, 3, 7, 7, 3, ks, kss, 147, 49, 7, 1, krow=192)
-        if self.grad_hook:
-            self.grad_hook(self, "backbone.stem")  # layer1 + bn1 + conv1
+        self._segment_done("backbone.stem")  # layer1 + bn1 + conv1
         self.saved = None
         return self.grads
+
+    def _segment_done(self, stage: str):
+        """All gradients of a sub-network are final: remove the loss scale from its slice of the flat buffer, then hand
+        it to the data-parallel hook (bucketed all-reduce on a side stream)."""
+        if self.grad_scale != 1.0:
+            names = ("backbone.conv1", "backbone.bn1", "backbone.layer1") if stage == "backbone.stem" else (stage,)
+            lo = min(self._seg[n][0] for n in names)
+            hi = max(self._seg[n][1] for n in names)
+            # TODO(round 2): fold 1/scale into unpack_wgrad / the BN, GN and bias-gradient kernels
+            self.flat_grad[lo:hi].mul_(1.0 / self.grad_scale)
+        if self.grad_hook:
+            self.grad_hook(self, stage)
 
     def _leaky_bwd(self, g: PT, y: PT) -> PT:
         out = ops.like(g)

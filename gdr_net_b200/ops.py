@@ -16,6 +16,24 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+_FMT = {}
+
+
+def storage_format():
+    """(torch dtype, lo-plane scale, name) of the library's compile-time 16-bit storage format (csrc/ptx.cuh)."""
+    if not _FMT:
+        dll = C.load()
+        dll.gdrn_lo_scale.restype = ctypes.c_float
+        f16 = bool(dll.gdrn_storage_format())
+        _FMT.update(dtype=torch.float16 if f16 else torch.bfloat16, lo_scale=float(dll.gdrn_lo_scale()), name="fp16" if f16 else "bf16")
+    return _FMT["dtype"], _FMT["lo_scale"], _FMT["name"]
+
+
+def round_storage(x: torch.Tensor) -> torch.Tensor:
+    """x rounded to the single-plane storage format, as fp32 (what a planes=1 operand effectively is)."""
+    return x.to(storage_format()[0]).float()
+
+
 def ptr(t):
     return None if t is None else t.data_ptr()
 
@@ -30,7 +48,7 @@ class PT:
         self.planes = planes
         if buf is None:
             alloc = torch.zeros if zero else torch.empty
-            buf = alloc((planes,) + self.shape, dtype=torch.bfloat16, device=device)
+            buf = alloc((planes,) + self.shape, dtype=storage_format()[0], device=device)
         self.buf = buf
 
     @property
@@ -59,7 +77,7 @@ class PT:
     def float(self):
         x = self.buf[0].float()
         if self.planes == 2:
-            x = x + self.buf[1].float()
+            x = x + self.buf[1].float() * (1.0 / storage_format()[1])
         return x
 
     def view(self, *shape):

@@ -3,9 +3,10 @@
   (b) the CPU oracle (oracle/gdrn_oracle.py) on the same seeded inputs.
 
 Tolerances (BASELINE.json north_star): outputs within 1e-3 relative fp32, region argmax bit-exact -- asserted in
-the fp32-faithful "fp32x3" mode (three tcgen05 passes over hi/lo bf16 planes).  The single-pass "bf16" mode is
-the throughput mode; its deviation is bounded by bf16 operand rounding (2^-9 per operand per layer) and is
-asserted at the looser, documented bound below.
+the fp32-faithful "fp32x3" mode (three tcgen05 passes over hi/lo fp16 planes = 22-bit operands).  The single-pass
+"half" mode (fp16 operands: 11-bit mantissa, the same as the TF32 convolutions cuDNN runs for the reference) is the
+throughput mode; its deviation is bounded by operand rounding (2^-12 per tensor per layer, accumulating over ~130
+roundings) and is asserted at the looser, documented bound below.
 """
 import os
 
@@ -19,10 +20,10 @@ from gdr_net_b200.config import a6_config
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 REL_FP32 = 1e-3          # north-star tolerance (dense maps, losses), fp32x3 mode
-REL_POSE = 3e-3          # rot / trans / ADD in fp32x3 mode: the rot6d normalisation + allo->ego chain amplifies the
-                         # ~6e-4 error of the 9 regressed numbers (16-bit operand planes, see DESIGN.md "Precision")
-REL_BF16 = 0.5           # sanity bound for the single-pass bf16 mode on this RANDOM-weight 50-layer net: 2^-9 operand
-                         # rounding accumulates ~linearly (measured ~0.13 relative at layer4, ~0.3 at the logits)
+REL_POSE = 1e-3          # rot / trans / ADD in fp32x3 mode (measured 1e-4 .. 2.5e-4)
+REL_HALF = 0.15          # sanity bound for the single-pass fp16 mode on this RANDOM-weight 50-layer net: 2^-12 operand
+                         # rounding accumulates ~linearly (measured 0.02 relative at layer4, 0.056 at the logits, 0.08 on the
+                         # pose); a bf16 build (GDRN_STORE_F16=0) measures 0.13 / 0.34 here
 
 
 def _rel(a, b):
@@ -57,7 +58,7 @@ def _cuda_batch(batch):
     return {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32x3", REL_FP32), ("bf16", REL_BF16)])
+@pytest.mark.parametrize("precision,tol", [("fp32x3", REL_FP32), ("half", REL_HALF)])
 def test_eval_forward_b2_vs_golden(sd, golden_dir, precision, tol):
     g = np.load(os.path.join(golden_dir, "eval_b2.npz"))
     model, _ = _model(sd, precision)
@@ -73,7 +74,7 @@ def test_eval_forward_b2_vs_golden(sd, golden_dir, precision, tol):
           f"trans {_rel(out['trans'], g['trans']):.2e}")
     assert _rel(head, ref) < tol, _rel(head, ref)
     assert _relmax(head, ref) < 2 * tol, _relmax(head, ref)
-    ptol = REL_POSE if precision == "fp32x3" else 2.0
+    ptol = REL_POSE if precision == "fp32x3" else 0.5
     assert _rel(out["rot"], g["rot"]) < ptol and _rel(out["trans"], g["trans"]) < ptol
     agree = (head[:, 4:].argmax(1).numpy().astype(np.uint8) == g["region_argmax"]).mean()
     if precision == "fp32x3":
@@ -84,15 +85,15 @@ def test_eval_forward_b2_vs_golden(sd, golden_dir, precision, tol):
         assert not (mism & margin_ok).any()
         assert agree > 0.995  # random-weight logits have many near-ties; every mismatch is inside the tie margin (above)
     else:
-        print(f"[bf16] region argmax agreement {agree:.4f}")
-        assert agree > 0.5
+        print(f"[half] region argmax agreement {agree:.4f}")
+        assert agree > 0.85
 
 
 # Gradient tolerance: the network is non-smooth (ReLU, L1 losses, max-pool), so gradients are discontinuous in the
 # forward values.  The reference's OWN fp32 gradients differ from its fp64 evaluation by 1.5e-2 relative L2 at the
-# stem (tools/noise_floor.py; forward difference only 4e-5).  We require <= 0.12 per tensor and cosine > 0.995 overall
+# stem (tools/noise_floor.py; forward difference only 4e-5).  We require <= 0.06 per tensor and cosine > 0.995 overall
 # in fp32x3 mode; per-op backward kernels are tested to ~1e-4 in tests/test_ops_gpu.py.
-@pytest.mark.parametrize("precision,tol,gtol", [("fp32x3", REL_FP32, 0.12), ("bf16", REL_BF16, 3.0)])
+@pytest.mark.parametrize("precision,tol,gtol", [("fp32x3", REL_FP32, 0.06), ("half", REL_HALF, 1.0)])
 @pytest.mark.parametrize("case,seed,sym", [("train_b4", 1, False), ("train_sym_b4", 2, True)])
 def test_train_fwd_bwd_b4(sd, golden_dir, precision, tol, gtol, case, seed, sym):
     from oracle import gdrn_oracle as O
@@ -114,7 +115,7 @@ def test_train_fwd_bwd_b4(sd, golden_dir, precision, tol, gtol, case, seed, sym)
         assert abs(float(v) - ref) <= tol * abs(ref), (k, float(v), ref)
     # logging side effect values (vis/*) against the reference's EventStorage scalars
     if "vis/error_R" in g.files:
-        assert abs(model.last_vis_dict["vis/error_R"] - float(g["vis/error_R"])) < (0.2 if precision == "fp32x3" else 180.0)
+        assert abs(model.last_vis_dict["vis/error_R"] - float(g["vis/error_R"])) < (0.05 if precision == "fp32x3" else 30.0)
         assert abs(model.last_vis_dict["vis/tz_gt"] - float(g["vis/tz_gt"])) < 1e-6
     # gradients: against the oracle's autograd (full tensors) and the reference's stored norms
     leaf = O.leaf_state_dict(sd)
@@ -170,7 +171,7 @@ def test_add_metric_parity(sd):
 
 
 def test_optimizer_step_runs(sd):
-    model, opt = _model(sd, "bf16")
+    model, opt = _model(sd, "half")
     model.train()
     batch = _cuda_batch(synth.make_batch(4, seed=3))
     before = model.pnp_net.fc_r.weight.detach().clone()

@@ -31,7 +31,7 @@ def _rel(a, b):
 
 def _operand(x, planes):
     """What the kernel effectively multiplies: bf16-rounded for planes=1, ~fp32 for planes=2."""
-    return x.bfloat16().float() if planes == 1 else x
+    return _ops().round_storage(x) if planes == 1 else x
 
 
 def _nhwc(x_nchw, planes):
@@ -59,7 +59,7 @@ def test_gemm_fwd(planes, M, N, K):
     ref = F.leaky_relu(_operand(a, planes) @ _operand(w, planes).t() + bias, 0.1)
     assert _rel(out32[:, :N], ref) < TOL[planes]
     got = out.float()[:, :N]
-    assert _rel(got, ref) < (5e-3 if planes == 1 else 3e-5)  # planes=1: output rounded to bf16
+    assert _rel(got, ref) < (5e-3 if planes == 1 else 3e-5)  # planes=1: output rounded to the 16-bit storage format
 
 
 CONV_CASES = [

@@ -6,7 +6,7 @@ import bench
 from gdr_net_b200 import ops, synth
 
 def main():
-    precision = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+    precision = sys.argv[1] if len(sys.argv) > 1 else "half"
     model, _ = bench.build(precision)
     eng = model.engine
     dev = torch.device("cuda")
