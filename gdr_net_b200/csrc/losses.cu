@@ -358,6 +358,8 @@ struct PoseParams {
     bf16* dy_hi;            // [B][64] gradient wrt the 9 FC outputs (rot6d | t), cols >= 9 zero
     bf16* dy_lo;
     int B, n_pts, do_loss;
+    float eps;  // 1e-4 in the differentiable train decode (utils.py:208-236); 0 = exact normalisation of the test-time
+                // decode (pose_from_pred_centroid_z.py:52-141 -> utils.py:39-94 axangle2mat)
 };
 
 __global__ void __launch_bounds__(128) pose_loss_kernel(const PoseParams p) {
@@ -398,11 +400,12 @@ __global__ void __launch_bounds__(128) pose_loss_kernel(const PoseParams p) {
         T[1] = zz * (cy - dconst(K[5])) / dconst(K[4]);
         T[2] = zz;
         // allocentric -> egocentric
-        Dual nT = dsqrt(T[0] * T[0] + T[1] * T[1] + T[2] * T[2]) + dconst(1e-4f);
+        Dual nT = dsqrt(T[0] * T[0] + T[1] * T[1] + T[2] * T[2]) + dconst(p.eps);
         Dual ray[3] = {T[0] / nT, T[1] / nT, T[2] / nT};
         Dual angle = dacos(ray[2]);
         Dual ax[3] = {-ray[1], ray[0], dconst(0.f)};
-        Dual na = dsqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]) + dconst(1e-4f);
+        Dual na = dsqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]) + dconst(p.eps);
+        if (na.v <= 0.f) na = dconst(1.f);  // object exactly on the optical axis: angle = 0, rotation = identity (utils.py:62)
         for (int i = 0; i < 3; ++i) ax[i] = ax[i] / na;
         Dual half = angle * 0.5f;
         Dual sh = dsin(half);
@@ -620,7 +623,7 @@ extern "C" int gdrn_pose_loss(const float* pred, int ld_pred, const float* cams,
                               const float* ratios, const float* extents, const float* points, const float* gt_rot,
                               const float* gt_trans, const float* gt_ratio, const float* syms, const int* sym_off,
                               const float* gw, float* out_rot, float* out_trans, double* sums, float* vis, void* dy_hi,
-                              void* dy_lo, int B, int n_pts, int do_loss, void* stream_) {
+                              void* dy_lo, int B, int n_pts, int do_loss, float eps, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     PoseParams p;
     p.rot6d = pred;
@@ -647,6 +650,7 @@ extern "C" int gdrn_pose_loss(const float* pred, int ld_pred, const float* cams,
     p.B = B;
     p.n_pts = n_pts;
     p.do_loss = do_loss;
+    p.eps = eps;
     if (do_loss) GDRN_CUDA_OK(cudaMemsetAsync(sums, 0, 4 * sizeof(double), stream));
     pose_loss_kernel<<<B, 128, 0, stream>>>(p);
     GDRN_CUDA_OK(cudaGetLastError());

@@ -298,7 +298,7 @@ class Engine:
             C.gdrn_pose_loss(pred.data_ptr(), 16, aux["roi_cams"].data_ptr(), aux["roi_centers"].data_ptr(),
                              aux["roi_whs"].data_ptr(), aux["resize_ratios"].data_ptr(), aux["roi_extents"].data_ptr(), None,
                              None, None, None, None, None, None, out_rot.data_ptr(), out_trans.data_ptr(), None, None, None,
-                             None, B, 0, 0, _stream())
+                             None, B, 0, 0, 0.0, _stream())
             if want_maps:
                 maps = logits.view(B, 64, 64, 72).permute(0, 3, 1, 2)
                 res.update(mask=maps[:, 0:1], coor_x=maps[:, 1:2], coor_y=maps[:, 2:3], coor_z=maps[:, 3:4], region=maps[:, 4:69])
@@ -353,7 +353,7 @@ class Engine:
                          aux["gt_points"].data_ptr(), aux["gt_ego_rot"].data_ptr(), aux["gt_trans"].data_ptr(),
                          aux["gt_trans_ratio"].data_ptr(), ops.ptr(S["syms"]), ops.ptr(S["sym_off"]), gw.data_ptr(),
                          S["out_rot"].data_ptr(), S["out_trans"].data_ptr(), S["pose_sums"].data_ptr(), S["vis_ps"].data_ptr(),
-                         S["dy9"].hi_ptr, S["dy9"].lo_ptr, B, n_pts, 1, _stream())
+                         S["dy9"].hi_ptr, S["dy9"].lo_ptr, B, n_pts, 1, 1e-4, _stream())
 
     # ------------------------------------------------------------------------------------------ backward
     def _wgrad_conv(self, du: PT, x_in: PT, conv, wname: str, ipad: Optional[int] = None):

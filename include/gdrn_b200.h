@@ -127,7 +127,7 @@ int gdrn_pose_loss(const float* pred, int ld_pred, const float* cams, const floa
                    const float* ratios, const float* extents, const float* points, const float* gt_rot,
                    const float* gt_trans, const float* gt_ratio, const float* syms, const int* sym_off, const float* gw,
                    float* out_rot, float* out_trans, double* sums, float* vis, void* dy_hi, void* dy_lo, int B, int n_pts,
-                   int do_loss, void* stream);
+                   int do_loss, float eps, void* stream);
 int gdrn_loss_finalize(const double* pix_sums, const double* pose_sums, const float* vis, float* losses, float* vis_out,
                        int B, int HW, int n_pts, void* stream);
 
