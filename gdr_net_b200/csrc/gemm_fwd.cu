@@ -21,27 +21,10 @@
 #include <stdlib.h>
 
 #include "gdrn_internal.h"
+#include "gemm_params.h"
 #include "ptx.cuh"
 
 namespace gdrn {
-
-struct GemmParams {
-    CUtensorMap tmA[2][4];  // [plane hi/lo][stride-2 phase]
-    CUtensorMap tmB[2];     // [plane hi/lo]
-    int mode;               // 0 = plain 2-D GEMM, 1 = conv (4-D boxes)
-    int M, N;               // valid rows / cols
-    int num_m_tiles, num_n_tiles, num_kb;
-    int cchunks, KW, pad, stride;
-    int tiles_per_img, TH, TN;
-    void* out_hi;
-    void* out_lo;
-    float* out_f32;
-    int ldc;
-    const float* bias;
-    int act;       // 0 none, 1 LeakyReLU(0.1)
-    float* stats;  // [2][N]: sum, sum of squares (accumulated with atomics) or nullptr
-    int cluster;   // 1, or 2: CTA pairs share one n_tile and each TMA-multicasts half of the weight tile to both
-};
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
@@ -459,6 +442,18 @@ static int pick_block_n(int n_pad, int nsplit, int num_m_tiles) {
 // Optional CTA pairs (cluster of 2) that TMA-multicast the weight tile.  MEASURED SLOWER on B200 (64x64 256->256 conv:
 // 1250 -> 1066 TFLOP/s; whole step 12.36 -> 12.75 ms): the two CTAs' stage rings become coupled and the halved TMA boxes
 // cost more than the saved L2 traffic, so it is off unless GDRN_CLUSTER=2 is set (kept for round-2 experiments).
+// 2-CTA (cta_group::2) 256x256 tiles for wide layers (gemm_fwd2.cu); GDRN_2CTA=0 disables
+// MEASURED (B=64): no gain over the 1-CTA kernel (64x64 256->256: 1217 vs 1204 TFLOP/s; 16x16 and 32x32 layers slower),
+// so it is off by default -- the big layers already run at ~84 % of the measured sustained cuBLAS rate.
+static int g_2cta_mode = -1;
+static bool want_2cta(int nsplit, int block_n, int num_m_tiles) {
+    if (g_2cta_mode < 0) {
+        const char* e = getenv("GDRN_2CTA");
+        g_2cta_mode = e ? atoi(e) : 0;
+    }
+    return g_2cta_mode == 1 && nsplit == 1 && block_n == 256 && num_m_tiles % 2 == 0 && num_m_tiles >= 2;
+}
+
 static int pick_cluster(int num_m_tiles) {
     static int forced = -1;
     if (forced < 0) {
@@ -472,6 +467,12 @@ static int pick_cluster(int num_m_tiles) {
 }  // namespace gdrn
 
 using namespace gdrn;
+
+// experiment switch: 1 = use the cta_group::2 256x256-tile kernel (gemm_fwd2.cu) for eligible layers
+extern "C" int gdrn_set_2cta(int on) {
+    g_2cta_mode = on ? 1 : 0;
+    return 0;
+}
 
 extern "C" int gdrn_conv_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, void* y_hi,
                              void* y_lo, float* y_f32, const float* bias, float* stats, int N, int H, int W, int Cin,
@@ -495,7 +496,8 @@ extern "C" int gdrn_conv_fwd(const void* x_hi, const void* x_lo, const void* w_h
 
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    const int cluster = pick_cluster((N * Ho * Wo + 127) / 128);
+    const bool two_cta = want_2cta(nsplit, block_n, (N * Ho * Wo + 127) / 128);
+    const int cluster = two_cta ? 2 : pick_cluster((N * Ho * Wo + 127) / 128);  // weight box = block_n / cluster rows
     const int npl = nsplit == 1 ? 1 : 2;
     const void* xs[2] = {x_hi, x_lo};
     const void* ws[2] = {w_hi, w_lo};
@@ -536,6 +538,7 @@ extern "C" int gdrn_conv_fwd(const void* x_hi, const void* x_lo, const void* w_h
     p.bias = bias;
     p.act = act;
     p.stats = stats;
+    if (two_cta) return launch_gemm_2cta(p, nsplit, stream);
     return dispatch_gemm(p, block_n, nsplit, stream);
 }
 

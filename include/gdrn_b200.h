@@ -30,6 +30,7 @@ long gdrn_launch_count(void); /* kernels launched by this library since load */
 int gdrn_abi_version(void);
 int gdrn_storage_format(void); /* 0: bf16 (hi, lo) planes; 1: fp16 planes, lo = fp16((x - hi) * gdrn_lo_scale()) */
 float gdrn_lo_scale(void);
+int gdrn_set_2cta(int on); /* experiment: cta_group::2 256x256 tiles for wide layers (default off: measured no faster) */
 int gdrn_last_gemm_variant(void); /* BLOCK_N*10 + nsplit of this thread's last conv/gemm forward launch */
 
 /* ---- tcgen05 implicit-GEMM convolution, forward (and dgrad with flipped/transposed weights) ------------

@@ -183,3 +183,26 @@ def test_optimizer_step_runs(sd):
         losses.backward()
         opt.step()
     assert not torch.equal(before, model.pnp_net.fc_r.weight)
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_ragged_batch_sizes(sd, B):
+    """Inference batches are 'detections per image' (any size, reference gdrn_evaluator.py:561-578); train batches may be odd."""
+    from oracle import gdrn_oracle as O
+
+    model, _ = _model(sd, "fp32x3")
+    batch_cpu = synth.make_batch(B, seed=11 + B)
+    batch = _cuda_batch(batch_cpu)
+    model.eval()
+    with torch.no_grad():
+        out = model(batch["roi_img"], **synth.forward_kwargs(batch, train=False))
+        o = O.gdrn_forward(O.leaf_state_dict(sd, requires_grad=False), batch_cpu, train=False, do_loss=False)
+    head = torch.cat([out["mask"], out["coor_x"], out["coor_y"], out["coor_z"], out["region"]], dim=1)
+    assert _rel(head, o["head"]) < REL_FP32 and _rel(out["rot"], o["rot"]) < 2e-3 and _rel(out["trans"], o["trans"]) < 2e-3
+    model.train()
+    _, loss_dict = model(batch["roi_img"], **synth.forward_kwargs(batch, train=True))
+    sum(loss_dict.values()).backward()
+    o = O.gdrn_forward(O.leaf_state_dict(sd, requires_grad=False), batch_cpu, train=True, do_loss=True)
+    for k, v in loss_dict.items():
+        assert abs(float(v) - float(o["losses"][k])) <= 2e-3 * abs(float(o["losses"][k])), (B, k, float(v), float(o["losses"][k]))
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters())

@@ -104,6 +104,29 @@ def test_conv_fwd(planes, case):
         assert _rel(stats[1], s2) < 1e-4
 
 
+def test_conv_fwd_2cta_variant():
+    """The cta_group::2 kernel (256x256 tile per CTA pair) on a layer wide and large enough to select it."""
+    ops = _ops()
+    from gdr_net_b200.capi import C
+
+    g = torch.Generator(device="cuda").manual_seed(77)
+    N, H, Cin, Cout = 8, 64, 256, 256
+    x = torch.randn(N, Cin, H, H, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / 48
+    X, Wp = _nhwc(x, 1), ops.pack_conv_fwd(w, 1)
+    out32 = torch.zeros(N, H, H, Cout, device="cuda")
+    stats = torch.zeros(2, Cout, device="cuda")
+    C.gdrn_set_2cta(1)
+    try:
+        ops.conv_fwd(X, Wp, Cout, 3, 3, 1, 1, out_f32=out32, stats=stats, want_planes=False)
+        torch.cuda.synchronize()
+    finally:
+        C.gdrn_set_2cta(0)
+    ref = F.conv2d(_operand(x, 1), _operand(w, 1), None, padding=1).permute(0, 2, 3, 1)
+    assert _rel(out32, ref) < TOL[1]
+    assert _rel(stats[1], (ref.reshape(-1, Cout) ** 2).sum(0)) < 1e-4
+
+
 @pytest.mark.parametrize("planes", [1, 2])
 def test_conv_dgrad_as_conv(planes):
     """dX of a 3x3 s1 conv = conv(dY, flipped/transposed weights); of a s2 conv = same over zero-inserted dY."""
