@@ -223,6 +223,7 @@ def run_ours(args):
         # ---- e2e through the public module API with pinned host inputs (H2D + D2H inside the timed region)
         model = main["model"]
         model.engine.grad_hook = main["eng"].grad_hook
+        model.use_cuda_graphs = args.graph and world == 1  # forward / backward graphs behind the public module API
         host = synth.make_batch(B, seed=200 + rank)
         pinned = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
         h2d = sum(v.numel() * v.element_size() for v in pinned.values() if isinstance(v, torch.Tensor))

@@ -211,12 +211,14 @@ class GDRN(nn.Module):
         self.concat = cfg.MODEL.CDPN.ROT_HEAD.ROT_CONCAT
         self.r_out_dim, self.mask_out_dim, self.region_out_dim = get_xyz_mask_region_out_dim(cfg)
         self._engine: Optional[Engine] = None
+        self.use_cuda_graphs = False  # set True for fixed-shape training loops: forward/backward replay CUDA graphs
         self.precision = {"bf16": "half", "fp16": "half"}.get(precision, precision)  # "half" (1 pass) | "fp32x3" (hi/lo planes)
 
     @property
     def engine(self) -> Engine:
         if self._engine is None or self._engine.precision != self.precision:
             self._engine = Engine(self, precision=self.precision)
+        self._engine.use_cuda_graphs = self.use_cuda_graphs
         return self._engine
 
     def forward(self, x, gt_xyz=None, gt_xyz_bin=None, gt_mask_trunc=None, gt_mask_visib=None, gt_mask_obj=None,

@@ -72,6 +72,8 @@ class Engine:
         self.wf: Dict[str, PT] = {}
         self.wd: Dict[str, PT] = {}
         self.grad_hook = None  # optional callable(engine) invoked at bucket boundaries during backward (DDP overlap)
+        self.use_cuda_graphs = False  # module API: replay forward / backward CUDA graphs (fixed shapes, no symmetric PM)
+        self._graphed = None
         # fp16 planes: activation gradients are carried with a static power-of-two loss scale (exactly removed from the
         # fp32 parameter gradients at the end of backward), like the GradScaler of the reference's AMP configs
         self.storage_name = ops.storage_format()[2]
@@ -540,19 +542,83 @@ class GraphedTrainStep:
         return self.losses
 
 
+class GraphedFwdBwd:
+    """Forward and backward captured as TWO CUDA graphs sharing one memory pool, for the public module API
+    (`GDRN.forward(..., do_loss=True)` then `.backward()`): the autograd Function replays them around static buffers."""
+
+    def __init__(self, engine: "Engine", x: torch.Tensor, aux: dict, train_bn: bool):
+        if aux.get("sym_infos") is not None:
+            raise NotImplementedError("graphed module path: symmetric PM loss (host-side symmetry packing) is not capturable yet")
+        self.engine, self.train_bn = engine, train_bn
+        self.x = x.clone()
+        self.aux = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in aux.items()}
+        self.gw = torch.ones(8, device=x.device)
+        self.key = self.signature(x, aux, train_bn)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):
+                engine.forward(self.x, self.aux, train_bn=train_bn, do_loss=True)
+                engine.backward(self.gw)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        hook, engine.grad_hook = engine.grad_hook, None  # collectives are issued by the caller after the replay
+        try:
+            self.g_fwd, self.g_bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            pool = torch.cuda.graph_pool_handle()
+            with torch.no_grad():
+                with torch.cuda.graph(self.g_fwd, pool=pool):
+                    res = engine.forward(self.x, self.aux, train_bn=train_bn, do_loss=True)
+                with torch.cuda.graph(self.g_bwd, pool=pool):
+                    engine.backward(self.gw)
+        finally:
+            engine.grad_hook = hook
+        self.losses, self.vis = res["losses"], res["vis"]
+
+    @staticmethod
+    def signature(x, aux, train_bn):
+        return (tuple(x.shape), train_bn, tuple(sorted((k, tuple(v.shape)) for k, v in aux.items() if isinstance(v, torch.Tensor))))
+
+    def forward(self, x, aux):
+        self.x.copy_(x, non_blocking=True)
+        for k, v in aux.items():
+            if isinstance(v, torch.Tensor):
+                self.aux[k].copy_(v, non_blocking=True)
+        self.g_fwd.replay()
+        return self.losses.clone(), self.vis.clone()
+
+    def backward(self, g_losses):
+        self.gw.copy_(g_losses)
+        self.g_bwd.replay()
+        eng = self.engine
+        if eng.grad_hook is not None:  # bucketed all-reduce after the replay (no overlap in this mode)
+            for stage in ("pnp_net", "rot_head_net", "backbone.layer4", "backbone.layer3", "backbone.layer2", "backbone.stem"):
+                eng.grad_hook(eng, stage)
+        return eng.grads
+
+
 class _GDRNFunction(torch.autograd.Function):
     """Autograd boundary: forward + losses and the hand-written backward are both ours; autograd only routes the
     8 loss gradients in and the 148 parameter gradients out (so optimizers / DDP / GradScaler keep working)."""
 
     @staticmethod
     def forward(ctx, engine: Engine, x, aux, train_bn, *params):
-        res = engine.forward(x, aux, train_bn=train_bn, do_loss=True)
         ctx.engine = engine
-        ctx.mark_non_differentiable(res["vis"])
-        return res["losses"], res["vis"]
+        ctx.graphed = None
+        if engine.use_cuda_graphs and aux.get("sym_infos") is None:
+            g = engine._graphed
+            if g is None or g.key != GraphedFwdBwd.signature(x, aux, train_bn):
+                g = engine._graphed = GraphedFwdBwd(engine, x, aux, train_bn)
+            losses, vis = g.forward(x, aux)
+            ctx.graphed = g
+        else:
+            res = engine.forward(x, aux, train_bn=train_bn, do_loss=True)
+            losses, vis = res["losses"], res["vis"]
+        ctx.mark_non_differentiable(vis)
+        return losses, vis
 
     @staticmethod
     def backward(ctx, g_losses, _g_vis):
         engine = ctx.engine
-        grads = engine.backward(g_losses)
+        grads = ctx.graphed.backward(g_losses) if ctx.graphed is not None else engine.backward(g_losses)
         return (None, None, None, None) + tuple(grads[name] for name, _ in engine.named_params)

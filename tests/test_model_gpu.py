@@ -206,3 +206,24 @@ def test_ragged_batch_sizes(sd, B):
     for k, v in loss_dict.items():
         assert abs(float(v) - float(o["losses"][k])) <= 2e-3 * abs(float(o["losses"][k])), (B, k, float(v), float(o["losses"][k]))
     assert all(torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+def test_module_api_cuda_graphs_match_eager(sd):
+    """`model.use_cuda_graphs = True` (forward/backward replayed as CUDA graphs) gives the eager path's losses and gradients."""
+    batch = _cuda_batch(synth.make_batch(4, seed=21))
+    res = []
+    for graphs in (False, True):
+        model, _ = _model(sd, "half")
+        model.train()
+        model.use_cuda_graphs = graphs
+        for it in range(2):  # second iteration replays
+            for p in model.parameters():
+                p.grad = None
+            _, loss_dict = model(batch["roi_img"], **synth.forward_kwargs(batch, train=True))
+            sum(loss_dict.values()).backward()
+        torch.cuda.synchronize()
+        res.append(({k: float(v) for k, v in loss_dict.items()}, {n: p.grad.clone() for n, p in model.named_parameters()}))
+    for k in res[0][0]:
+        assert abs(res[0][0][k] - res[1][0][k]) <= 2e-3 * abs(res[0][0][k]), k  # BN running stats differ by the extra warm-up steps only
+    for n in ("pnp_net.fc_t.weight", "rot_head_net.features.23.weight", "backbone.conv1.weight"):
+        assert _rel(res[1][1][n], res[0][1][n]) < 5e-2, n
