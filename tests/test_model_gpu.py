@@ -213,7 +213,7 @@ def test_module_api_cuda_graphs_match_eager(sd):
     batch = _cuda_batch(synth.make_batch(4, seed=21))
     res = []
     for graphs in (False, True):
-        model, _ = _model(sd, "half")
+        model, _ = _model(sd, "fp32x3")  # the 3-MMA mode: run-to-run noise (BN-stat atomics order) stays ~1e-5, so a real replay bug shows
         model.train()
         model.use_cuda_graphs = graphs
         for it in range(2):  # second iteration replays
@@ -224,6 +224,6 @@ def test_module_api_cuda_graphs_match_eager(sd):
         torch.cuda.synchronize()
         res.append(({k: float(v) for k, v in loss_dict.items()}, {n: p.grad.clone() for n, p in model.named_parameters()}))
     for k in res[0][0]:
-        assert abs(res[0][0][k] - res[1][0][k]) <= 2e-3 * abs(res[0][0][k]), k  # BN running stats differ by the extra warm-up steps only
+        assert abs(res[0][0][k] - res[1][0][k]) <= 2e-3 * abs(res[0][0][k]), k
     for n in ("pnp_net.fc_t.weight", "rot_head_net.features.23.weight", "backbone.conv1.weight"):
         assert _rel(res[1][1][n], res[0][1][n]) < 5e-2, n
