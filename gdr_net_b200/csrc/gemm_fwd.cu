@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
     const uint32_t crank = cl > 1 ? cluster_ctarank() : 0u;
     const uint16_t cmask = (uint16_t)((1u << cl) - 1u);
     const int my_cluster = blockIdx.x / cl, num_clusters = gridDim.x / cl;
-    const int num_groups = num_tiles / cl;
+    const int num_groups = (p.nphase ? p.nphase : 1) * num_tiles / cl;  // phase-major tile list for the stride-2 dgrad
     if (cl > 1) cluster_sync_all();  // peers' barriers are initialised before any remote arrive / multicast write
 
     if (warp == 0) {
@@ -131,8 +131,15 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
             int stage = 0;
             uint32_t phase = 0;
             for (int grp = my_cluster; grp < num_groups; grp += num_clusters) {
-                const int n_tile = grp % p.num_n_tiles;
-                const int m_tile = (grp / p.num_n_tiles) * cl + (int)crank;
+                int rem = grp, nkb = p.num_kb, tap_base = 0;
+                if (p.nphase) {
+                    const int ph = grp / num_tiles;
+                    rem = grp - ph * num_tiles;
+                    tap_base = p.ph_tap0[ph];
+                    nkb = (p.ph_tap0[ph + 1] - tap_base) * p.cchunks;
+                }
+                const int n_tile = rem % p.num_n_tiles;
+                const int m_tile = (rem / p.num_n_tiles) * cl + (int)crank;
                 int n0 = 0, h0 = 0;
                 if (p.mode == 1) {
                     if (p.TN == 1) {
@@ -142,20 +149,29 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
                         n0 = m_tile * p.TN;
                     }
                 }
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+                    int kb_w = kb;  // k-block of the packed weight matrix
                     if (p.mode == 1) {
                         const int tap = kb / p.cchunks;
                         const int cc = kb - tap * p.cchunks;
-                        const int r = tap / p.KW;
-                        const int s = tap - r * p.KW;
-                        int dh = r - p.pad, dw = s - p.pad, map = 0;
-                        if (p.stride == 2) {
-                            map = ((dh & 1) << 1) | (dw & 1);
-                            dh >>= 1;  // arithmetic shift == floor division
-                            dw >>= 1;
+                        int dh, dw, map = 0;
+                        if (p.nphase) {
+                            dh = p.tap_dh[tap_base + tap];
+                            dw = p.tap_dw[tap_base + tap];
+                            kb_w = p.tap_w[tap_base + tap] * p.cchunks + cc;
+                        } else {
+                            const int r = tap / p.KW;
+                            const int s = tap - r * p.KW;
+                            dh = r - p.pad;
+                            dw = s - p.pad;
+                            if (p.stride == 2) {
+                                map = ((dh & 1) << 1) | (dw & 1);
+                                dh >>= 1;  // arithmetic shift == floor division
+                                dw >>= 1;
+                            }
                         }
 #pragma unroll
                         for (int pl = 0; pl < NPL; ++pl)
@@ -171,7 +187,7 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
 #pragma unroll
                         for (int pl = 0; pl < NPL; ++pl)
                             tma_load_2d(st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES, &p.tmB[pl], &full_bar[stage],
-                                        kb * kBlockK, n_tile * BLOCK_N);
+                                        kb_w * kBlockK, n_tile * BLOCK_N);
                     } else {
                         // this CTA fetches rows [crank * BLOCK_N/cl, +BLOCK_N/cl) of the weight tile and multicasts them to
                         // the same smem offset of every CTA in the cluster: L2 -> SM weight traffic drops by cl
@@ -179,7 +195,7 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
 #pragma unroll
                         for (int pl = 0; pl < NPL; ++pl)
                             tma_load_2d_mcast(st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES + crank * rows * 128, &p.tmB[pl],
-                                              &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N + crank * rows, cmask);
+                                              &full_bar[stage], kb_w * kBlockK, n_tile * BLOCK_N + crank * rows, cmask);
                     }
                     if (++stage == STAGES) {
                         stage = 0;
@@ -201,7 +217,12 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_set = tmem_base + acc * Cfg::NACC * BLOCK_N;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                int nkb = p.num_kb;
+                if (p.nphase) {
+                    const int ph = grp / num_tiles;
+                    nkb = (p.ph_tap0[ph + 1] - p.ph_tap0[ph]) * p.cchunks;
+                }
+                for (int kb = 0; kb < nkb; ++kb) {
                     const uint32_t d_tmem = d_set + (NSPLIT == 3 ? (kb % Cfg::NMAIN) * BLOCK_N : 0);
                     const uint32_t d_cross = d_set + Cfg::NMAIN * BLOCK_N;
                     mbar_wait(&full_bar[stage], phase);
@@ -243,14 +264,27 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
         __nv_bfloat16* out_hi = reinterpret_cast<__nv_bfloat16*>(p.out_hi);
         __nv_bfloat16* out_lo = reinterpret_cast<__nv_bfloat16*>(p.out_lo);
         for (int tg = my_cluster + grp * num_clusters, it = grp; tg < num_groups; tg += 2 * num_clusters, it += 2) {
-            const int n_tile = tg % p.num_n_tiles;
-            const int m_tile = (tg / p.num_n_tiles) * cl + (int)crank;
+            int rem = tg, ph = 0;
+            if (p.nphase) {
+                ph = tg / num_tiles;
+                rem = tg - ph * num_tiles;
+            }
+            const int n_tile = rem % p.num_n_tiles;
+            const int m_tile = (rem / p.num_n_tiles) * cl + (int)crank;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const long grow = (long)m_tile * kBlockM + row;
-            const bool row_ok = grow < p.M;
+            const long mrow = (long)m_tile * kBlockM + row;
+            const bool row_ok = mrow < p.M;
+            long grow = mrow;  // output row
+            if (p.nphase) {    // (n, i, j) of the dY lattice -> pixel (2i + a, 2j + b) of the 2x larger dX
+                const long j = mrow & ((1L << p.pw_log2) - 1);
+                const long t = mrow >> p.pw_log2;
+                const long i = t & ((1L << p.ph_log2) - 1);
+                const long n = t >> p.ph_log2;
+                grow = (((n << (p.ph_log2 + 1)) + 2 * i + p.ph_a[ph]) << (p.pw_log2 + 1)) + 2 * j + p.ph_b[ph];
+            }
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 32; ++c) {
                 const int col0 = n_tile * BLOCK_N + c * 32;
@@ -389,7 +423,7 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
         attr_set = true;
     }
     const int cl = p.cluster;
-    const int groups = p.num_m_tiles * p.num_n_tiles / cl;
+    const int groups = (p.nphase ? p.nphase : 1) * p.num_m_tiles * p.num_n_tiles / cl;
     int clusters = groups < num_sms() / cl ? groups : num_sms() / cl;
     clusters -= clusters % p.num_n_tiles;  // every CTA keeps one n_tile => per-CTA BatchNorm partial sums
     if (clusters <= 0) clusters = p.num_n_tiles;
@@ -539,6 +573,90 @@ extern "C" int gdrn_conv_fwd(const void* x_hi, const void* x_lo, const void* w_h
     p.act = act;
     p.stats = stats;
     if (two_cta) return launch_gemm_2cta(p, nsplit, stream);
+    return dispatch_gemm(p, block_n, nsplit, stream);
+}
+
+// Data gradient of a stride-2 convolution (k = 3, pad 1 or k = 1, pad 0), decomposed by OUTPUT PARITY: the pixels
+// (2i + a, 2j + b) of dX only receive the filter taps r = a + pad (mod 2), so each of the four phases is a small stride-1
+// conv over the UN-dilated dY with 1 / 2 / 2 / 4 taps -- 9 taps per 4 output pixels instead of the 36 of the
+// "conv over zero-inserted dY" formulation, and no zero-inserted tensor in HBM.  One launch covers all phases.
+//   du [N][Ho][Wo][Cy] (Cy % 64 == 0), w = the dgrad-packed weights [Cx_pad][K*K*Cy] with flipped taps (pack_conv_dgrad),
+//   dx [N][2Ho][2Wo][ldc].  k = 1: only phase (0, 0) is computed, the caller passes a zero-filled dx.
+extern "C" int gdrn_conv_dgrad_s2(const void* du_hi, const void* du_lo, const void* w_hi, const void* w_lo, void* dx_hi,
+                                  void* dx_lo, int N, int Ho, int Wo, int Cy, int Cx, int Cx_pad, int K, int pad, int ldc,
+                                  int nsplit, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (nsplit != 1 && nsplit != 3) return set_error(GDRN_ERR_ARG, "conv_dgrad_s2: nsplit must be 1 or 3");
+    if (nsplit == 3 && (du_lo == nullptr || w_lo == nullptr)) return set_error(GDRN_ERR_ARG, "conv_dgrad_s2: lo planes missing");
+    if (!((K == 3 && pad == 1) || (K == 1 && pad == 0))) return set_error(GDRN_ERR_ARG, "conv_dgrad_s2: k3 p1 or k1 p0 only");
+    if (Cy % 64 != 0) return set_error(GDRN_ERR_ARG, "conv_dgrad_s2: Cy=%d must be a multiple of 64", Cy);
+    if (ldc % 8 != 0 || ldc < Cx) return set_error(GDRN_ERR_ARG, "conv_dgrad_s2: bad ldc=%d", ldc);
+    if (Wo > 128 || 128 % Wo != 0 || (Ho & (Ho - 1)) != 0) return set_error(GDRN_ERR_ARG, "conv_dgrad_s2: unsupported dY size %dx%d", Ho, Wo);
+    int TH = 128 / Wo;
+    if (TH > Ho) TH = Ho;
+    const int TN = 128 / (Wo * TH);
+    if (Ho % TH != 0) return set_error(GDRN_ERR_ARG, "conv_dgrad_s2: Ho=%d not divisible by tile rows %d", Ho, TH);
+    const int num_m_tiles = (N * Ho * Wo + 127) / 128;
+    const int nphase = K == 3 ? 4 : 1;
+    const int block_n = pick_block_n(Cx_pad, nsplit, num_m_tiles * nphase);
+    if (block_n < 0) return set_error(GDRN_ERR_ARG, "conv_dgrad_s2: Cx_pad=%d must be a multiple of 64", Cx_pad);
+
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    const int npl = nsplit == 1 ? 1 : 2;
+    const void* xs[2] = {du_hi, du_lo};
+    const void* ws[2] = {w_hi, w_lo};
+    const int Kw = K * K * Cy;
+    for (int pl = 0; pl < npl; ++pl) {
+        uint64_t dims[4] = {(uint64_t)Cy, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
+        uint64_t strides[3] = {(uint64_t)Cy * 2, (uint64_t)Wo * Cy * 2, (uint64_t)Ho * Wo * Cy * 2};
+        uint32_t box[4] = {64, (uint32_t)Wo, (uint32_t)TH, (uint32_t)TN};
+        if (make_tmap(&p.tmA[pl][0], xs[pl], 4, dims, strides, box)) return GDRN_ERR_CUDA;
+        uint64_t wdims[2] = {(uint64_t)Kw, (uint64_t)Cx_pad};
+        uint64_t wstr[1] = {(uint64_t)Kw * 2};
+        uint32_t wbox[2] = {64, (uint32_t)block_n};
+        if (make_tmap(&p.tmB[pl], ws[pl], 2, wdims, wstr, wbox)) return GDRN_ERR_CUDA;
+    }
+    p.cluster = 1;
+    p.mode = 1;
+    p.M = N * Ho * Wo;
+    p.N = Cx;
+    p.num_m_tiles = num_m_tiles;
+    p.num_n_tiles = Cx_pad / block_n;
+    p.cchunks = Cy / 64;
+    p.KW = K;
+    p.pad = pad;
+    p.stride = 1;
+    p.TH = TH;
+    p.TN = TN;
+    p.tiles_per_img = (TN == 1) ? Ho / TH : 0;
+    p.out_hi = dx_hi;
+    p.out_lo = dx_lo;
+    p.ldc = ldc;
+    // phases in order of decreasing tap count (longest tiles first on the persistent CTAs)
+    p.nphase = nphase;
+    int nt = 0;
+    const int order[4][2] = {{1, 1}, {1, 0}, {0, 1}, {0, 0}};
+    for (int q = 0; q < nphase; ++q) {
+        const int a = K == 3 ? order[q][0] : 0, b = K == 3 ? order[q][1] : 0;
+        p.ph_a[q] = a;
+        p.ph_b[q] = b;
+        p.ph_tap0[q] = nt;
+        for (int r = 0; r < K; ++r) {
+            if ((a + pad - r) & 1) continue;
+            for (int s2 = 0; s2 < K; ++s2) {
+                if ((b + pad - s2) & 1) continue;
+                p.tap_dh[nt] = (signed char)((a + pad - r) / 2);
+                p.tap_dw[nt] = (signed char)((b + pad - s2) / 2);
+                p.tap_w[nt] = (signed char)((K - 1 - r) * K + (K - 1 - s2));  // pack_conv_dgrad stores flipped taps
+                ++nt;
+            }
+        }
+    }
+    p.ph_tap0[nphase] = nt;
+    p.num_kb = nt * p.cchunks;  // bookkeeping only (per-tile counts come from the phase table)
+    for (p.pw_log2 = 0; (1 << p.pw_log2) < Wo; ++p.pw_log2) {}
+    for (p.ph_log2 = 0; (1 << p.ph_log2) < Ho; ++p.ph_log2) {}
     return dispatch_gemm(p, block_n, nsplit, stream);
 }
 

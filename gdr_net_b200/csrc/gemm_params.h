@@ -20,6 +20,14 @@ struct GemmParams {
     int act;       // 0 none, 1 LeakyReLU(0.1)
     float* stats;  // [2][N]: sum, sum of squares (accumulated with atomics) or nullptr
     int cluster;   // 1, or 2: CTA pairs share one n_tile and each TMA-multicasts half of the weight tile to both
+    // Stride-2 dgrad by output-parity phases (mode 1, nphase > 0): rows index the (n, i, j) lattice of dY; phase ph writes
+    // output pixel (2i + ph_a, 2j + ph_b) and sums taps [ph_tap0[ph], ph_tap0[ph+1]) of the tables below
+    // (dY offset (tap_dh, tap_dw); tap_w = tap slot of the packed weight matrix).  Tiles are enumerated phase-major.
+    int nphase;
+    int ph_tap0[5];
+    int ph_a[4], ph_b[4];
+    signed char tap_dh[12], tap_dw[12], tap_w[12];
+    int pw_log2, ph_log2;  // log2 of the dY width / height
 };
 
 

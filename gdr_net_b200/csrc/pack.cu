@@ -6,6 +6,7 @@
 // IOHW (cdpn_rot_head_region.py:82-91), Linear [out][in] with fc1's input flattened from NCHW
 // (conv_pnp_net.py:145).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "gdrn_internal.h"
 #include "ptx.cuh"
@@ -46,78 +47,199 @@ struct PackJob {
     __nv_bfloat16* dst_hi;
     __nv_bfloat16* dst_lo;
     long so, si, sr, ss;
-    long elem_begin;  // prefix sum of ceil256(opad * ipad): (dst row, dst channel) work items
+    long elem_begin;  // prefix sum of the job's tile counts: ceil(opad/16) * ceil(ipad/64) * ceil(taps/9)
     int O, I, KH, KW, opad, ipad, krow, flip;
 };
 
+constexpr int kPackDR = 16;  // dst rows per tile
+constexpr int kPackDC = 64;  // dst channels per tile (128 bytes of one dst row segment)
+constexpr int kPackTC = 9;   // taps per tile
+constexpr int kPackLD = kPackDC + 1;
+
 __global__ void __launch_bounds__(256) pack_weight_batched_kernel(const PackJob* __restrict__ jobs, int njobs, long total_blocks) {
-    // One thread = one (dst row o, dst channel i) pair, looping over the taps: a warp reads 32 short contiguous runs of
-    // the fp32 source (the taps of OIHW / IOHW are innermost: >= 50 % sector efficiency) and writes 64 contiguous bytes
-    // per tap and plane.  (The first version mapped threads to dst elements: 2-byte gathers with a 36-byte stride.)
+    // One block = one tile of 16 dst rows x 64 dst channels x <= 9 taps, staged through shared memory:
+    //   load : threads walk the tile in SOURCE order (taps innermost, then whichever of the row / channel strides is
+    //          smaller), so a warp reads runs of >= 36..1152 contiguous bytes of the fp32 parameter;
+    //   store: 8 threads write the 128-byte (row, tap) segment of each plane with 16-byte stores.
+    // (The previous version had one thread per (row, channel) pair looping over the taps: 4-byte loads with a 36-byte
+    // lane stride and 2-byte stores -- 374 us per step for 360 MB of traffic.)
     __shared__ PackJob job;
+    __shared__ float tile[kPackDR * kPackTC * kPackLD];
+    __shared__ int tapoff[kPackTC];
     for (long blk = blockIdx.x; blk < total_blocks; blk += gridDim.x) {
         __syncthreads();
         if (threadIdx.x == 0) {
-            const long e = blk * 256;
             int lo = 0, hi = njobs - 1;
             while (lo < hi) {
                 const int mid = (lo + hi + 1) >> 1;
-                if (jobs[mid].elem_begin <= e) lo = mid; else hi = mid - 1;
+                if (jobs[mid].elem_begin <= blk) lo = mid; else hi = mid - 1;
             }
             job = jobs[lo];
         }
         __syncthreads();
-        const long item = blk * 256 + threadIdx.x - job.elem_begin;  // elem_begin counts (o, i) ITEMS here
-        if (item >= (long)job.opad * job.ipad) continue;
-        const int o = (int)(item / job.ipad);
-        const int i = (int)(item - (long)o * job.ipad);
         const int taps = job.KH * job.KW;
-        const bool valid = (o < job.O) && (i < job.I);
-        const float* sp = job.src + o * job.so + i * job.si;
-        __nv_bfloat16* dh = job.dst_hi + (long)o * job.krow + i;
-        __nv_bfloat16* dl = job.dst_lo != nullptr ? job.dst_lo + (long)o * job.krow + i : nullptr;
-        for (int tap = 0; tap < taps; ++tap) {
+        const int n_tc = (taps + kPackTC - 1) / kPackTC;
+        const int n_dc = (job.ipad + kPackDC - 1) / kPackDC;
+        int t = (int)(blk - job.elem_begin);  // elem_begin counts TILES
+        const int tc = t % n_tc;
+        t /= n_tc;
+        const int dcb = t % n_dc;
+        const int drb = t / n_dc;
+        const int t0 = tc * kPackTC, tcn = min(kPackTC, taps - t0);
+        const int dr0 = drb * kPackDR, dc0 = dcb * kPackDC;
+        if (threadIdx.x < tcn) {
+            int tap = t0 + threadIdx.x;
+            if (job.flip) tap = taps - 1 - tap;
+            const int r = tap / job.KW, s2 = tap - r * job.KW;
+            tapoff[threadIdx.x] = (int)(r * job.sr + s2 * job.ss);
+        }
+        __syncthreads();
+        const float inv_tcn = 1.f / (float)tcn;
+        const bool chan_fast = job.si <= job.so;  // consecutive source addresses: (tap, channel, row) or (tap, row, channel)
+        for (int f = threadIdx.x; f < kPackDR * kPackDC * tcn; f += 256) {
+            const int q = __float2int_rd(((float)f + 0.5f) * inv_tcn);
+            const int tl = f - q * tcn;
+            const int dc = chan_fast ? (q % kPackDC) : (q / kPackDR);
+            const int dr = chan_fast ? (q / kPackDC) : (q % kPackDR);
+            const int o = dr0 + dr, i = dc0 + dc;
             float v = 0.f;
-            if (valid) {
-                int r = tap / job.KW, s2 = tap - (tap / job.KW) * job.KW;
-                if (job.flip) {
-                    r = job.KH - 1 - r;
-                    s2 = job.KW - 1 - s2;
-                }
-                v = __ldg(sp + r * job.sr + s2 * job.ss);
+            if (o < job.O && i < job.I) v = __ldg(job.src + o * job.so + i * job.si + tapoff[tl]);
+            tile[(dr * kPackTC + tl) * kPackLD + dc] = v;
+        }
+        __syncthreads();
+        uint16_t* dh = reinterpret_cast<uint16_t*>(job.dst_hi);
+        uint16_t* dl = reinterpret_cast<uint16_t*>(job.dst_lo);
+        if ((job.ipad & 7) == 0 && (job.krow & 7) == 0) {
+            for (int it = threadIdx.x; it < kPackDR * tcn * (kPackDC / 8); it += 256) {
+                const int g = it & 7, row = it >> 3;
+                const int dr = __float2int_rd(((float)row + 0.5f) * inv_tcn);
+                const int tl = row - dr * tcn;
+                const int o = dr0 + dr, i = dc0 + g * 8;
+                if (o >= job.opad || i >= job.ipad) continue;
+                const float* src = tile + (dr * kPackTC + tl) * kPackLD + g * 8;
+                uint4 h, l;
+                split2(src[0], src[1], h.x, l.x);
+                split2(src[2], src[3], h.y, l.y);
+                split2(src[4], src[5], h.z, l.z);
+                split2(src[6], src[7], h.w, l.w);
+                const long off = (long)o * job.krow + (long)(t0 + tl) * job.ipad + i;
+                *reinterpret_cast<uint4*>(dh + off) = h;
+                if (dl != nullptr) *reinterpret_cast<uint4*>(dl + off) = l;
             }
-            uint16_t h, l;
-            split1(v, h, l);
-            reinterpret_cast<uint16_t*>(dh)[(long)tap * job.ipad] = h;
-            if (dl != nullptr) reinterpret_cast<uint16_t*>(dl)[(long)tap * job.ipad] = l;
+        } else {  // odd channel padding (the 7x7 stem: 3 channels per tap): scalar stores
+            for (int it = threadIdx.x; it < kPackDR * tcn * kPackDC; it += 256) {
+                const int dc = it & (kPackDC - 1), row = it / kPackDC;
+                const int dr = __float2int_rd(((float)row + 0.5f) * inv_tcn);
+                const int tl = row - dr * tcn;
+                const int o = dr0 + dr, i = dc0 + dc;
+                if (o >= job.opad || i >= job.ipad) continue;
+                uint16_t h, l;
+                split1(tile[(dr * kPackTC + tl) * kPackLD + dc], h, l);
+                const long off = (long)o * job.krow + (long)(t0 + tl) * job.ipad + i;
+                dh[off] = h;
+                if (dl != nullptr) dl[off] = l;
+            }
         }
     }
 }
 
 // grad[o*so + i*si + r'*sr + s'*ss] (+)= sum_ks ws[ks][o*krow + tap*ipad + i]
-__global__ void unpack_wgrad_kernel(const float* __restrict__ ws, float* __restrict__ grad, int O, int I, int KH, int KW,
-                                    int ipad, int krow_, int ksplit, long ks_stride, long so, long si, long sr, long ss, int flip,
-                                    int accumulate) {
-    // one thread per (o, tap, i): reads of every split are coalesced over i.  (A thread-per-(o, i) variant with contiguous
-    // per-thread tap writes was measured 2.4x SLOWER: too few threads for 9 x ksplit dependent loads each.)
+//
+// One block per (output row o, chunk of IC input channels): the split-K partial sums are read with KP-way parallelism
+// over the splits (coalesced over i, 4 independent loads in flight per thread), reduced through shared memory, transposed
+// there from the workspace's (tap, i) order to the parameter's (i, tap) order and written out as one contiguous run
+// (Conv2d OIHW: IC*taps floats).  The first version (one thread per element, serial loop over the splits, 36-byte-strided
+// stores) was latency-bound: 50-150 us for layers whose whole workspace is a few MB.
+template <int VARIANT>
+__global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ ws, float* __restrict__ grad, int O, int I,
+                                                           int KH, int KW, int IC, int n_ic, int KP, int ipad, int krow_,
+                                                           int ksplit, long ks_stride, long so, long si, long sr, long ss,
+                                                           int flip, int accumulate) {
+    extern __shared__ __align__(16) float sm[];
     const int taps = KH * KW;
-    const long krow = krow_;
-    const long total = (long)O * taps * I;
-    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int i = (int)(idx % I);
-        const long t2 = idx / I;
-        const int tap = (int)(t2 % taps);
-        const int o = (int)(t2 / taps);
-        const float* src = ws + (long)o * krow + (long)tap * ipad + i;
-        float acc = 0.f;
-        for (int ks = 0; ks < ksplit; ++ks) acc += src[ks * ks_stride];
-        int r = tap / KW, s = tap - (tap / KW) * KW;
-        if (flip) {
-            r = KH - 1 - r;
-            s = KW - 1 - s;
+    const int nelem = taps * IC;
+    const int tstride = taps | 1;  // odd: conflict-free transposed stores
+    float* red = sm;               // [KP][nelem]
+    float* out = sm + KP * nelem;  // [IC][tstride]
+    const int o = blockIdx.x / n_ic;
+    const int i0 = (blockIdx.x - o * n_ic) * IC;
+    const int icn = min(IC, I - i0);
+    const float inv_nelem = 1.f / (float)nelem, inv_ic = 1.f / (float)IC, inv_taps = 1.f / (float)taps;
+    const float* base = ws + (long)o * krow_ + i0;
+    const long kstep = (long)KP * ks_stride;
+    if (VARIANT == 1) {  // scalar loads: shapes whose rows are not 16-byte aligned (the 7x7 stem, 3 channels per tap)
+        for (int item = threadIdx.x; item < KP * nelem; item += 256) {
+            const int kp = __float2int_rd(((float)item + 0.5f) * inv_nelem);
+            const int e = item - kp * nelem;
+            const int tap = __float2int_rd(((float)e + 0.5f) * inv_ic);
+            const int i = e - tap * IC;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            if (i < icn) {
+                const float* sp = base + (long)tap * ipad + i + (long)kp * ks_stride;
+                int ks = kp;
+                for (; ks + 3 * KP < ksplit; ks += 4 * KP) {
+                    a0 += sp[0];
+                    a1 += sp[kstep];
+                    a2 += sp[2 * kstep];
+                    a3 += sp[3 * kstep];
+                    sp += 4 * kstep;
+                }
+                for (; ks < ksplit; ks += KP) {
+                    a0 += *sp;
+                    sp += kstep;
+                }
+            }
+            red[item] = (a0 + a1) + (a2 + a3);
         }
-        float* d = grad + o * so + i * si + r * sr + s * ss;
-        *d = accumulate ? (*d + acc) : acc;
+    } else {
+        // 16-byte loads (IC, ipad, krow and the split stride are multiples of 4 floats -- checked by the host): with one
+        // request per thread in flight, 4-byte loads cap an SM at ~8 KB outstanding (~1.7 TB/s of L2 reads over 148 SMs).
+        const int ic4 = IC >> 2;
+        const int nvec = taps * ic4;
+        const float inv_nvec = 1.f / (float)nvec, inv_ic4 = 1.f / (float)ic4;
+        const long kstep4 = kstep >> 2;
+#pragma unroll 2
+        for (int item = threadIdx.x; item < KP * nvec; item += 256) {
+            const int kp = __float2int_rd(((float)item + 0.5f) * inv_nvec);
+            const int e4 = item - kp * nvec;
+            const int tap = __float2int_rd(((float)e4 + 0.5f) * inv_ic4);
+            const int i = (e4 - tap * ic4) * 4;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < icn) {  // icn is a multiple of 4 here
+                const float4* sp = reinterpret_cast<const float4*>(base + (long)tap * ipad + i + (long)kp * ks_stride);
+                int ks = kp;
+                for (; ks + KP < ksplit; ks += 2 * KP) {
+                    const float4 v0 = __ldg(sp), v1 = __ldg(sp + kstep4);
+                    a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
+                    b.x += v1.x; b.y += v1.y; b.z += v1.z; b.w += v1.w;
+                    sp += 2 * kstep4;
+                }
+                if (ks < ksplit) {
+                    const float4 v0 = __ldg(sp);
+                    a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
+                }
+            }
+            float* r = red + kp * nelem + tap * IC + i;
+            *reinterpret_cast<float4*>(r) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nelem; e += 256) {
+        float v = red[e];
+        for (int kp = 1; kp < KP; ++kp) v += red[kp * nelem + e];
+        const int tap = __float2int_rd(((float)e + 0.5f) * inv_ic);
+        const int i = e - tap * IC;
+        out[i * tstride + (flip ? taps - 1 - tap : tap)] = v;
+    }
+    __syncthreads();
+    float* gbase = grad + (long)o * so + (long)i0 * si;
+    for (int j = threadIdx.x; j < icn * taps; j += 256) {
+        const int i = __float2int_rd(((float)j + 0.5f) * inv_taps);
+        const int tp = j - i * taps;
+        const int r = tp / KW, s = tp - r * KW;
+        float* d = gbase + (long)i * si + r * sr + s * ss;
+        const float v = out[i * tstride + tp];
+        *d = accumulate ? (*d + v) : v;
     }
 }
 
@@ -194,9 +316,39 @@ extern "C" int gdrn_unpack_wgrad(const float* ws, float* grad, int O, int I, int
                                  long ks_stride, long so, long si, long sr, long ss, int flip, int accumulate,
                                  void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    const long total = (long)O * KH * KW * I;
-    unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, stream>>>(ws, grad, O, I, KH, KW, ipad, krow, ksplit, ks_stride, so, si,
-                                                                 sr, ss, flip, accumulate);
+    const int taps = KH * KW;
+    if (O <= 0 || I <= 0 || taps <= 0 || ksplit <= 0) return set_error(GDRN_ERR_ARG, "unpack_wgrad: empty shape");
+    // tile: all taps x IC channels of one output row.  IC grows (32 -> 256) until a block has >= 512 sixteen-byte loads to
+    // issue (few-split layers such as 512->512 would otherwise run thousands of blocks with 144 busy threads each);
+    // the split-K partials of a tile are staged in <= 32 KB of shared memory, KP = ways of parallelism over the splits.
+    int IC = taps == 1 ? 256 : 32, KP = 1, nelem = 0;
+    if (IC > I) IC = I;
+    while (taps * IC > 2048 && IC > 1) IC >>= 1;
+    for (;;) {
+        nelem = taps * IC;
+        KP = 8192 / nelem;
+        if (KP > 16) KP = 16;
+        if (KP > ksplit) KP = ksplit;
+        if (KP < 1) KP = 1;
+        if (KP * nelem / 4 >= 512 || IC * 2 > I || IC * 2 > 256 || taps * IC * 2 > 2304) break;
+        IC *= 2;
+    }
+    if (nelem > 2304) return set_error(GDRN_ERR_ARG, "unpack_wgrad: kernel window too large");
+    const int n_ic = (I + IC - 1) / IC;
+    const size_t smem = ((size_t)KP * nelem + (size_t)IC * (taps | 1)) * sizeof(float);
+    static int variant = -1;
+    if (variant < 0) {
+        const char* e = getenv("GDRN_UNPACK");
+        variant = e ? atoi(e) : 0;
+    }
+    const bool vec_ok = (IC % 4 == 0) && (I % 4 == 0) && (ipad % 4 == 0) && (krow % 4 == 0) && (ks_stride % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(ws) & 15) == 0);
+    if (variant == 1 || !vec_ok)
+        unpack_wgrad_kernel<1><<<O * n_ic, 256, smem, stream>>>(ws, grad, O, I, KH, KW, IC, n_ic, KP, ipad, krow, ksplit, ks_stride,
+                                                               so, si, sr, ss, flip, accumulate);
+    else
+        unpack_wgrad_kernel<0><<<O * n_ic, 256, smem, stream>>>(ws, grad, O, I, KH, KW, IC, n_ic, KP, ipad, krow, ksplit, ks_stride,
+                                                               so, si, sr, ss, flip, accumulate);
     GDRN_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;

@@ -18,6 +18,10 @@ from . import ops
 from .capi import C
 from .ops import PT, _stream
 
+import os
+
+_DGRAD_ZERO_INSERT = os.environ.get("GDRN_DGRAD_ZERO_INSERT") == "1"  # A/B switch: the first (zero-insert + s1 conv) s2 dgrad
+
 LOSS_NAMES = ["loss_coor_x", "loss_coor_y", "loss_coor_z", "loss_mask", "loss_region", "loss_PM_R", "loss_centroid", "loss_z"]
 HEAD_CONVS = [(3, 4, False), (6, 7, False), (10, 11, True), (13, 14, False), (17, 18, True), (20, 21, False)]
 
@@ -122,9 +126,9 @@ class Engine:
             begin = 0
             for n, (src, out, O, I, KH, KW, opad, ipad, krow, so, si, sr, ss, flip) in enumerate(jobs):
                 arr[n] = (src.data_ptr(), out.hi_ptr, out.lo_ptr or 0, so, si, sr, ss, begin, O, I, KH, KW, opad, ipad, krow, flip)
-                begin += (opad * ipad + 255) // 256 * 256  # work items = (dst row, dst channel) pairs
+                begin += -(-opad // 16) * -(-ipad // 64) * -(-(KH * KW) // 9)  # tiles of 16 rows x 64 channels x 9 taps (pack.cu)
             self._pack_jobs = torch.from_numpy(arr.view(np.uint8).copy()).to(self.dev)
-            self._pack_njobs, self._pack_blocks = len(jobs), begin // 256
+            self._pack_njobs, self._pack_blocks = len(jobs), begin
             self._pack_srcs = [j[0] for j in jobs]  # keep the sources alive
             self._pack_key = key
         with torch.no_grad():
@@ -365,6 +369,9 @@ class Engine:
 
     def _dgrad_conv(self, du: PT, conv, wkey: str) -> PT:
         k, stride, pad = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        if stride == 2 and not _DGRAD_ZERO_INSERT:
+            # four output-parity phases over the un-dilated dY (no zero-inserted tensor, 1/4 of its MACs)
+            return ops.conv_dgrad_s2(du, self.wd[wkey], conv.in_channels, k, pad)
         z = ops.zero_insert(du) if stride == 2 else du
         return ops.conv_fwd(z, self.wd[wkey], conv.in_channels, k, k, 1, k - 1 - pad, algo_scale=0.25 if stride == 2 else 1.0)
 

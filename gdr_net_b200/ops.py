@@ -207,6 +207,18 @@ def conv_fwd(x: PT, wp: PT, Cout: int, KH: int, KW: int, stride: int, pad: int, 
     return out
 
 
+def conv_dgrad_s2(du: PT, wd: PT, Cx: int, K: int, pad: int, *, out: PT | None = None) -> PT:
+    """dX of a stride-2 conv (k3 p1 / k1 p0) from the UN-dilated dY, decomposed by output parity (gdrn_conv_dgrad_s2);
+    wd = pack_conv_dgrad(weight).  Replaces zero_insert + stride-1 conv (4x the MACs, plus the dilated tensor in HBM)."""
+    N, Ho, Wo, Cy = du.shape
+    ldc = _round_up(Cx, 64)
+    if out is None:
+        out = PT((N, 2 * Ho, 2 * Wo, ldc), du.planes, device=du.buf.device, zero=(K == 1 or ldc != Cx))
+    C.gdrn_conv_dgrad_s2(du.hi_ptr, du.lo_ptr, wd.hi_ptr, wd.lo_ptr, out.hi_ptr, out.lo_ptr, N, Ho, Wo, Cy, Cx, wd.shape[0], K,
+                         pad, ldc, du.nsplit, _stream())
+    return out
+
+
 def gemm_fwd(a: PT, wp: PT, N: int, *, out: PT | None = None, out_f32: torch.Tensor | None = None, bias=None, stats=None,
              act: int = 0, ldc: int | None = None, want_planes: bool = True) -> PT | None:
     M, K = a.shape

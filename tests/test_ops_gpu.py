@@ -150,6 +150,28 @@ def test_conv_dgrad_as_conv(planes):
 
 
 @pytest.mark.parametrize("planes", [1, 2])
+@pytest.mark.parametrize("case", [(2, 64, 64, 128, 3, 1), (3, 32, 128, 256, 3, 1), (4, 16, 256, 512, 3, 1), (2, 64, 69, 128, 3, 1),
+                                  (2, 64, 64, 128, 1, 0), (4, 16, 256, 512, 1, 0)])
+def test_conv_dgrad_s2_phases(planes, case):
+    """dX of a stride-2 conv through the output-parity decomposition == torch's conv backward-data."""
+    ops = _ops()
+    N, H, Cin, Cout, k, pad = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case))
+    x = torch.randn(N, Cin, H, H, device="cuda", generator=g, requires_grad=True)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (3 * k * Cin ** 0.5)
+    y = F.conv2d(x, _operand(w, planes), None, stride=2, padding=pad)
+    dy = torch.randn_like(y)
+    (gx,) = torch.autograd.grad(y, x, _operand(dy, planes))
+    out = ops.conv_dgrad_s2(_nhwc(dy, planes), ops.pack_conv_dgrad(w, planes), Cin, k, pad)
+    torch.cuda.synchronize()
+    got = out.float()
+    assert got.shape[:3] == (N, H, H)
+    assert _rel(got[..., :Cin], gx.permute(0, 2, 3, 1)) < (TOL[planes] if planes == 2 else 2e-3)
+    if got.shape[-1] > Cin:
+        assert float(got[..., Cin:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("planes", [1, 2])
 def test_deconv_fwd_and_dgrad(planes):
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(9)
