@@ -443,26 +443,46 @@ __device__ __forceinline__ void masked_grad(const uint4& gah, const uint4& gal, 
         for (int j = 0; j < 8; ++j) g[j] = y[j] > 0.f ? g[j] : 0.f;
     }
 }
+// 8 consecutive per-channel constants from shared memory with two 16-byte loads (the arrays are 16-byte aligned, c0 % 8 == 0)
+__device__ __forceinline__ void lds8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+// ReLU mask recomputed from the BN input: [sc*u + sh > 0] with the forward's own scale / shift (bn_fwd_kernel), so the
+// activation y need not be read back (plain conv-BN-ReLU layers: 2 of the 14 bytes per element of BN backward)
+__device__ __forceinline__ void mask_from_u(const float (&u)[8], const float* sc_, const float* sh_, float (&g)[8]) {
+    float sc[8], sh[8];
+    lds8(sc_, sc);
+    lds8(sh_, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = fmaf(sc[j], u[j], sh[j]) > 0.f ? g[j] : 0.f;
+}
 
-template <bool LO>
+template <bool LO, bool MASKU>
 __global__ void __launch_bounds__(kBnBwdThreads, 3) bn_bwd_reduce_kernel(
     const bf16* __restrict__ ga_hi, const bf16* __restrict__ ga_lo, const bf16* __restrict__ gb_hi,
     const bf16* __restrict__ gb_lo, const bf16* __restrict__ y_hi, const bf16* __restrict__ u_hi,
     const bf16* __restrict__ u_lo, const float* __restrict__ mean, const float* __restrict__ invstd,
-    float* __restrict__ sums, long rows, int C) {
+    const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ sums, long rows, int C) {
     // block = (C/8) channel groups x rpb row lanes
     const int cg = C / 8;
     const int rpb = kBnBwdThreads / cg;  // cg in {8,16,32,64}: always divides 256
     const int g = threadIdx.x % cg;
     const int rl = threadIdx.x / cg;
-    __shared__ float s_mu[512], s_is[512];
+    __shared__ __align__(16) float s_mu[512], s_is[512], s_sc[512], s_sh[512];
     __shared__ float red[2][kBnBwdThreads][8 + 1];
     for (int c = threadIdx.x; c < C; c += kBnBwdThreads) {
         s_mu[c] = mean[c];
         s_is[c] = invstd[c];
+        if (MASKU) {
+            const float sc = gamma[c] * invstd[c];
+            s_sc[c] = sc;
+            s_sh[c] = beta[c] - mean[c] * sc;
+        }
     }
     __syncthreads();
-    const bool has_gb = gb_hi != nullptr, has_y = y_hi != nullptr;
+    const bool has_gb = gb_hi != nullptr, has_y = !MASKU && y_hi != nullptr;
     float s0[8], s1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
@@ -493,10 +513,14 @@ __global__ void __launch_bounds__(kBnBwdThreads, 3) bn_bwd_reduce_kernel(
                 masked_grad<LO>(gah[t], gal[t], gbh[t], gbl[t], yh[t], has_gb, has_y, gv);
                 unpack8(uh[t], u);
                 if (LO) unpack8_lo(ul[t], u);
+                if (MASKU) mask_from_u(u, s_sc + g * 8, s_sh + g * 8, gv);
+                float mu[8], is[8];
+                lds8(s_mu + g * 8, mu);
+                lds8(s_is + g * 8, is);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     s0[j] += gv[j];
-                    s1[j] = fmaf(gv[j], (u[j] - s_mu[g * 8 + j]) * s_is[g * 8 + j], s1[j]);
+                    s1[j] = fmaf(gv[j], (u[j] - mu[j]) * is[j], s1[j]);
                 }
             }
         }
@@ -517,15 +541,15 @@ __global__ void __launch_bounds__(kBnBwdThreads, 3) bn_bwd_reduce_kernel(
 }
 
 // du = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) = k1*g + k2*u + k3 with per-channel constants (shared memory)
-template <bool LO>
+template <bool LO, bool MASKU>
 __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(
     const bf16* __restrict__ ga_hi, const bf16* __restrict__ ga_lo, const bf16* __restrict__ gb_hi,
     const bf16* __restrict__ gb_lo, const bf16* __restrict__ y_hi, const bf16* __restrict__ u_hi,
     const bf16* __restrict__ u_lo, const float* __restrict__ mean, const float* __restrict__ invstd,
-    const float* __restrict__ gamma, const float* __restrict__ sums, bf16* __restrict__ du_hi, bf16* __restrict__ du_lo,
-    bf16* __restrict__ gout_hi, bf16* __restrict__ gout_lo, float* __restrict__ dgamma, float* __restrict__ dbeta, long rows,
-    int C, int train) {
-    __shared__ float s_k1[512], s_k2[512], s_k3[512];
+    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ sums, bf16* __restrict__ du_hi,
+    bf16* __restrict__ du_lo, bf16* __restrict__ gout_hi, bf16* __restrict__ gout_lo, float* __restrict__ dgamma,
+    float* __restrict__ dbeta, long rows, int C, int train) {
+    __shared__ __align__(16) float s_k1[512], s_k2[512], s_k3[512], s_sc[512], s_sh[512];
     const int cg = C / 8;
     const long total = rows * cg;
     const float inv_n = 1.f / (float)rows;
@@ -541,13 +565,17 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(
         s_k1[c] = k1;
         s_k2[c] = k2;
         s_k3[c] = k3;
+        if (MASKU) {
+            s_sc[c] = k1;  // gamma * invstd: the forward's scale
+            s_sh[c] = beta[c] - mean[c] * k1;
+        }
         if (blockIdx.x == 0 && dgamma != nullptr) {
             dbeta[c] = sums[c];
             dgamma[c] = sums[C + c];
         }
     }
     __syncthreads();
-    const bool has_gb = gb_hi != nullptr, has_y = y_hi != nullptr, has_gout = gout_hi != nullptr;
+    const bool has_gb = gb_hi != nullptr, has_y = !MASKU && y_hi != nullptr, has_gout = gout_hi != nullptr;
     const long stride = (long)gridDim.x * blockDim.x;
     const long first = blockIdx.x * (long)blockDim.x + threadIdx.x;
     const int c0 = (int)(first % cg) * 8;
@@ -576,8 +604,13 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(
                 masked_grad<LO>(gah[t], gal[t], gbh[t], gbl[t], yh[t], has_gb, has_y, gv);
                 unpack8(uh[t], u);
                 if (LO) unpack8_lo(ul[t], u);
+                if (MASKU) mask_from_u(u, s_sc + c0, s_sh + c0, gv);
+                float k1[8], k2[8], k3[8];
+                lds8(s_k1 + c0, k1);
+                lds8(s_k2 + c0, k2);
+                lds8(s_k3 + c0, k3);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = fmaf(s_k1[c0 + j], gv[j], fmaf(s_k2[c0 + j], u[j], s_k3[c0 + j]));
+                for (int j = 0; j < 8; ++j) o[j] = fmaf(k1[j], gv[j], fmaf(k2[j], u[j], k3[j]));
                 store8(du_hi, LO ? du_lo : nullptr, it, o);
                 if (has_gout) store8(gout_hi, LO ? gout_lo : nullptr, it, gv);
             }
@@ -897,35 +930,43 @@ extern "C" int gdrn_zero_insert(const void* x_hi, const void* x_lo, void* y_hi, 
 
 extern "C" int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_hi, const void* gb_lo, const void* y_hi,
                            const void* u_hi, const void* u_lo, const float* mean, const float* invstd, const float* gamma,
-                           float* sums, void* du_hi, void* du_lo, void* gout_hi, void* gout_lo, float* dgamma,
-                           float* dbeta, long rows, int C, int train, void* stream_) {
+                           const float* beta, float* sums, void* du_hi, void* du_lo, void* gout_hi, void* gout_lo,
+                           float* dgamma, float* dbeta, long rows, int C, int train, int flags, void* stream_) {
     STREAM;
     if (C % 64 || C > 512) return set_error(GDRN_ERR_ARG, "bn_bwd: unsupported C=%d", C);
+    const int mask_u = flags & 1;
+    if (mask_u && (y_hi != nullptr || beta == nullptr)) return set_error(GDRN_ERR_ARG, "bn_bwd: mask-from-u needs beta and no y");
     {  // the reductions also provide dgamma / dbeta when BN runs on frozen (eval) statistics
-        GDRN_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream));
+        if (!(flags & 2)) GDRN_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream));
         const int rpb = kBnBwdThreads / (C / 8);
         long blocks = (rows + (long)rpb * 16 - 1) / ((long)rpb * 16);  // >= 16 rows per thread: few atomics, amortised prologue
         const long cap = (long)num_sms() * 2;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        if (u_lo != nullptr)
-            bn_bwd_reduce_kernel<true><<<(int)blocks, kBnBwdThreads, 0, stream>>>(CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo), CBF(y_hi),
-                                                                                  CBF(u_hi), CBF(u_lo), mean, invstd, sums, rows, C);
-        else
-            bn_bwd_reduce_kernel<false><<<(int)blocks, kBnBwdThreads, 0, stream>>>(CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo), CBF(y_hi),
-                                                                                   CBF(u_hi), CBF(u_lo), mean, invstd, sums, rows, C);
+#define GDRN_BN_RED(LO, MU)                                                                                                   \
+    bn_bwd_reduce_kernel<LO, MU><<<(int)blocks, kBnBwdThreads, 0, stream>>>(CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo),       \
+                                                                            CBF(y_hi), CBF(u_hi), CBF(u_lo), mean, invstd, gamma, \
+                                                                            beta, sums, rows, C)
+        if (u_lo != nullptr) {
+            if (mask_u) GDRN_BN_RED(true, true); else GDRN_BN_RED(true, false);
+        } else {
+            if (mask_u) GDRN_BN_RED(false, true); else GDRN_BN_RED(false, false);
+        }
+#undef GDRN_BN_RED
         GDRN_CUDA_OK(cudaGetLastError());
         count_launch();
     }
     const int agrid = ew_grid_amortised(rows * (C / 8), 256, 4);
-    if (u_lo != nullptr)
-        bn_bwd_apply_kernel<true><<<agrid, 256, 0, stream>>>(CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo), CBF(y_hi), CBF(u_hi), CBF(u_lo),
-                                                             mean, invstd, gamma, sums, BF(du_hi), BF(du_lo), BF(gout_hi), BF(gout_lo),
-                                                             dgamma, dbeta, rows, C, train);
-    else
-        bn_bwd_apply_kernel<false><<<agrid, 256, 0, stream>>>(CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo), CBF(y_hi), CBF(u_hi), CBF(u_lo),
-                                                              mean, invstd, gamma, sums, BF(du_hi), BF(du_lo), BF(gout_hi), BF(gout_lo),
-                                                              dgamma, dbeta, rows, C, train);
+#define GDRN_BN_APP(LO, MU)                                                                                                      \
+    bn_bwd_apply_kernel<LO, MU><<<agrid, 256, 0, stream>>>(CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo), CBF(y_hi), CBF(u_hi),    \
+                                                           CBF(u_lo), mean, invstd, gamma, beta, sums, BF(du_hi), BF(du_lo),       \
+                                                           BF(gout_hi), BF(gout_lo), dgamma, dbeta, rows, C, train)
+    if (u_lo != nullptr) {
+        if (mask_u) GDRN_BN_APP(true, true); else GDRN_BN_APP(true, false);
+    } else {
+        if (mask_u) GDRN_BN_APP(false, true); else GDRN_BN_APP(false, false);
+    }
+#undef GDRN_BN_APP
     LAUNCH_DONE();
 }
 

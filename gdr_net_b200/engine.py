@@ -22,6 +22,11 @@ import os
 
 _DGRAD_ZERO_INSERT = os.environ.get("GDRN_DGRAD_ZERO_INSERT") == "1"  # A/B switch: the first (zero-insert + s1 conv) s2 dgrad
 
+# A/B switch: recompute the ReLU mask of plain conv-BN-ReLU layers from u instead of reading y back in BN backward.
+# MEASURED (same box, graphed step): 11.39-11.47 ms with the recompute vs 11.11-11.33 ms reading y -- 2 B/element less HBM
+# traffic does not pay for the extra per-element FMA + compare + shared-memory constants, so it is off.
+_BN_MASK_FROM_U = os.environ.get("GDRN_BN_MASK_FROM_U") == "1"
+
 LOSS_NAMES = ["loss_coor_x", "loss_coor_y", "loss_coor_z", "loss_mask", "loss_region", "loss_PM_R", "loss_centroid", "loss_z"]
 HEAD_CONVS = [(3, 4, False), (6, 7, False), (10, 11, True), (13, 14, False), (17, 18, True), (20, 21, False)]
 
@@ -60,10 +65,12 @@ class Engine:
                 self._bn_mods[name] = m
                 total += 2 * m.num_features
         self.stats_all = torch.zeros(total, device=self.dev)
+        self.bwd_sums_all = torch.zeros(total, device=self.dev)  # BN-backward accumulators: one memset per backward
         off = 0
         for name, m in self._bn_mods.items():
             n = 2 * m.num_features
             self.bn[name].stats = self.stats_all[off:off + n]
+            self.bn[name].sums = self.bwd_sums_all[off:off + n].view(2, m.num_features)
             off += n
         # flat gradient buffer (one NCCL-friendly allocation); per-parameter views
         self.flat_grad = torch.zeros(sum(p.numel() for _, p in self.named_params), device=self.dev)
@@ -375,10 +382,13 @@ class Engine:
         z = ops.zero_insert(du) if stride == 2 else du
         return ops.conv_fwd(z, self.wd[wkey], conv.in_channels, k, k, 1, k - 1 - pad, algo_scale=0.25 if stride == 2 else 1.0)
 
-    def _bn_bwd(self, bkey: str, ga: PT, gb: Optional[PT], y: Optional[PT], u: PT, want_gout=False):
+    def _bn_bwd(self, bkey: str, ga: PT, gb: Optional[PT], y: Optional[PT], u: PT, want_gout=False, relu_from_u=False):
+        """relu_from_u: conv-BN-ReLU without a residual -- the mask is recomputed from u (y is not read)."""
         mod, st = self._bn_mods[bkey], self.bn[bkey]
-        return ops.bn_bwd(ga, gb, y, u, st.mean, st.invstd, mod.weight, st.sums, self.grads[bkey + ".weight"],
-                          self.grads[bkey + ".bias"], self.saved["train_bn"], want_gout=want_gout)
+        relu_from_u = relu_from_u and _BN_MASK_FROM_U
+        return ops.bn_bwd(ga, gb, None if relu_from_u else y, u, st.mean, st.invstd, mod.weight, st.sums,
+                          self.grads[bkey + ".weight"], self.grads[bkey + ".bias"], self.saved["train_bn"], want_gout=want_gout,
+                          beta=mod.bias, relu_from_u=relu_from_u, sums_zeroed=True)
 
     def backward(self, grad_losses: torch.Tensor):
         """grad_losses: [8] upstream gradients of LOSS_NAMES.  Fills self.grads (views of self.flat_grad)."""
@@ -386,6 +396,7 @@ class Engine:
         assert S is not None, "backward called without a do_loss forward"
         B, aux, pn = S["B"], S["aux"], m.pnp_net
         self.flat_grad.zero_()
+        self.bwd_sums_all.zero_()
         gw = grad_losses.float().contiguous()
         if self.grad_scale != 1.0:
             gw = gw * self.grad_scale  # the whole backward is linear in the loss gradients
@@ -441,13 +452,13 @@ class Engine:
         # ---- head convs (cdpn_rot_head_region.py:95-125)
         for L in reversed(S["head"]):
             ci, bi = L["ci"], L["bi"]
-            du, _ = self._bn_bwd(f"rot_head_net.features.{bi}", g, None, L["y"], L["u"])
+            du, _ = self._bn_bwd(f"rot_head_net.features.{bi}", g, None, L["y"], L["u"], relu_from_u=True)
             self._wgrad_conv(du, L["x_in"], hf[ci], f"rot_head_net.features.{ci}.weight")
             g = self._dgrad_conv(du, hf[ci], f"rot_head_net.features.{ci}")
             if L["up"]:
                 g = ops.upsample2x_bwd(g)
         D = S["deconv"]
-        du, _ = self._bn_bwd("rot_head_net.features.1", g, None, D["y"], D["u"])
+        du, _ = self._bn_bwd("rot_head_net.features.1", g, None, D["y"], D["u"], relu_from_u=True)
         buf, ks, kss = ops.conv_wgrad(du, D["z"], self.ws, 256, 3, 3, 1, 1)
         # ConvTranspose2d weight is IOHW [512][256][3][3] with flipped taps relative to the equivalent conv
         ops.unpack_wgrad(buf, self.grads["rot_head_net.features.0.weight"], 256, 512, 3, 3, 512, ks, kss, 9, 256 * 9, 3, 1, flip=1)
@@ -461,7 +472,7 @@ class Engine:
             du2, gout = self._bn_bwd(p + ".bn2", ga, gb, Lb["out"], Lb["u2"], want_gout=True)
             self._wgrad_conv(du2, Lb["a1"], blk.conv2, p + ".conv2.weight")
             da1 = self._dgrad_conv(du2, blk.conv2, p + ".conv2")
-            du1, _ = self._bn_bwd(p + ".bn1", da1, None, Lb["a1"], Lb["u1"])
+            du1, _ = self._bn_bwd(p + ".bn1", da1, None, Lb["a1"], Lb["u1"], relu_from_u=True)
             self._wgrad_conv(du1, Lb["x_in"], blk.conv1, p + ".conv1.weight")
             dx_main = self._dgrad_conv(du1, blk.conv1, p + ".conv1")
             if blk.downsample is not None:
@@ -476,7 +487,7 @@ class Engine:
         g_pool = ops.add2(ga, gb)
         St = S["stem"]
         g_a0 = ops.maxpool_bwd(St["pool_arg"], g_pool)
-        du0, _ = self._bn_bwd("backbone.bn1", g_a0, None, St["a0"], St["u0"])
+        du0, _ = self._bn_bwd("backbone.bn1", g_a0, None, St["a0"], St["u0"], relu_from_u=True)
         buf, ks, kss = ops.gemm_wgrad(du0.view(B * 128 * 128, 64), St["a_col"], self.ws)
         # ws rows [64][192] with k = (r*7+s)*3 + c  ->  OIHW [64][3][7][7]
         ops.unpack_wgrad(buf, self.grads["backbone.conv1.weight"], 64, 3, 7, 7, 3, ks, kss, 147, 49, 7, 1, krow=192)

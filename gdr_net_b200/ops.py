@@ -300,15 +300,18 @@ def bn_act(x: PT, scale, shift, relu: bool, res: PT | None = None, out: PT | Non
 
 
 def bn_bwd(ga: PT, gb: PT | None, y: PT | None, u: PT, mean, invstd, gamma, sums, dgamma, dbeta, train: bool,
-           want_gout: bool = False):
+           want_gout: bool = False, beta=None, relu_from_u: bool = False, sums_zeroed: bool = False):
+    """y: activation whose sign gives the ReLU mask (needed when a residual was added before the ReLU); relu_from_u: plain
+    conv-BN-ReLU, the mask is recomputed from u and beta and y is not read."""
     du = like(u)
     gout = like(u) if want_gout else None
     Cc = u.shape[-1]
     rows = u.numel() // Cc
+    assert not (relu_from_u and y is not None)
     C.gdrn_bn_bwd(ga.hi_ptr, ga.lo_ptr, gb.hi_ptr if gb else None, gb.lo_ptr if gb else None, y.hi_ptr if y else None,
-                  u.hi_ptr, u.lo_ptr, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), sums.data_ptr(), du.hi_ptr, du.lo_ptr,
-                  gout.hi_ptr if gout else None, gout.lo_ptr if gout else None, ptr(dgamma), ptr(dbeta), rows, Cc, int(train),
-                  _stream())
+                  u.hi_ptr, u.lo_ptr, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), ptr(beta), sums.data_ptr(), du.hi_ptr,
+                  du.lo_ptr, gout.hi_ptr if gout else None, gout.lo_ptr if gout else None, ptr(dgamma), ptr(dbeta), rows, Cc,
+                  int(train), (1 if relu_from_u else 0) | (2 if sums_zeroed else 0), _stream())
     return du, gout
 
 

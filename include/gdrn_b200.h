@@ -88,10 +88,12 @@ int gdrn_bn_fwd(const void* x_hi, const void* x_lo, const void* r_hi, const void
                 void* stream);
 int gdrn_bn_act(const void* x_hi, const void* x_lo, const void* r_hi, const void* r_lo, void* y_hi, void* y_lo,
                 const float* scale, const float* shift, long rows, int C, int relu, void* stream);
+/* flags: bit 0 = the ReLU mask is recomputed from u (plain conv-BN-ReLU: pass y_hi = NULL and beta); bit 1 = `sums` is
+ * already zero (the caller cleared all layers' accumulators in one memset) */
 int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_hi, const void* gb_lo, const void* y_hi,
                 const void* u_hi, const void* u_lo, const float* mean, const float* invstd, const float* gamma,
-                float* sums, void* du_hi, void* du_lo, void* gout_hi, void* gout_lo, float* dgamma, float* dbeta,
-                long rows, int C, int train, void* stream);
+                const float* beta, float* sums, void* du_hi, void* du_lo, void* gout_hi, void* gout_lo, float* dgamma,
+                float* dbeta, long rows, int C, int train, int flags, void* stream);
 
 /* ---- MaxPool2d(3,2,1) resnet_backbone.py:72; UpsamplingBilinear2d(x2) cdpn_rot_head_region.py:102;
  * zero insertion (stride-2 transposed convs); GroupNorm(32)+ReLU conv_pnp_net.py:76-80 */

@@ -285,6 +285,36 @@ def test_bn_train_fwd_bwd(planes, C_):
 
 
 @pytest.mark.parametrize("planes", [1, 2])
+@pytest.mark.parametrize("C_", [64, 256])
+def test_bn_bwd_relu_mask_from_u(planes, C_):
+    """Plain conv-BN-ReLU: the ReLU mask recomputed from u (flags bit 0, y not read) gives the same result as reading y."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(100 + C_)
+    N, H = 4, 16
+    U = _nhwc(torch.randn(N, C_, H, H, device="cuda", generator=g) * 2 + 0.3, planes)
+    gamma = torch.rand(C_, device="cuda", generator=g) + 0.5
+    beta = torch.randn(C_, device="cuda", generator=g) * 0.3
+    rm, rv = torch.zeros(C_, device="cuda"), torch.ones(C_, device="cuda")
+    flat = U.float().reshape(-1, C_)
+    stats = torch.stack([flat.sum(0), (flat * flat).sum(0)]).contiguous()
+    scale, shift, mean, invstd = (torch.empty(C_, device="cuda") for _ in range(4))
+    ops.bn_finalize(stats, gamma, beta, rm, rv, scale, shift, mean, invstd, C_, flat.shape[0], 1e-5, 0.1, True)
+    Y = ops.bn_act(U, scale, shift, True)
+    GY = _nhwc(torch.randn(N, C_, H, H, device="cuda", generator=g), planes)
+    outs = []
+    for from_u in (False, True):
+        sums = torch.zeros(2, C_, device="cuda")
+        dgamma, dbeta = torch.zeros(C_, device="cuda"), torch.zeros(C_, device="cuda")
+        DU, _ = ops.bn_bwd(GY, None, None if from_u else Y, U, mean, invstd, gamma, sums, dgamma, dbeta, True, beta=beta,
+                           relu_from_u=from_u, sums_zeroed=True)
+        torch.cuda.synchronize()
+        outs.append((DU.float(), dgamma, dbeta))
+    # elements with 0 < bn(u) < 3e-8 round to y == 0 in the 16-bit activation: their mask (hence du) may differ
+    assert int(((outs[0][0] - outs[1][0]).abs() > 1e-4).sum()) <= 4
+    assert _rel(outs[1][1], outs[0][1]) < 1e-3 and _rel(outs[1][2], outs[0][2]) < 1e-3
+
+
+@pytest.mark.parametrize("planes", [1, 2])
 def test_maxpool_upsample_zero_insert(planes):
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(3)
