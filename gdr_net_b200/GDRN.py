@@ -211,8 +211,27 @@ class GDRN(nn.Module):
         self.concat = cfg.MODEL.CDPN.ROT_HEAD.ROT_CONCAT
         self.r_out_dim, self.mask_out_dim, self.region_out_dim = get_xyz_mask_region_out_dim(cfg)
         self._engine: Optional[Engine] = None
+        self._vis_dev, self._vis_host = None, None
         self.use_cuda_graphs = False  # set True for fixed-shape training loops: forward/backward replay CUDA graphs
         self.precision = {"bf16": "half", "fp16": "half"}.get(precision, precision)  # "half" (1 pass) | "fp32x3" (hi/lo planes)
+
+    @property
+    def last_vis_dict(self) -> dict:
+        """The `vis/*` scalars of the most recent do_loss forward (synchronises on first access)."""
+        if self._vis_host is None:
+            if self._vis_dev is None:
+                return {}
+            v = self._vis_dev.tolist()
+            self._vis_host = {
+                "vis/error_R": v[0], "vis/error_t": v[1] * 100,
+                "vis/error_tx": abs(v[2] - v[8]) * 100, "vis/error_ty": abs(v[3] - v[9]) * 100,
+                "vis/error_tz": abs(v[4] - v[10]) * 100,
+                "vis/tx_pred": v[2], "vis/ty_pred": v[3], "vis/tz_pred": v[4],
+                "vis/tx_net": v[5], "vis/ty_net": v[6], "vis/tz_net": v[7],
+                "vis/tx_gt": v[8], "vis/ty_gt": v[9], "vis/tz_gt": v[10],
+                "vis/tx_rel_gt": v[11], "vis/ty_rel_gt": v[12], "vis/tz_rel_gt": v[13],
+            }
+        return self._vis_host
 
     @property
     def engine(self) -> Engine:
@@ -253,21 +272,13 @@ class GDRN(nn.Module):
             if name in ("loss_centroid", "loss_z") and lw[name] <= 0:
                 continue
             loss_dict[name] = losses[i] * lw[name]
-        # logging side effect (GDRN.py:246-303): ONE device->host copy instead of 18 .item() syncs
-        v = res["vis"].tolist()
-        vis_dict = {
-            "vis/error_R": v[0], "vis/error_t": v[1] * 100,
-            "vis/error_tx": abs(v[2] - v[8]) * 100, "vis/error_ty": abs(v[3] - v[9]) * 100,
-            "vis/error_tz": abs(v[4] - v[10]) * 100,
-            "vis/tx_pred": v[2], "vis/ty_pred": v[3], "vis/tz_pred": v[4],
-            "vis/tx_net": v[5], "vis/ty_net": v[6], "vis/tz_net": v[7],
-            "vis/tx_gt": v[8], "vis/ty_gt": v[9], "vis/tz_gt": v[10],
-            "vis/tx_rel_gt": v[11], "vis/ty_rel_gt": v[12], "vis/tz_rel_gt": v[13],
-        }
+        # logging side effect (GDRN.py:246-303): ONE device->host copy of 14 scalars instead of 18 .item() syncs -- and only
+        # when somebody consumes them: with an active detectron2 EventStorage now (reference behaviour), otherwise lazily
+        # through `last_vis_dict`, so a training loop without a logger never stalls the GPU between forward and backward.
+        self._vis_dev, self._vis_host = res["vis"], None
         storage = _get_event_storage()
         if storage is not None:
-            storage.put_scalars(**vis_dict)
-        self.last_vis_dict = vis_dict
+            storage.put_scalars(**self.last_vis_dict)
         return {}, loss_dict
 
 
