@@ -220,6 +220,27 @@ __global__ void __launch_bounds__(256, 4) bn_fwd_kernel(const bf16* __restrict__
     bn_apply_loop<LO, RES>(x_hi, x_lo, r_hi, r_lo, y_hi, y_lo, s_sc, s_sh, rows * (C / 8), C / 8, relu);
 }
 
+
+// (channel group, x, y, image) of a flat NHWC index with 32-bit arithmetic (every tensor of the step has < 2^31 groups;
+// 64-bit div / mod costs ~100 instructions each and dominated the gather kernels)
+struct Pix {
+    int g, x, y, b;
+};
+__device__ __forceinline__ Pix decode_pix(long idx, int cg, int W, int H) {
+    unsigned t = (unsigned)idx;
+    Pix p;
+    unsigned q = t / (unsigned)cg;
+    p.g = (int)(t - q * (unsigned)cg);
+    t = q;
+    q = t / (unsigned)W;
+    p.x = (int)(t - q * (unsigned)W);
+    t = q;
+    q = t / (unsigned)H;
+    p.y = (int)(t - q * (unsigned)H);
+    p.b = (int)q;
+    return p;
+}
+
 // ------------------------------------------------------------------------------------------------
 // MaxPool 3x3 s2 p1 (first maximum in row-major window order wins, like ATen)
 // ------------------------------------------------------------------------------------------------
@@ -228,12 +249,8 @@ __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x_hi, const bf16* __
     const int cg = C / 8, Ho = H / 2, Wo = W / 2;
     const long total = (long)B * Ho * Wo * cg;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int g = (int)(idx % cg);
-        long t = idx / cg;
-        const int ox = (int)(t % Wo);
-        t /= Wo;
-        const int oy = (int)(t % Ho);
-        const int b = (int)(t / Ho);
+        const Pix px = decode_pix(idx, cg, Wo, Ho);
+        const int g = px.g, ox = px.x, oy = px.y, b = px.b;
         float m[8];
         uint32_t arg[8];
 #pragma unroll
@@ -276,29 +293,37 @@ __global__ void maxpool_bwd_kernel(const uint8_t* __restrict__ arg_in, const bf1
     const int cg = C / 8, Ho = H / 2, Wo = W / 2;
     const long total = (long)B * H * W * cg;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int g = (int)(idx % cg);
-        long t = idx / cg;
-        const int ix = (int)(t % W);
-        t /= W;
-        const int iy = (int)(t % H);
-        const int b = (int)(t / H);
+        const Pix px = decode_pix(idx, cg, W, H);
+        const int g = px.g, ix = px.x, iy = px.y, b = px.b;
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        for (int oy = iy / 2; oy <= (iy + 1) / 2; ++oy) {  // windows with oy*2-1 <= iy <= oy*2+1
-            if (oy >= Ho) continue;
-            for (int ox = ix / 2; ox <= (ix + 1) / 2; ++ox) {
-                if (ox >= Wo) continue;
-                const uint32_t code = (uint32_t)((iy - (oy * 2 - 1)) * 3 + (ix - (ox * 2 - 1)));
-                const long o = (((long)b * Ho + oy) * Wo + ox) * cg + g;
-                const uint2 a = __ldg(reinterpret_cast<const uint2*>(arg_in) + o);
-                float gv[8];
-                load8(g_hi, g_lo, o, gv);
+        // windows (oy, ox) with oy*2-1 <= iy <= oy*2+1: oy in {iy/2, (iy+1)/2} (one window per axis for even iy, two for odd).
+        // All four candidates' loads are issued before any is consumed (the loop form serialised 8 dependent L2 round trips).
+        const int oyA = iy >> 1, oyB = (iy + 1) >> 1, oxA = ix >> 1, oxB = (ix + 1) >> 1;
+        const bool vyB = (oyB != oyA) && (oyB < Ho), vxB = (oxB != oxA) && (oxB < Wo);
+        const int oys[2] = {oyA, vyB ? oyB : oyA}, oxs[2] = {oxA, vxB ? oxB : oxA};
+        uint2 codes[4];
+        uint4 gh[4], gl[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t aj = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xffu;
-                    if (aj == code) acc[j] += gv[j];
-                }
+        for (int q = 0; q < 4; ++q) {
+            const long o = (((long)b * Ho + oys[q >> 1]) * Wo + oxs[q & 1]) * cg + g;
+            codes[q] = __ldg(reinterpret_cast<const uint2*>(arg_in) + o);
+            gh[q] = ld16(g_hi, o);
+            if (g_lo != nullptr) gl[q] = ld16(g_lo, o);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const bool valid = ((q >> 1) == 0 || vyB) && ((q & 1) == 0 || vxB);
+            if (!valid) continue;
+            const uint32_t code = (uint32_t)((iy - (oys[q >> 1] * 2 - 1)) * 3 + (ix - (oxs[q & 1] * 2 - 1)));
+            float gv[8];
+            unpack8(gh[q], gv);
+            if (g_lo != nullptr) unpack8_lo(gl[q], gv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t aj = ((j < 4 ? codes[q].x : codes[q].y) >> (8 * (j & 3))) & 0xffu;
+                if (aj == code) acc[j] += gv[j];
             }
         }
         store8(dx_hi, dx_lo, idx, acc);
@@ -314,12 +339,8 @@ __global__ void upsample2x_fwd_kernel(const bf16* __restrict__ x_hi, const bf16*
     const float sh = (float)(H - 1) / (float)(Ho - 1), sw = (float)(W - 1) / (float)(Wo - 1);
     const long total = (long)B * Ho * Wo * cg;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int g = (int)(idx % cg);
-        long t = idx / cg;
-        const int ox = (int)(t % Wo);
-        t /= Wo;
-        const int oy = (int)(t % Ho);
-        const int b = (int)(t / Ho);
+        const Pix px = decode_pix(idx, cg, Wo, Ho);
+        const int g = px.g, ox = px.x, oy = px.y, b = px.b;
         const float fy = sh * oy, fx = sw * ox;
         const int y0 = (int)fy, x0 = (int)fx;
         const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
@@ -343,18 +364,33 @@ __global__ void upsample2x_bwd_kernel(const bf16* __restrict__ g_hi, const bf16*
     const float sh = (float)(H - 1) / (float)(Ho - 1), sw = (float)(W - 1) / (float)(Wo - 1);
     const long total = (long)B * H * W * cg;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int g = (int)(idx % cg);
-        long t = idx / cg;
-        const int ix = (int)(t % W);
-        t /= W;
-        const int iy = (int)(t % H);
-        const int b = (int)(t / H);
+        const Pix px = decode_pix(idx, cg, W, H);
+        const int g = px.g, ix = px.x, iy = px.y, b = px.b;
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        const int oy_lo = max(0, 2 * iy - 3), oy_hi = min(Ho - 1, 2 * iy + 3);
-        const int ox_lo = max(0, 2 * ix - 3), ox_hi = min(Wo - 1, 2 * ix + 3);
-        for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+        // output rows whose source coordinate sh*oy lies in [iy-1, iy+1): oy in [2iy-2, 2iy+3] since 1/sh is in (2, 2.07];
+        // the exact weight computed below is zero for the one or two extra candidates.  Column weights do not depend on
+        // the row, so they are computed once; the (<= 6) loads of a row are issued together.
+        const int oy0 = 2 * iy - 2, ox0 = 2 * ix - 2;
+        float wxs[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const int ox = ox0 + c;
+            float wx = 0.f;
+            if (ox >= 0 && ox < Wo) {
+                const float fx = sw * ox;
+                const int x0 = (int)fx;
+                const int x1 = x0 + (x0 < W - 1 ? 1 : 0);
+                const float lx1 = fx - x0, lx0 = 1.f - lx1;
+                if (x0 == ix) wx += lx0;
+                if (x1 == ix) wx += lx1;
+            }
+            wxs[c] = wx;
+        }
+        for (int r = 0; r < 6; ++r) {
+            const int oy = oy0 + r;
+            if (oy < 0 || oy >= Ho) continue;
             const float fy = sh * oy;
             const int y0 = (int)fy;
             const int y1 = y0 + (y0 < H - 1 ? 1 : 0);
@@ -363,20 +399,25 @@ __global__ void upsample2x_bwd_kernel(const bf16* __restrict__ g_hi, const bf16*
             if (y0 == iy) wy += ly0;
             if (y1 == iy) wy += ly1;
             if (wy == 0.f) continue;
-            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-                const float fx = sw * ox;
-                const int x0 = (int)fx;
-                const int x1 = x0 + (x0 < W - 1 ? 1 : 0);
-                const float lx1 = fx - x0, lx0 = 1.f - lx1;
-                float wx = 0.f;
-                if (x0 == ix) wx += lx0;
-                if (x1 == ix) wx += lx1;
-                if (wx == 0.f) continue;
-                float gv[8];
-                load8(g_hi, g_lo, (((long)b * Ho + oy) * Wo + ox) * cg + g, gv);
-                const float w = wy * wx;
+            const long rowbase = (((long)b * Ho + oy) * Wo + ox0) * cg + g;
+            uint4 vh[6], vl[6];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, gv[j], acc[j]);
+            for (int c = 0; c < 6; ++c) {
+                if (wxs[c] != 0.f) {
+                    vh[c] = ld16(g_hi, rowbase + (long)c * cg);
+                    if (g_lo != nullptr) vl[c] = ld16(g_lo, rowbase + (long)c * cg);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                if (wxs[c] != 0.f) {
+                    float gv[8];
+                    unpack8(vh[c], gv);
+                    if (g_lo != nullptr) unpack8_lo(vl[c], gv);
+                    const float w = wy * wxs[c];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, gv[j], acc[j]);
+                }
             }
         }
         store8(dx_hi, dx_lo, idx, acc);

@@ -35,3 +35,22 @@ for name, H, Cc in [("stem 128x128x64", 128, 64), ("layer1 64x64x64", 64, 64), (
     t_copy = timeit(lambda: y.buf.copy_(u.buf))
     print(f"{name:20s} {nbytes/1e6:7.1f} MB/tensor | bn_fwd {t_fwd:7.1f} us ({2*nbytes/t_fwd/1e6:5.2f} TB/s) | bn_act {t_act:7.1f} us | "
           f"bn_bwd(reduce+apply) {t_bwd:7.1f} us ({7*nbytes/t_bwd/1e6:5.2f} TB/s) | torch copy {t_copy:7.1f} us ({2*nbytes/t_copy/1e6:5.2f} TB/s)")
+
+# gather kernels at their step sizes
+x = ops.PT((B, 128, 128, 64), 1); x.buf.normal_()
+t_mp = timeit(lambda: ops.maxpool_fwd(x, want_arg=True))
+yp, arg = ops.maxpool_fwd(x, want_arg=True)
+gp = ops.like(yp); gp.buf.normal_()
+t_mpb = timeit(lambda: ops.maxpool_bwd(arg, gp))
+print(f"maxpool 128x128x64: fwd {t_mp:7.1f} us  bwd {t_mpb:7.1f} us   (ideal ~34 / ~35 us at 5.5 TB/s)")
+for H in (16, 32):
+    xs = ops.PT((B, H, H, 256), 1); xs.buf.normal_()
+    t_uf = timeit(lambda: ops.upsample2x_fwd(xs))
+    gs = ops.PT((B, 2 * H, 2 * H, 256), 1); gs.buf.normal_()
+    t_ub = timeit(lambda: ops.upsample2x_bwd(gs))
+    mb = xs.numel() * 2 * 5 / 1e6
+    print(f"upsample {H}->{2*H} x256: fwd {t_uf:7.1f} us  bwd {t_ub:7.1f} us   ({mb:.0f} MB each way, ideal {mb/5.5:.0f} us)")
+xi = torch.randn(B, 3, 256, 256, device="cuda")
+a_col = ops.PT((B * 128 * 128, 192), 1)
+t_im = timeit(lambda: C.gdrn_stem_im2col(xi.data_ptr(), a_col.hi_ptr, a_col.lo_ptr, B, 256, 256, _stream()))
+print(f"stem im2col: {t_im:7.1f} us  (writes {a_col.numel()*2/1e6:.0f} MB, ideal {a_col.numel()*2/5.5e6:.0f} us)")
