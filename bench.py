@@ -334,7 +334,7 @@ def roofline_live(main, peaks):
     aux = {k: (v.float().contiguous() if isinstance(v, torch.Tensor) and v.dtype != torch.long else v)
            for k, v in aux_from_batch(batch).items()}
     records = []
-    orig = {n: getattr(ops, n) for n in ("conv_fwd", "gemm_fwd", "conv_wgrad", "gemm_wgrad")}
+    orig = {n: getattr(ops, n) for n in ("conv_fwd", "gemm_fwd", "conv_dgrad_s2", "conv_wgrad", "gemm_wgrad")}
 
     from gdr_net_b200.capi import C as _C
 
@@ -344,7 +344,7 @@ def roofline_live(main, peaks):
             e0.record()
             r = fn(*a, **k)
             e1.record()
-            variant = _C.load().gdrn_last_gemm_variant() if name in ("conv_fwd", "gemm_fwd") else 0
+            variant = _C.load().gdrn_last_gemm_variant() if name in ("conv_fwd", "gemm_fwd", "conv_dgrad_s2") else 0
             records.append((name, flops_of(*a, **k), e0, e1, variant))
             return r
 
@@ -353,6 +353,10 @@ def roofline_live(main, peaks):
     def f_conv(x_, wp, Cout, KH, KW, stride, pad, **k):
         N, H, W, Cin = x_.shape
         return 2.0 * N * (H // stride) * (W // stride) * Cout * Cin * KH * KW * k.get("algo_scale", 1.0)
+
+    def f_dg2(du, wd, Cx, K, pad, **k):  # stride-2 dgrad by output-parity phases: exactly the conv's MACs
+        N, Ho, Wo, Cy = du.shape
+        return 2.0 * N * Ho * Wo * Cy * Cx * K * K
 
     def f_gemm(a, wp, N, **k):
         return 2.0 * a.shape[0] * N * a.shape[1]
@@ -366,6 +370,7 @@ def roofline_live(main, peaks):
 
     ops.conv_fwd = timed("conv_fwd", orig["conv_fwd"], f_conv)
     ops.gemm_fwd = timed("gemm_fwd", orig["gemm_fwd"], f_gemm)
+    ops.conv_dgrad_s2 = timed("conv_dgrad_s2", orig["conv_dgrad_s2"], f_dg2)
     ops.conv_wgrad = timed("conv_wgrad", orig["conv_wgrad"], f_cw)
     ops.gemm_wgrad = timed("gemm_wgrad", orig["gemm_wgrad"], f_gw)
     try:
@@ -407,10 +412,11 @@ def roofline_live(main, peaks):
         "peak_source": "bf16_tflops_sustained (fp16 and bf16 tcgen05 rates are equal) of " + peaks["source"] + " (kernel timed inside the long step)",
         "launches_per_step": dom[1][2], "avg_launch_ms": round(dom[1][1] / dom[1][2], 4),
         "algorithmic_gflop_per_launch": round(dom[1][0] / dom[1][2] / 1e9, 2), "share_of_step": round(dom[1][1] / step_ms, 3),
-        "traffic": 222.1e6,
+        "traffic": 224.1e6,
         "traffic_note": "dram read+write of ONE launch of this kernel on the 64x64 256->256 conv (B=64), ncu --set full "
-                        "(profiles/r1_ncu_full_kernel_metrics.txt); algorithmic bytes of that launch 269.7e6 (bf16 in + out + weights)",
-        "tensor_pipe_pct_ncu": 57.3,
+                        "(profiles/r1_ncu_full_gemm_fwd_final.txt: 135.5 MB read + 88.7 MB written); algorithmic bytes of that "
+                        "launch 269.7e6 (16-bit in + out + weights)",
+        "tensor_pipe_pct_ncu": 49.4,
         "gemm_family": {"achieved": round(tot_fl / (tot_ms * 1e-3) / 1e12, 1), "frac": round(tot_fl / (tot_ms * 1e-3) / 1e12 / peak, 4),
                         "share_of_step": round(tot_ms / step_ms, 3), "launches_per_step": sum(v[2] for v in fam.values()),
                         "algorithmic_gflop_per_step": round(tot_fl / 1e9, 1)},
