@@ -263,7 +263,14 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
         float* tr = s_tr + (warp - 4) * (32 * 17);
         __nv_bfloat16* out_hi = reinterpret_cast<__nv_bfloat16*>(p.out_hi);
         __nv_bfloat16* out_lo = reinterpret_cast<__nv_bfloat16*>(p.out_lo);
-        for (int tg = my_cluster + grp * num_clusters, it = grp; tg < num_groups; tg += 2 * num_clusters, it += 2) {
+        // One tile per CTA (small-M layers: 16x16 / 8x8 maps, FC): there is no second tile to overlap with, so both
+        // warpgroups share the single tile's epilogue, each draining half of its column chunks.
+        constexpr int NCH = BLOCK_N / 32;
+        const bool split_epi = num_groups <= num_clusters && !p.no_split_epi;
+        const int c_begin = split_epi ? grp * (NCH / 2) : 0;
+        const int c_end = split_epi ? (grp + 1) * (NCH / 2) : NCH;
+        for (int tg = split_epi ? my_cluster : my_cluster + grp * num_clusters, it = split_epi ? 0 : grp; tg < num_groups;
+             tg += 2 * num_clusters, it += 2) {
             int rem = tg, ph = 0;
             if (p.nphase) {
                 ph = tg / num_tiles;
@@ -286,7 +293,7 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
                 grow = (((n << (p.ph_log2 + 1)) + 2 * i + p.ph_a[ph]) << (p.pw_log2 + 1)) + 2 * j + p.ph_b[ph];
             }
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
+            for (int c = c_begin; c < c_end; ++c) {
                 const int col0 = n_tile * BLOCK_N + c * 32;
                 if (col0 >= p.N) continue;  // warp-uniform
                 float f[32];
@@ -386,7 +393,7 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0 && !(split_epi && grp == 1)) mbar_arrive(&tempty_bar[acc]);
         }
         if (p.stats != nullptr) {
             asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
@@ -447,7 +454,14 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
 
 static thread_local int g_last_variant = 0;
 
-static int dispatch_gemm(const GemmParams& p, int block_n, int nsplit, cudaStream_t stream) {
+static int dispatch_gemm(const GemmParams& p_in, int block_n, int nsplit, cudaStream_t stream) {
+    static int no_split = -1;
+    if (no_split < 0) {
+        const char* e = getenv("GDRN_NO_SPLIT_EPI");
+        no_split = e ? atoi(e) : 0;
+    }
+    GemmParams p = p_in;
+    p.no_split_epi = no_split;
     g_last_variant = block_n * 10 + nsplit;
     if (nsplit == 1) {
         if (block_n == 256) return launch_gemm<256, 1>(p, stream);

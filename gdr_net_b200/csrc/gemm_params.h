@@ -28,6 +28,7 @@ struct GemmParams {
     int ph_a[4], ph_b[4];
     signed char tap_dh[12], tap_dw[12], tap_w[12];
     int pw_log2, ph_log2;  // log2 of the dY width / height
+    int no_split_epi;      // A/B switch (GDRN_NO_SPLIT_EPI=1): single-tile CTAs keep the whole epilogue on one warpgroup
 };
 
 
