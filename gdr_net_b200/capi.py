@@ -8,7 +8,7 @@ import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "gdrn_b200.h")
-LIB_PATH = os.path.join(_HERE, "lib", "libgdrn_b200.so")
+LIB_PATH = os.environ.get("GDRN_LIB_PATH") or os.path.join(_HERE, "lib", "libgdrn_b200.so")  # override: A/B of two builds
 
 _SCALARS = {"int": ctypes.c_int, "long": ctypes.c_long, "float": ctypes.c_float, "double": ctypes.c_double,
             "long long": ctypes.c_longlong}

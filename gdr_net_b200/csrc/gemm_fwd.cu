@@ -76,8 +76,11 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
     constexpr int NPL = Cfg::NPL;
     constexpr int STAGES = Cfg::STAGES;
 
+    // 1024-byte alignment by POINTER arithmetic on the __shared__ array (not through uintptr_t): the compiler keeps the
+    // shared address space, so the epilogue's transposes / statistics compile to STS / LDS / ATOMS instead of generic
+    // ST / LD / ATOM (+ an address-space check each) -- the BN-statistics epilogue was the bottleneck of the 64-channel layers
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
     uint64_t* empty_bar = full_bar + STAGES;

@@ -37,6 +37,7 @@ struct WgradParams {
 };
 
 constexpr int kWgStageA = 2 * 8192;
+constexpr int kWgThreads = 64 + 256;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-9: two epilogue warpgroups (column halves)
 
 template <int N_TILE, int NSPLIT>
 struct WgradCfg {
@@ -58,7 +59,7 @@ struct WgradCfg {
 };
 
 template <int N_TILE, int NSPLIT>
-__global__ void __launch_bounds__(192, 1) gemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
+__global__ void __launch_bounds__(kWgThreads, 1) gemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
     using Cfg = WgradCfg<N_TILE, NSPLIT>;
     constexpr int NPL = Cfg::NPL;
     constexpr int STAGES = Cfg::STAGES;
@@ -198,8 +199,10 @@ __global__ void __launch_bounds__(192, 1) gemm_wgrad_kernel(const __grid_constan
             umma_commit(done_bar);
         }
     } else {
-        // epilogue warps 2..5: TMEM lane quadrant = warp % 4
+        // epilogue warps 2..9: TMEM lane quadrant = warp % 4; the CTA's single tile is drained by two warpgroups, each
+        // taking half of the 32-column chunks (one work item per CTA: the epilogue is fully exposed)
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const int co = m_tile * 128 + row;
         if (nkb > 0) {
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(192, 1) gemm_wgrad_kernel(const __grid_constan
         const size_t col0 = p.tap_pack ? (size_t)tap * N_TILE : (size_t)tap * p.Ntot + (size_t)n_tile * N_TILE;
         float* dst_row = p.ws + ((size_t)ks * p.num_m_tiles * 128 + co) * ld + col0;
 #pragma unroll 1
-        for (int c = 0; c < N_TILE / 32; ++c) {
+        for (int c = half * (N_TILE / 64); c < (half + 1) * (N_TILE / 64); ++c) {
             uint32_t raw[32];
             if (nkb > 0) {
                 const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + c * 32;
@@ -258,7 +261,7 @@ static int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
         attr_set = true;
     }
     const int grid = p.num_m_tiles * p.num_n_tiles * p.items * p.ksplit;
-    kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(p);
+    kern<<<grid, kWgThreads, Cfg::SMEM_BYTES, stream>>>(p);
     GDRN_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;
