@@ -130,7 +130,101 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        if (cl == 1) {
+            // Fast path (no cluster), executed by the whole warp with warp-uniform control flow; one elected lane issues.  This single thread used to spend ~1100 cycles per k-block on index arithmetic (two
+            // integer divisions, generic->shared conversions, parameter reloads) -- more than the 128..512 cycles of MMA
+            // work a k-block carries, so EVERY layer ran at the producer's pace (ncu: this warp ~100 % busy, tensor pipe
+            // 11 % / 50 %).  Taps and channel chunks are now nested loops with incremental state; per k-block only the
+            // barrier wait, the expect_tx and the TMA issues remain.
+            const uint32_t smem_base = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+            const uint64_t tmB0 = reinterpret_cast<uint64_t>(&p.tmB[0]), tmB1 = reinterpret_cast<uint64_t>(&p.tmB[1]);
+            const int cch = p.cchunks, mode = p.mode, KWv = p.KW, padv = p.pad, stride2 = (p.stride == 2), nph = p.nphase;
+            const int ntap_all = mode == 1 ? p.num_kb / (cch > 0 ? cch : 1) : 0;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int grp = my_cluster; grp < num_groups; grp += num_clusters) {
+                int rem = grp, tap_base = 0, ntap = ntap_all;
+                if (nph) {
+                    const int ph = grp / num_tiles;
+                    rem = grp - ph * num_tiles;
+                    tap_base = p.ph_tap0[ph];
+                    ntap = p.ph_tap0[ph + 1] - tap_base;
+                }
+                const int n_tile = rem % p.num_n_tiles;
+                const int m_tile = rem / p.num_n_tiles;
+                const int bn0 = n_tile * BLOCK_N;
+                if (mode == 1) {
+                    int n0 = 0, h0 = 0;
+                    if (p.TN == 1) {
+                        n0 = m_tile / p.tiles_per_img;
+                        h0 = (m_tile - n0 * p.tiles_per_img) * p.TH;
+                    } else {
+                        n0 = m_tile * p.TN;
+                    }
+                    int r = 0, s2 = 0;
+                    for (int t = 0; t < ntap; ++t) {
+                        int dh, dw, map = 0, wt = t;
+                        if (nph) {
+                            dh = p.tap_dh[tap_base + t];
+                            dw = p.tap_dw[tap_base + t];
+                            wt = p.tap_w[tap_base + t];
+                        } else {
+                            dh = r - padv;
+                            dw = s2 - padv;
+                            if (stride2) {
+                                map = ((dh & 1) << 1) | (dw & 1);
+                                dh >>= 1;  // arithmetic shift == floor division
+                                dw >>= 1;
+                            }
+                            if (++s2 == KWv) {
+                                s2 = 0;
+                                ++r;
+                            }
+                        }
+                        const uint64_t tmA0 = reinterpret_cast<uint64_t>(&p.tmA[0][map]);
+                        const uint64_t tmA1 = reinterpret_cast<uint64_t>(&p.tmA[1][map]);
+                        const int hh = h0 + dh;
+                        int kw = wt * cch * kBlockK;
+                        for (int cc = 0; cc < cch; ++cc, kw += kBlockK) {
+                            const uint32_t fb = full0 + stage * 8, dst = smem_base + stage * Cfg::STAGE_BYTES;
+                            mbar_wait_u32(empty0 + stage * 8, phase ^ 1);
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx_u32(fb, Cfg::STAGE_BYTES);
+                                tma_load_4d_u32(dst, tmA0, fb, cc * kBlockK, dw, hh, n0);
+                                if (NPL == 2) tma_load_4d_u32(dst + Cfg::A_BYTES, tmA1, fb, cc * kBlockK, dw, hh, n0);
+                                tma_load_2d_u32(dst + NPL * Cfg::A_BYTES, tmB0, fb, kw, bn0);
+                                if (NPL == 2) tma_load_2d_u32(dst + NPL * Cfg::A_BYTES + Cfg::B_BYTES, tmB1, fb, kw, bn0);
+                            }
+                            __syncwarp();
+                            if (++stage == STAGES) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+                    }
+                } else {
+                    const uint64_t tmA0 = reinterpret_cast<uint64_t>(&p.tmA[0][0]);
+                    const uint64_t tmA1 = reinterpret_cast<uint64_t>(&p.tmA[1][0]);
+                    const int row0 = m_tile * kBlockM;
+                    for (int kb = 0, kc = 0; kb < p.num_kb; ++kb, kc += kBlockK) {
+                        const uint32_t fb = full0 + stage * 8, dst = smem_base + stage * Cfg::STAGE_BYTES;
+                        mbar_wait_u32(empty0 + stage * 8, phase ^ 1);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx_u32(fb, Cfg::STAGE_BYTES);
+                            tma_load_2d_u32(dst, tmA0, fb, kc, row0);
+                            if (NPL == 2) tma_load_2d_u32(dst + Cfg::A_BYTES, tmA1, fb, kc, row0);
+                            tma_load_2d_u32(dst + NPL * Cfg::A_BYTES, tmB0, fb, kc, bn0);
+                            if (NPL == 2) tma_load_2d_u32(dst + NPL * Cfg::A_BYTES + Cfg::B_BYTES, tmB1, fb, kc, bn0);
+                        }
+                        __syncwarp();
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        } else if (lane == 0) {  // cluster (multicast) experiment: the original generic loop
             int stage = 0;
             uint32_t phase = 0;
             for (int grp = my_cluster; grp < num_groups; grp += num_clusters) {
@@ -209,7 +303,64 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (single thread)
-        if (lane == 0) {
+        if (cl == 1) {
+            // Fast path, executed by the WHOLE warp with warp-uniform control flow; only the tcgen05 instructions are issued by
+            // one elected lane.  (Inside an `if (lane == 0)` region the compiler wraps every UTCHMMA in an ELECT + 5x R2UR
+            // "waterfall" loop, ~20 instructions per MMA.)
+            // The shared-memory descriptors of a stage differ only in their 14-bit address field, so they are
+            // one constant OR-ed with (address >> 4) and advanced by +2 (32 bytes) per 16-wide k-step -- the generic loop
+            // rebuilt eight descriptors per k-block (126 instructions on this single thread).
+            constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N, 0, 0);
+            const uint64_t desc_const = make_smem_desc(0, 16, 1024);
+            const uint32_t smem_base = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+            const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
+            const int cch = p.cchunks, nph = p.nphase, nkb_all = p.num_kb;
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int grp = my_cluster; grp < num_groups; grp += num_clusters, ++it) {
+                const int acc = it & 1;
+                mbar_wait_u32(tempty0 + acc * 8, ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_main = tmem_base + acc * Cfg::NACC * BLOCK_N;
+                const uint32_t d_cross = d_main + Cfg::NMAIN * BLOCK_N;
+                int nkb = nkb_all;
+                if (nph) {
+                    const int ph = grp / num_tiles;
+                    nkb = (p.ph_tap0[ph + 1] - p.ph_tap0[ph]) * cch;
+                }
+                uint32_t accum = 0;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint64_t da = desc_const | (uint64_t)(a_addr >> 4);
+                    const uint64_t db = da + ((NPL * Cfg::A_BYTES) >> 4);
+                    mbar_wait_u32(full0 + stage * 8, phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            const uint32_t ac = (k == 0) ? accum : 1u;
+                            if (NSPLIT == 3) {
+                                umma_bf16(d_main, da + 2 * k, db + 2 * k, idesc, ac);
+                                umma_bf16(d_cross, da + 2 * k, db + (Cfg::B_BYTES >> 4) + 2 * k, idesc, ac);
+                                umma_bf16(d_cross, da + (Cfg::A_BYTES >> 4) + 2 * k, db + 2 * k, idesc, 1u);
+                            } else {
+                                umma_bf16(d_main, da + 2 * k, db + 2 * k, idesc, ac);
+                            }
+                        }
+                        umma_commit_u32(empty0 + stage * 8);
+                    }
+                    __syncwarp();
+                    accum = 1u;
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                if (elect_one()) umma_commit_u32(tfull0 + acc * 8);
+                __syncwarp();
+            }
+        } else if (lane == 0) {  // cluster (multicast) experiment: the original generic loop
             constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
@@ -287,6 +438,7 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
             tc_fence_after();
             const long mrow = (long)m_tile * kBlockM + row;
             const bool row_ok = mrow < p.M;
+            const bool all_rows = (long)(m_tile + 1) * kBlockM <= p.M;
             long grow = mrow;  // output row
             if (p.nphase) {    // (n, i, j) of the dY lattice -> pixel (2i + a, 2j + b) of the 2x larger dX
                 const long j = mrow & ((1L << p.pw_log2) - 1);
@@ -351,7 +503,9 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
                                 if (col0 + 2 * j >= p.N) a = 0.f;
                                 if (col0 + 2 * j + 1 >= p.N) b = 0.f;
                             }
-                            split2(a, b, hi[j], lo[j]);
+                            // single-plane outputs skip the residual (lo) plane arithmetic: the epilogue warps run alone on
+                            // their schedulers, so every instruction here is on the critical path of the small-K layers
+                            if (out_lo != nullptr) split2(a, b, hi[j], lo[j]); else hi[j] = pack_hi2(a, b);
                         }
                         const int ncopy = full_chunk ? 4 : ((min(p.ldc, col0 + 32) - col0) / 8);
                         uint4* dh = reinterpret_cast<uint4*>(out_hi + grow * p.ldc + col0);
@@ -373,8 +527,13 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
                     // (A shuffle butterfly was latency-bound: ~60 dependent shuffles per chunk.)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
+                        if (all_rows) {  // warp-uniform: every row of the tile is a valid pixel (no per-element select)
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) tr[lane * 17 + j] = row_ok ? f[h * 16 + j] : 0.f;
+                            for (int j = 0; j < 16; ++j) tr[lane * 17 + j] = f[h * 16 + j];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) tr[lane * 17 + j] = row_ok ? f[h * 16 + j] : 0.f;
+                        }
                         __syncwarp();
                         float s1 = 0.f, s2 = 0.f;
                         const int col = lane & 15, r0 = (lane >> 4) * 16;
