@@ -106,8 +106,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) gemm_wgrad_kernel(const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Producer and MMA issuer run their loops with the WHOLE warp (warp-uniform control flow, operands in uniform registers);
+    // one elected lane issues the TMA / tcgen05 instructions.  Per k-block nothing but the barrier wait, the expect_tx and the
+    // issues remains (the first version rebuilt coordinates with divisions and eight descriptors per k-block on one thread,
+    // which -- not the tensor pipe -- set the pace; see gemm_fwd.cu).
     if (warp == 0) {
-        if (lane == 0 && nkb > 0) {
+        if (nkb > 0) {
             int dh = 0, dw = 0, map = 0;
             if (p.mode == 1 && p.tap_pack) {
                 dh = tap - p.pad;  // `tap` is the filter row; the column shift varies per 64-channel chunk below
@@ -122,42 +126,61 @@ __global__ void __launch_bounds__(kWgThreads, 1) gemm_wgrad_kernel(const __grid_
                     dw >>= 1;
                 }
             }
+            const uint32_t smem_base = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+            const uint64_t tmA0 = reinterpret_cast<uint64_t>(&p.tmA[0]), tmA1 = reinterpret_cast<uint64_t>(&p.tmA[1]);
+            const uint64_t tmB0 = reinterpret_cast<uint64_t>(&p.tmB[0][map]), tmB1 = reinterpret_cast<uint64_t>(&p.tmB[1][map]);
+            const int mode = p.mode, tap_pack = p.tap_pack, padv = p.pad, bpi = p.blocks_per_img, THk = p.THk, TNk = p.TNk;
+            const int m0 = m_tile * 128, nb0 = n_tile * N_TILE;
+            // (image, 64-pixel block inside the image) of the first k-block, advanced incrementally
+            int n0 = 0, hb = 0;
+            if (mode == 1) {
+                if (TNk == 1) {
+                    n0 = kb_begin / bpi;
+                    hb = kb_begin - n0 * bpi;
+                } else {
+                    n0 = kb_begin * TNk;
+                }
+            }
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = kb_begin; kb < kb_end; ++kb) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+                const uint32_t fb = full0 + stage * 8, dst = smem_base + stage * Cfg::STAGE_BYTES;
+                const int hh = hb * THk + dh, prow = kb * 64;
+                mbar_wait_u32(empty0 + stage * 8, phase ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx_u32(fb, Cfg::STAGE_BYTES);
 #pragma unroll
-                for (int pl = 0; pl < NPL; ++pl) {
-                    uint8_t* a_dst = st + pl * Cfg::A_BYTES;
-                    tma_load_2d(a_dst, &p.tmA[pl], &full_bar[stage], m_tile * 128, kb * 64);
-                    tma_load_2d(a_dst + 8192, &p.tmA[pl], &full_bar[stage], m_tile * 128 + 64, kb * 64);
-                    uint8_t* b_dst = st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES;
-                    if (p.mode == 1) {
-                        int n0, h0;
-                        if (p.TNk == 1) {
-                            n0 = kb / p.blocks_per_img;
-                            h0 = (kb - n0 * p.blocks_per_img) * p.THk;
+                    for (int pl = 0; pl < NPL; ++pl) {
+                        const uint32_t a_dst = dst + pl * Cfg::A_BYTES;
+                        const uint64_t tmA = pl ? tmA1 : tmA0, tmB = pl ? tmB1 : tmB0;
+                        tma_load_2d_u32(a_dst, tmA, fb, m0, prow);
+                        tma_load_2d_u32(a_dst + 8192, tmA, fb, m0 + 64, prow);
+                        const uint32_t b_dst = dst + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES;
+                        if (mode == 1) {
+                            if (tap_pack) {
+#pragma unroll
+                                for (int c = 0; c < NCH; ++c)  // chunk c = filter column c (all 64 input channels)
+                                    tma_load_4d_u32(b_dst + c * 8192, tmB, fb, 0, c - padv, hh, n0);
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < NCH; ++c)
+                                    tma_load_4d_u32(b_dst + c * 8192, tmB, fb, nb0 + c * 64, dw, hh, n0);
+                            }
                         } else {
-                            n0 = kb * p.TNk;
-                            h0 = 0;
+#pragma unroll
+                            for (int c = 0; c < NCH; ++c) tma_load_2d_u32(b_dst + c * 8192, tmB, fb, nb0 + c * 64, prow);
                         }
-                        if (p.tap_pack) {
-#pragma unroll
-                            for (int c = 0; c < NCH; ++c)  // chunk c = filter column c (all 64 input channels)
-                                tma_load_4d(b_dst + c * 8192, &p.tmB[pl][0], &full_bar[stage], 0, c - p.pad, h0 + dh, n0);
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < NCH; ++c)
-                                tma_load_4d(b_dst + c * 8192, &p.tmB[pl][map], &full_bar[stage], n_tile * N_TILE + c * 64, dw,
-                                            h0 + dh, n0);
+                    }
+                }
+                __syncwarp();
+                if (mode == 1) {
+                    if (TNk == 1) {
+                        if (++hb == bpi) {
+                            hb = 0;
+                            ++n0;
                         }
                     } else {
-#pragma unroll
-                        for (int c = 0; c < NCH; ++c)
-                            tma_load_2d(b_dst + c * 8192, &p.tmB[pl][0], &full_bar[stage], n_tile * N_TILE + c * 64,
-                                        kb * 64);
+                        n0 += TNk;
                     }
                 }
                 if (++stage == STAGES) {
@@ -167,36 +190,42 @@ __global__ void __launch_bounds__(kWgThreads, 1) gemm_wgrad_kernel(const __grid_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && nkb > 0) {
+        if (nkb > 0) {
             constexpr uint32_t idesc = make_idesc(128, N_TILE, 1, 1);
-            int stage = 0;
+            const uint64_t desc_const = make_smem_desc(0, 8192, 1024);  // only the 14-bit address field varies
+            const uint32_t smem_base = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+            int stage = 0, main_idx = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
+                const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
+                const uint64_t da = desc_const | (uint64_t)(a_addr >> 4);
+                const uint64_t db = da + ((NPL * Cfg::A_BYTES) >> 4);
+                mbar_wait_u32(full0 + stage * 8, phase);
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                const uint32_t b_hi = a_hi + NPL * Cfg::A_BYTES;
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {  // 16 pixels (= 16 rows of 128 B) per MMA
-                    const uint64_t da = make_smem_desc(a_hi + k * 2048, 8192, 1024);
-                    const uint64_t db = make_smem_desc(b_hi + k * 2048, 8192, 1024);
-                    if (NSPLIT == 3) {
-                        const uint64_t da_lo = make_smem_desc(a_hi + Cfg::A_BYTES + k * 2048, 8192, 1024);
-                        const uint64_t db_lo = make_smem_desc(b_hi + Cfg::B_BYTES + k * 2048, 8192, 1024);
-                        umma_bf16(tmem_base + (kb % Cfg::NMAIN) * N_TILE, da, db, idesc, (kb >= Cfg::NMAIN || k != 0) ? 1u : 0u);
-                        umma_bf16(tmem_base + Cfg::NMAIN * N_TILE, da, db_lo, idesc, (kb | k) != 0 ? 1u : 0u);
-                        umma_bf16(tmem_base + Cfg::NMAIN * N_TILE, da_lo, db, idesc, 1u);
-                    } else {
-                        umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {  // 16 pixels (= 16 rows of 128 B = 2048 B) per MMA
+                        if (NSPLIT == 3) {
+                            umma_bf16(tmem_base + main_idx * N_TILE, da + 128 * k, db + 128 * k, idesc,
+                                      (kb >= Cfg::NMAIN || k != 0) ? 1u : 0u);
+                            umma_bf16(tmem_base + Cfg::NMAIN * N_TILE, da + 128 * k, db + (Cfg::B_BYTES >> 4) + 128 * k, idesc,
+                                      (kb | k) != 0 ? 1u : 0u);
+                            umma_bf16(tmem_base + Cfg::NMAIN * N_TILE, da + (Cfg::A_BYTES >> 4) + 128 * k, db + 128 * k, idesc, 1u);
+                        } else {
+                            umma_bf16(tmem_base, da + 128 * k, db + 128 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
+                    umma_commit_u32(empty0 + stage * 8);
                 }
-                umma_commit(&empty_bar[stage]);
+                __syncwarp();
+                if (++main_idx == Cfg::NMAIN) main_idx = 0;
                 if (++stage == STAGES) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
-            umma_commit(done_bar);
+            if (elect_one()) umma_commit(done_bar);
+            __syncwarp();
         }
     } else {
         // epilogue warps 2..9: TMEM lane quadrant = warp % 4; the CTA's single tile is drained by two warpgroups, each
