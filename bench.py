@@ -412,11 +412,11 @@ def roofline_live(main, peaks):
         "peak_source": "bf16_tflops_sustained (fp16 and bf16 tcgen05 rates are equal) of " + peaks["source"] + " (kernel timed inside the long step)",
         "launches_per_step": dom[1][2], "avg_launch_ms": round(dom[1][1] / dom[1][2], 4),
         "algorithmic_gflop_per_launch": round(dom[1][0] / dom[1][2] / 1e9, 2), "share_of_step": round(dom[1][1] / step_ms, 3),
-        "traffic": 224.1e6,
+        "traffic": 222.6e6,
         "traffic_note": "dram read+write of ONE launch of this kernel on the 64x64 256->256 conv (B=64), ncu --set full "
-                        "(profiles/r1_ncu_full_gemm_fwd_final.txt: 135.5 MB read + 88.7 MB written); algorithmic bytes of that "
+                        "(profiles/r1_ncu_full_gemm_fwd_final.txt: 135.7 MB read + 87.0 MB written); algorithmic bytes of that "
                         "launch 269.7e6 (16-bit in + out + weights)",
-        "tensor_pipe_pct_ncu": 49.4,
+        "tensor_pipe_pct_ncu": 70.1,
         "gemm_family": {"achieved": round(tot_fl / (tot_ms * 1e-3) / 1e12, 1), "frac": round(tot_fl / (tot_ms * 1e-3) / 1e12 / peak, 4),
                         "share_of_step": round(tot_ms / step_ms, 3), "launches_per_step": sum(v[2] for v in fam.values()),
                         "algorithmic_gflop_per_step": round(tot_fl / 1e9, 1)},
