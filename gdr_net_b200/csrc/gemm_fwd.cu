@@ -4,20 +4,23 @@
 // path (reference call sites: resnet_backbone.py:69-76 convs, cdpn_rot_head_region.py:82-135,
 // conv_pnp_net.py:76-80 + fc1/fc2/fc_r/fc_t :111-157) and, with flipped weights, every dgrad:
 //
-//   D[M = pixels][N = Cout] = sum_k A[M][K] * W[N][K]          (bf16 operands, fp32 accumulate in TMEM)
+//   D[M = pixels][N = Cout] = sum_k A[M][K] * W[N][K]          (16-bit operands, fp32 accumulate in TMEM)
 //
 //   * A is never materialised: for a conv, each 64-wide k-block is one (tap, channel-chunk) and its
 //     128x64 A tile is ONE 4-D TMA box {64 ch, Wo, TH, TN} of the NHWC activation tensor at the
 //     tap-shifted coordinate; out-of-image rows/cols are zero-filled by TMA (= conv padding).
-//     Stride-2 convs read from four phase sub-lattices (one tensor map per (row, col) parity).
-//   * W is a K-major [Cout][KH*KW*Cin] bf16 matrix (prepared by pack kernels), 2-D TMA boxes.
+//     Stride-2 convs read from four phase sub-lattices (one tensor map per (row, col) parity);
+//     stride-2 DGRADS run as four output-parity phases over the un-dilated dY (gdrn_conv_dgrad_s2).
+//   * W is a K-major [Cout][KH*KW*Cin] 16-bit matrix (prepared by pack kernels), 2-D TMA boxes.
 //   * Both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes.
-//   * warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
-//     warps 4-7 = epilogue (tcgen05.ld -> bias/activation -> bf16 hi[/lo] or fp32 stores, per-channel
-//     sum / sum-of-squares for BatchNorm batch statistics).  Accumulators are double-buffered in
-//     TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
-//   * NSPLIT = 3 is the fp32-faithful mode: operands are (hi, lo) bf16 planes and each k-step issues
-//     hi*hi + hi*lo + lo*hi (the lo*lo term, 2^-18 relative, is dropped).
+//   * warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-11 = two epilogue
+//     warpgroups (tcgen05.ld -> bias/activation -> 16-bit hi[/lo] or fp32 stores, per-channel sum /
+//     sum-of-squares for BatchNorm batch statistics).  Accumulators are double-buffered in TMEM and
+//     each warpgroup drains one buffer, so two tile epilogues overlap the MMAs of the next tiles.
+//     Producer and issuer loops run warp-uniformly (operands in uniform registers), one elected lane
+//     issues the asynchronous instructions: ~33 instructions per k-block.
+//   * NSPLIT = 3 is the fp32-faithful mode: operands are (hi, lo) 16-bit planes and each k-step issues
+//     hi*hi + hi*lo + lo*hi (the lo*lo term, 2^-22 relative with fp16 planes, is dropped).
 #include <stdlib.h>
 
 #include "gdrn_internal.h"

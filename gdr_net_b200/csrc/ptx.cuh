@@ -191,17 +191,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     d |= (uint64_t)2 << 61;
     return d;
 }
-// Instruction descriptor, kind::f16: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10),
-// a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-// same with explicit operand formats (0 = F16, 1 = BF16): the cross terms multiply a bf16 hi plane by an fp16 lo plane
-__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major, int a_fmt, int b_fmt) {
-    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn_major << 15) |
-           ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
+// The instruction descriptor (make_idesc) follows the storage-format section below: its operand format bits depend on it.
 
 // ---------------------------------------------------------------- 16-bit storage format of the (hi, lo) planes
 // GDRN_STORE_F16 = 0: hi = bf16(x),  lo = bf16(x - hi)               (8 + 8 bits; fp32 exponent range)
@@ -260,6 +250,9 @@ __device__ __forceinline__ void split1(float x, uint16_t& h, uint16_t& l) {
     h = (uint16_t)(hh & 0xffffu);
     l = (uint16_t)(ll & 0xffffu);
 }
+// Instruction descriptor, kind::f16 (PTX ISA "instruction descriptor" table): c_format F32 (1 << 4), a / b operand format at
+// bits 7 / 10 (0 = F16, 1 = BF16; both planes share kOperandFmt), a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major),
+// N >> 3 at [17,23), M >> 4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | ((uint32_t)kOperandFmt << 7) | ((uint32_t)kOperandFmt << 10) | ((uint32_t)a_mn_major << 15) |
            ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
