@@ -273,7 +273,7 @@ def run_ours(args):
 
         n_e2e = max(3, args.steps // 2)
         cur = upload()
-        n_w = max(2, args.warmup // 2)
+        n_w = max(3, args.warmup // 2)  # >= 3 untimed steps (the first one also captures the forward / backward graphs)
         for i in range(n_w):
             cur = e2e_step(cur, i)
         drain(n_w - 1)
