@@ -311,7 +311,8 @@ def test_bn_bwd_relu_mask_from_u(planes, C_):
         outs.append((DU.float(), dgamma, dbeta))
     # elements with 0 < bn(u) < 3e-8 round to y == 0 in the 16-bit activation: their mask (hence du) may differ
     assert int(((outs[0][0] - outs[1][0]).abs() > 1e-4).sum()) <= 4
-    assert _rel(outs[1][1], outs[0][1]) < 1e-3 and _rel(outs[1][2], outs[0][2]) < 1e-3
+    # (a single flipped element moves one channel's dgamma / dbeta by |g| ~ 1-4 out of ~100)
+    assert _rel(outs[1][1], outs[0][1]) < 5e-2 and _rel(outs[1][2], outs[0][2]) < 5e-2
 
 
 @pytest.mark.parametrize("planes", [1, 2])
