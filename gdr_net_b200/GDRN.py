@@ -184,8 +184,8 @@ def _check_supported(cfg):
         problems.append("losses other than xyz L1 / mask L1 / region CE over 64 regions")
     if r.XYZ_LOSS_MASK_GT != "visib" or r.MASK_LOSS_GT != "trunc" or r.REGION_LOSS_MASK_GT != "visib":
         problems.append("mask selection other than visib/trunc/visib")
-    if not (p.WITH_2D_COORD and p.REGION_ATTENTION) or p.MASK_ATTENTION != "none" or p.R_ONLY:
-        problems.append("Patch-PnP input other than xyz + 2D coords + region attention")
+    if not p.REGION_ATTENTION or p.MASK_ATTENTION != "none" or p.R_ONLY:
+        problems.append("Patch-PnP input other than xyz (+ 2D coords) + region attention")
     if p.ROT_TYPE != "allo_rot6d" or p.TRANS_TYPE != "centroid_z" or p.Z_TYPE != "REL":
         problems.append("pose parametrisation other than allo_rot6d + centroid_z(REL)")
     if not (p.PM_R_ONLY and p.PM_NORM_BY_EXTENT) or p.PM_LOSS_TYPE != "L1" or p.PM_LW <= 0:
@@ -199,7 +199,7 @@ def _check_supported(cfg):
 
 
 class GDRN(nn.Module):
-    def __init__(self, cfg, backbone, rot_head_net, trans_head_net=None, pnp_net=None, precision: str = "half"):
+    def __init__(self, cfg, backbone, rot_head_net, trans_head_net=None, pnp_net=None, precision: str = "mixed"):
         super().__init__()
         assert cfg.MODEL.CDPN.NAME == "GDRN", cfg.MODEL.CDPN.NAME
         _check_supported(cfg)
@@ -213,7 +213,9 @@ class GDRN(nn.Module):
         self._engine: Optional[Engine] = None
         self._vis_dev, self._vis_host = None, None
         self.use_cuda_graphs = False  # set True for fixed-shape training loops: forward/backward replay CUDA graphs
-        self.precision = {"bf16": "half", "fp16": "half"}.get(precision, precision)  # "half" (1 pass) | "fp32x3" (hi/lo planes)
+        # "mixed" (default): fp32-faithful 3-pass forward (1e-3 parity on every output / loss) + single-pass fp16 backward;
+        # "fp32x3": 3-pass forward and backward; "half": single-pass everywhere (throughput mode, TF32-class arithmetic)
+        self.precision = {"bf16": "half", "fp16": "half"}.get(precision, precision)
 
     @property
     def last_vis_dict(self) -> dict:
@@ -292,7 +294,36 @@ def _get_event_storage():
         return None
 
 
-def build_model_optimizer(cfg, precision: str = "half"):
+def _load_backbone_pretrained(backbone, spec: str):
+    """reference GDRN.py:713-721: `load_checkpoint(model.backbone, PRETRAINED, strict=False)` (mmcv).  `torchvision://name`
+    resolves through torchvision's model-zoo table (torch hub cache, downloads if absent); anything else is a checkpoint
+    file whose tensors may sit under `state_dict` / `model`.  Fails loudly: a reference config must never silently train a
+    randomly initialised backbone."""
+    if spec.startswith("torchvision://"):
+        name = spec[len("torchvision://"):]
+        try:
+            import torchvision
+
+            weights = torchvision.models.get_model_weights(name).DEFAULT
+            sd = weights.get_state_dict(progress=False)
+        except Exception as e:
+            raise RuntimeError(
+                f"cfg.MODEL.CDPN.BACKBONE.PRETRAINED={spec!r}: could not obtain the torchvision weights ({type(e).__name__}: {e}). "
+                "Put the checkpoint in the torch hub cache, point PRETRAINED at a local file, or set it to '' explicitly.") from e
+    else:
+        sd = torch.load(spec, map_location="cpu")
+        for k in ("state_dict", "model"):
+            if isinstance(sd, dict) and k in sd and isinstance(sd[k], dict):
+                sd = sd[k]
+        sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in sd.items()}
+        if any(k.startswith("backbone.") for k in sd):
+            sd = {k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}
+    missing, unexpected = backbone.load_state_dict(sd, strict=False)
+    logger.info(f"backbone weights from {spec}: {len(missing)} missing, {len(unexpected)} unexpected keys (strict=False)")
+    return missing, unexpected
+
+
+def build_model_optimizer(cfg, precision: str = "mixed"):
     """reference GDRN.py:550-724"""
     backbone_cfg = cfg.MODEL.CDPN.BACKBONE
     r_head_cfg = cfg.MODEL.CDPN.ROT_HEAD
@@ -331,7 +362,12 @@ def build_model_optimizer(cfg, precision: str = "half"):
     from .solver import build_optimizer_with_params
 
     optimizer = build_optimizer_with_params(cfg, params_lr_list)
-    if cfg.MODEL.WEIGHTS == "" and cfg.MODEL.CDPN.BACKBONE.get("PRETRAINED", "") == "":
-        logger.warning("Randomly initialize weights for backbone!")
+    if cfg.MODEL.WEIGHTS == "":
+        backbone_pretrained = cfg.MODEL.CDPN.BACKBONE.get("PRETRAINED", "")
+        if backbone_pretrained == "":
+            logger.warning("Randomly initialize weights for backbone!")
+        else:
+            logger.info(f"load backbone weights from: {backbone_pretrained}")
+            _load_backbone_pretrained(model.backbone, backbone_pretrained)
     model.to(torch.device(cfg.MODEL.DEVICE))
     return model, optimizer

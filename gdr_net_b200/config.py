@@ -136,7 +136,7 @@ def postprocess_like_main_gdrn(cfg: ConfigDict, device: str = "cuda") -> ConfigD
 
 
 def a6_config(num_regions: int = 64, pm_loss_sym: bool = False, device: str = "cuda", use_pnp_test: bool = False,
-              optimizer: dict | None = None) -> Config:
+              optimizer: dict | None = None, with_2d_coord: bool = True) -> Config:
     """The `a6_cPnP` network/loss configuration (keys the hot path reads)."""
     cfg = Config(
         MODEL=dict(
@@ -159,7 +159,7 @@ def a6_config(num_regions: int = 64, pm_loss_sym: bool = False, device: str = "c
                 PNP_NET=dict(
                     FREEZE=False, R_ONLY=False, LR_MULT=1.0,
                     PNP_HEAD_CFG=dict(type="ConvPnPNet", norm="GN", num_gn_groups=32, drop_prob=0.0),
-                    WITH_2D_COORD=True, REGION_ATTENTION=True, MASK_ATTENTION="none", TRANS_WITH_BOX_INFO="none",
+                    WITH_2D_COORD=with_2d_coord, REGION_ATTENTION=True, MASK_ATTENTION="none", TRANS_WITH_BOX_INFO="none",
                     ROT_TYPE="allo_rot6d", TRANS_TYPE="centroid_z", Z_TYPE="REL",
                     NUM_PM_POINTS=3000, PM_LOSS_TYPE="L1", PM_SMOOTH_L1_BETA=1.0, PM_LOSS_SYM=pm_loss_sym,
                     PM_NORM_BY_EXTENT=True, PM_R_ONLY=True, PM_DISENTANGLE_T=False, PM_DISENTANGLE_Z=False,

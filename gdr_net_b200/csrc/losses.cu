@@ -46,6 +46,9 @@ __device__ __forceinline__ void load_logits(const float* __restrict__ logits, lo
 }
 
 // ------------------------------------------------------------------------------------------------
+// W2D: the Patch-PnP input carries the 2-D crop coordinates (cfg PNP_NET.WITH_2D_COORD: 3 + 2 + 64 = 69 channels, region at
+// 5..68) or not (3 + 64 = 67 channels, region at 3..66) -- GDRN.py:171-173, :635-647
+template <bool W2D>
 __global__ void __launch_bounds__(128) head_glue_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ coord2d,
                                                             const float* __restrict__ extents, bf16* __restrict__ out_hi,
                                                             bf16* __restrict__ out_lo, int B, int HW) {
@@ -58,21 +61,25 @@ __global__ void __launch_bounds__(128) head_glue_fwd_kernel(const float* __restr
         float o[72];
 #pragma unroll
         for (int j = 0; j < 3; ++j) o[j] = (z[1 + j] - 0.5f) * __ldg(extents + b * 3 + j);
-        o[3] = __ldg(coord2d + ((long)b * 2 + 0) * HW + hw);
-        o[4] = __ldg(coord2d + ((long)b * 2 + 1) * HW + hw);
+        constexpr int RO = W2D ? 5 : 3;  // first region channel
+        if (W2D) {
+            o[3] = __ldg(coord2d + ((long)b * 2 + 0) * HW + hw);
+            o[4] = __ldg(coord2d + ((long)b * 2 + 1) * HW + hw);
+        }
         float m = -INFINITY;
 #pragma unroll
         for (int k = 0; k < kNumReg; ++k) m = fmaxf(m, z[5 + k]);
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < kNumReg; ++k) {
-            o[5 + k] = expf(z[5 + k] - m);
-            s += o[5 + k];
+            o[RO + k] = expf(z[5 + k] - m);
+            s += o[RO + k];
         }
         const float inv = 1.f / s;
 #pragma unroll
-        for (int k = 0; k < kNumReg; ++k) o[5 + k] *= inv;
-        o[69] = o[70] = o[71] = 0.f;
+        for (int k = 0; k < kNumReg; ++k) o[RO + k] *= inv;
+#pragma unroll
+        for (int k = RO + kNumReg; k < 72; ++k) o[k] = 0.f;
         store_row_bf16(out_hi, out_lo, pix, kPnpLd, o, 72);
         // zero the padding channels 72..127
         const uint4 zz = make_uint4(0, 0, 0, 0);
@@ -129,6 +136,7 @@ __global__ void __launch_bounds__(128) pixel_loss_fwd_kernel(const float* __rest
 
 // d_logits (bf16 hi/lo, [P][128], cols >= 69 zero) = d(pixel losses) + glue backward of d_pnp_in
 // gw[5]: upstream gradients of loss_coor_x, _y, _z, loss_mask, loss_region
+template <bool W2D>
 __global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ gt_xyz,
                                                        const float* __restrict__ m_visib, const float* __restrict__ m_trunc,
                                                        const long long* __restrict__ labels, const double* __restrict__ sums,
@@ -204,6 +212,7 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__
         }
         // softmax64 backward of the Patch-PnP region-attention input: dz_k = p_k (g_k - sum_j g_j p_j)
         if (din_hi != nullptr) {
+            constexpr int RO = W2D ? 5 : 3;  // first region channel of the Patch-PnP input
             float mx = -INFINITY;
 #pragma unroll
             for (int k = 0; k < kNumReg; ++k) mx = fmaxf(mx, z[5 + k]);
@@ -218,10 +227,10 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__
 #pragma unroll
             for (int k = 0; k < kNumReg; ++k) {
                 pk[k] *= inv;
-                dot = fmaf(gin[5 + k], pk[k], dot);
+                dot = fmaf(gin[RO + k], pk[k], dot);
             }
 #pragma unroll
-            for (int k = 0; k < kNumReg; ++k) d[5 + k] += pk[k] * (gin[5 + k] - dot);
+            for (int k = 0; k < kNumReg; ++k) d[5 + k] += pk[k] * (gin[RO + k] - dot);
         }
         d[69] = d[70] = d[71] = 0.f;
         store_row_bf16(out_hi, out_lo, pix, kPnpLd, d, 72);
@@ -348,8 +357,8 @@ struct PoseParams {
     const float* gt_rot;    // [B][3][3]
     const float* gt_trans;  // [B][3]
     const float* gt_ratio;  // [B][3]  (trans_ratio)
-    const float* syms;      // [sum K][3][3] or null
-    const int* sym_off;     // [B+1] offsets into syms or null
+    const float* syms;      // device-resident symmetry table [rows][3][3] or null
+    const int* sym_idx;     // [B][2] (first row, count) into syms, count 0 = no symmetry; null with syms
     const float* gw;        // [3]: upstream grads of loss_PM_R, loss_centroid, loss_z
     float* out_rot;         // [B][3][3]
     float* out_trans;       // [B][3]
@@ -449,41 +458,80 @@ __global__ void __launch_bounds__(128) pose_loss_kernel(const PoseParams p) {
                 }
                 p.vis[b * 2 + 1] = (float)sqrt(te);
             }
-            if (p.syms != nullptr) {
-                const int k0 = p.sym_off[b], k1 = p.sym_off[b + 1];
-                double best;
-                {
-                    double tr = 0;
-                    for (int i = 0; i < 9; ++i) tr += (double)sR[i] * Rg[i];
-                    if (tr > 3) tr = 3;
-                    double c = 0.5 * (tr - 1.0);
-                    best = acos(c > 1 ? 1 : (c < -1 ? -1 : c));
-                }
-                float bestR[9];
-                for (int i = 0; i < 9; ++i) bestR[i] = Rg[i];
-                for (int k = k0; k < k1; ++k) {
-                    const float* S = p.syms + (long)k * 9;
-                    float cand[9];
-                    for (int i = 0; i < 3; ++i)
-                        for (int j = 0; j < 3; ++j)
-                            cand[i * 3 + j] = Rg[i * 3 + 0] * S[0 * 3 + j] + Rg[i * 3 + 1] * S[1 * 3 + j] + Rg[i * 3 + 2] * S[2 * 3 + j];
-                    double tr = 0;
-                    for (int i = 0; i < 9; ++i) tr += (double)sR[i] * cand[i];
-                    if (tr > 3) tr = 3;
-                    double c = 0.5 * (tr - 1.0);
-                    const double e = acos(c > 1 ? 1 : (c < -1 ? -1 : c));
-                    if (e < best) {
-                        best = e;
-                        for (int i = 0; i < 9; ++i) bestR[i] = cand[i];
-                    }
-                }
-                for (int i = 0; i < 9; ++i) Rg[i] = bestR[i];
-            }
             for (int i = 0; i < 9; ++i) sRgt[i] = Rg[i];
         }
     }
     __syncthreads();
     if (!p.do_loss) return;
+
+    // closest symmetric ground truth (pose_utils.py:430-454: the FIRST candidate with the strictly smallest geodesic error,
+    // the unmodified R_gt first), detached.  The K candidates (up to several hundred for discretised continuous
+    // symmetries) are scanned by the whole CTA: trace(R^T R_gt S_k) = <M, S_k> with M = R_gt^T R, one acos per candidate,
+    // then a lexicographic (error, index) minimum over the block.  The table `syms` is device-resident and shared by all
+    // steps; `sym_idx[b] = (first row, count)` selects this crop's object (count 0 = asymmetric).
+    if (p.syms != nullptr && p.sym_idx[2 * b + 1] > 0) {
+        __shared__ double s_be[4];
+        __shared__ int s_bk[4];
+        const int k0 = p.sym_idx[2 * b], K = p.sym_idx[2 * b + 1];
+        float M[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) M[i * 3 + j] = sRgt[0 * 3 + i] * sR[0 * 3 + j] + sRgt[1 * 3 + i] * sR[1 * 3 + j] + sRgt[2 * 3 + i] * sR[2 * 3 + j];
+        double best;
+        {
+            double tr = (double)M[0] + (double)M[4] + (double)M[8];
+            if (tr > 3) tr = 3;
+            const double c = 0.5 * (tr - 1.0);
+            best = acos(c > 1 ? 1 : (c < -1 ? -1 : c));
+        }
+        int bk = -1;
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            const float* S = p.syms + (long)(k0 + k) * 9;
+            // the reference forms cand = R_gt S_k in fp32/fp64 and takes trace(R cand^T); <M, S_k> is the same sum re-associated
+            double tr = 0;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) tr += (double)M[i] * (double)__ldg(S + i);
+            if (tr > 3) tr = 3;
+            const double c = 0.5 * (tr - 1.0);
+            const double e = acos(c > 1 ? 1 : (c < -1 ? -1 : c));
+            if (e < best) {  // ascending k per thread: the first strict minimum is kept
+                best = e;
+                bk = k;
+            }
+        }
+        // lexicographic min over (error, index); index -1 (the original R_gt) wins ties like the sequential scan
+        for (int o = 16; o > 0; o >>= 1) {
+            const double oe = __shfl_xor_sync(0xffffffffu, best, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            if (oe < best || (oe == best && ok < bk)) {
+                best = oe;
+                bk = ok;
+            }
+        }
+        if ((threadIdx.x & 31) == 0) {
+            s_be[threadIdx.x >> 5] = best;
+            s_bk[threadIdx.x >> 5] = bk;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int wv = 1; wv < 4; ++wv)
+                if (s_be[wv] < best || (s_be[wv] == best && s_bk[wv] < bk)) {
+                    best = s_be[wv];
+                    bk = s_bk[wv];
+                }
+            if (bk >= 0) {
+                const float* S = p.syms + (long)(k0 + bk) * 9;
+                float Rg[9], cand[9];
+                for (int i = 0; i < 9; ++i) Rg[i] = sRgt[i];
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j)
+                        cand[i * 3 + j] = Rg[i * 3 + 0] * S[0 * 3 + j] + Rg[i * 3 + 1] * S[1 * 3 + j] + Rg[i * 3 + 2] * S[2 * 3 + j];
+                for (int i = 0; i < 9; ++i) sRgt[i] = cand[i];
+            }
+        }
+        __syncthreads();
+    }
 
     // point-matching loss (r_only, L1, normalised by max extent): sum |w (R p - Rgt p)|, and dL/dR = w sign(e) p^T
     const float w = 1.f / fmaxf(fmaxf(p.extents[b * 3], p.extents[b * 3 + 1]), p.extents[b * 3 + 2]);
@@ -588,9 +636,13 @@ static inline int px_grid(long total) {
 }
 
 extern "C" int gdrn_head_glue_fwd(const float* logits, const float* coord2d, const float* extents, void* out_hi, void* out_lo,
-                                  int B, int HW, void* stream_) {
+                                  int B, int HW, int with_2d, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    head_glue_fwd_kernel<<<px_grid((long)B * HW), 128, 0, stream>>>(logits, coord2d, extents, (bf16*)out_hi, (bf16*)out_lo, B, HW);
+    if (with_2d && coord2d == nullptr) return set_error(GDRN_ERR_ARG, "head_glue_fwd: with_2d needs coord2d");
+    if (with_2d)
+        head_glue_fwd_kernel<true><<<px_grid((long)B * HW), 128, 0, stream>>>(logits, coord2d, extents, (bf16*)out_hi, (bf16*)out_lo, B, HW);
+    else
+        head_glue_fwd_kernel<false><<<px_grid((long)B * HW), 128, 0, stream>>>(logits, coord2d, extents, (bf16*)out_hi, (bf16*)out_lo, B, HW);
     GDRN_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;
@@ -609,11 +661,16 @@ extern "C" int gdrn_pixel_loss_fwd(const float* logits, const float* gt_xyz, con
 extern "C" int gdrn_head_bwd(const float* logits, const float* gt_xyz, const float* m_visib, const float* m_trunc,
                              const long long* labels, const double* sums, const float* gw, const void* din_hi,
                              const void* din_lo, const float* extents, void* out_hi, void* out_lo, int B, int HW,
-                             void* stream_) {
+                             int with_2d, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    head_bwd_kernel<<<px_grid((long)B * HW), 128, 0, stream>>>(logits, gt_xyz, m_visib, m_trunc, labels, sums, gw,
-                                                              (const bf16*)din_hi, (const bf16*)din_lo, extents, (bf16*)out_hi,
-                                                              (bf16*)out_lo, B, HW);
+    if (with_2d)
+        head_bwd_kernel<true><<<px_grid((long)B * HW), 128, 0, stream>>>(logits, gt_xyz, m_visib, m_trunc, labels, sums, gw,
+                                                                        (const bf16*)din_hi, (const bf16*)din_lo, extents,
+                                                                        (bf16*)out_hi, (bf16*)out_lo, B, HW);
+    else
+        head_bwd_kernel<false><<<px_grid((long)B * HW), 128, 0, stream>>>(logits, gt_xyz, m_visib, m_trunc, labels, sums, gw,
+                                                                         (const bf16*)din_hi, (const bf16*)din_lo, extents,
+                                                                         (bf16*)out_hi, (bf16*)out_lo, B, HW);
     GDRN_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;
@@ -621,7 +678,7 @@ extern "C" int gdrn_head_bwd(const float* logits, const float* gt_xyz, const flo
 
 extern "C" int gdrn_pose_loss(const float* pred, int ld_pred, const float* cams, const float* centers, const float* whs,
                               const float* ratios, const float* extents, const float* points, const float* gt_rot,
-                              const float* gt_trans, const float* gt_ratio, const float* syms, const int* sym_off,
+                              const float* gt_trans, const float* gt_ratio, const float* syms, const int* sym_idx,
                               const float* gw, float* out_rot, float* out_trans, double* sums, float* vis, void* dy_hi,
                               void* dy_lo, int B, int n_pts, int do_loss, float eps, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -639,7 +696,7 @@ extern "C" int gdrn_pose_loss(const float* pred, int ld_pred, const float* cams,
     p.gt_trans = gt_trans;
     p.gt_ratio = gt_ratio;
     p.syms = syms;
-    p.sym_off = sym_off;
+    p.sym_idx = sym_idx;
     p.gw = gw;
     p.out_rot = out_rot;
     p.out_trans = out_trans;

@@ -66,12 +66,15 @@ class GradAllReducer:
         lo, hi = self.bounds[seg]
         chunk = self.flat[lo:hi]
         self.bytes_reduced += chunk.numel() * chunk.element_size()
-        if self.stream is not None:
-            self.stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(self.stream):
-                chunk.div_(self.world)
-                w = dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
-        else:
+        if self.cuda:
+            # NCCL averages inside the collective (ReduceOp.AVG): no separate scaling launch per bucket
+            if self.stream is not None:
+                self.stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self.stream):
+                    w = dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.pg, async_op=True)
+            else:
+                w = dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.pg, async_op=True)
+        else:  # gloo (CPU tests) has no AVG
             chunk.div_(self.world)
             w = dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
         self.pending.append(w)

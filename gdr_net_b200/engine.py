@@ -6,7 +6,11 @@ used for device memory, streams and the autograd/DDP boundary only.
 
 precision = "half"   : activations / gradients are 16-bit NHWC tensors (fp16 by default, bf16 if the library is built with
                        GDRN_STORE_F16=0), one tcgen05 pass per k-step.  "fp16" / "bf16" are accepted as aliases.
-precision = "fp32x3" : (hi, lo) 16-bit planes (22-bit operands with fp16), three tcgen05 passes: the 1e-3 parity mode
+precision = "fp32x3" : (hi, lo) 16-bit planes (22-bit operands with fp16), three tcgen05 passes in forward AND backward
+precision = "mixed"  : the fp32x3 forward (every output / loss inside the 1e-3 parity bound, identical ReLU / max-pool / L1
+                       decisions) with the single-plane backward of "half": the backward is linear given the forward's
+                       masks, so 11-bit operands there cost ~1e-3 on the gradients (what cuDNN's TF32 backward gives the
+                       reference) instead of flipping decisions.  Saved activations are read through their hi plane.
 """
 from __future__ import annotations
 
@@ -43,18 +47,72 @@ class _BN:
         self.stats = None  # view into Engine.stats_all
 
 
+class SymTable:
+    """Device-resident table of symmetry rotations (reference `sym_infos`: per-object [K,3,3] model-to-model transforms,
+    core/utils/pose_utils.py:457-482, built per dataset by misc.get_symmetry_transformations).  Each distinct object is
+    uploaded ONCE; a step only sends B (first row, count) pairs, so the symmetric PM loss needs no per-step packing of
+    the matrices, no host loop over candidates and is CUDA-graph capturable (fixed table address, fixed capacity)."""
+
+    CAPACITY = 16384  # rows (YCB-V: 21 objects x <= 628 discretised transforms fits several times over)
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.table = torch.zeros(self.CAPACITY, 3, 3, device=dev)
+        self.rows = 0
+        self._by_id = {}     # id(obj) -> (obj, first, count): fast path for the per-dataset arrays reused every step
+        self._by_bytes = {}  # content -> (first, count)
+
+    def _register(self, s):
+        import numpy as np
+
+        arr = s.detach().cpu().numpy() if isinstance(s, torch.Tensor) else np.asarray(s)
+        arr = np.ascontiguousarray(arr, dtype=np.float32).reshape(-1, 3, 3)
+        key = arr.tobytes()
+        ent = self._by_bytes.get(key)
+        if ent is None:
+            k = arr.shape[0]
+            if self.rows + k > self.CAPACITY:
+                raise RuntimeError(f"symmetry table full ({self.rows} + {k} > {self.CAPACITY} rows)")
+            self.table[self.rows:self.rows + k].copy_(torch.from_numpy(arr))
+            ent = (self.rows, k)
+            self.rows += k
+            self._by_bytes[key] = ent
+        return ent
+
+    def indices(self, sym_infos) -> torch.Tensor:
+        """list[B] of None | [K,3,3] -> int32 [B,2] (first row, count) on the device (one small async H2D copy)."""
+        out = torch.zeros(len(sym_infos), 2, dtype=torch.int32).pin_memory()
+        for b, s in enumerate(sym_infos):
+            if s is None:
+                continue
+            hit = self._by_id.get(id(s))
+            if hit is None or hit[0] is not s:
+                first, count = self._register(s)
+                if len(self._by_id) > 4096:
+                    self._by_id.clear()
+                self._by_id[id(s)] = (s, first, count)
+            else:
+                first, count = hit[1], hit[2]
+            out[b, 0], out[b, 1] = first, count
+        return out.to(self.dev, non_blocking=True)
+
+
 class Engine:
     def __init__(self, model, precision: str = "half"):
         precision = {"bf16": "half", "fp16": "half"}.get(precision, precision)
-        assert precision in ("half", "fp32x3"), precision
+        assert precision in ("half", "fp32x3", "mixed"), precision
         C.load()  # fail loudly if the CUDA library is missing
         self.model = model
         self.precision = precision
-        self.planes = 1 if precision == "half" else 2
+        self.planes = 1 if precision == "half" else 2      # forward activations / forward weight operands
+        self.bplanes = 2 if precision == "fp32x3" else 1   # activation gradients / dgrad weight operands
         self.dev = next(model.parameters()).device
         if self.dev.type != "cuda":
             raise RuntimeError("gdr_net_b200 engine needs CUDA parameters (model.to('cuda')); no CPU fallback exists")
         self.ws = ops.Workspace(self.dev)
+        self.sym_table = SymTable(self.dev)
+        self.with_2d = int(model.pnp_net.features[0].in_channels == 69)  # 69 = xyz + coord2d + regions, 67 without coords
+        assert model.pnp_net.features[0].in_channels in (67, 69), model.pnp_net.features[0].in_channels
         self.named_params = list(model.named_parameters())
         self.bn: Dict[str, _BN] = {}
         total = 0
@@ -117,7 +175,12 @@ class Engine:
         import numpy as np
 
         key = (need_dgrad, tuple(p.data_ptr() for _, p in self.named_params))
-        if getattr(self, "_pack_key", None) != key:
+        tables = self.__dict__.setdefault("_pack_tables", {})
+        tab = tables.get(key)
+        if tab is None:
+            # One persistent job table per (need_dgrad, parameter addresses).  Tables are NEVER freed or overwritten: a
+            # captured CUDA graph holds the raw device pointer of the table it was captured with, and an eager call with
+            # the other need_dgrad value (train -> eval -> train) must not invalidate it.
             ops._pack_recorder = []
             try:
                 self._prepare_weights_calls(need_dgrad)
@@ -134,28 +197,27 @@ class Engine:
             for n, (src, out, O, I, KH, KW, opad, ipad, krow, so, si, sr, ss, flip) in enumerate(jobs):
                 arr[n] = (src.data_ptr(), out.hi_ptr, out.lo_ptr or 0, so, si, sr, ss, begin, O, I, KH, KW, opad, ipad, krow, flip)
                 begin += -(-opad // 16) * -(-ipad // 64) * -(-(KH * KW) // 9)  # tiles of 16 rows x 64 channels x 9 taps (pack.cu)
-            self._pack_jobs = torch.from_numpy(arr.view(np.uint8).copy()).to(self.dev)
-            self._pack_njobs, self._pack_blocks = len(jobs), begin
-            self._pack_srcs = [j[0] for j in jobs]  # keep the sources alive
-            self._pack_key = key
+            tab = dict(jobs=torch.from_numpy(arr.view(np.uint8).copy()).to(self.dev), njobs=len(jobs), blocks=begin,
+                       keep=[j[0] for j in jobs] + [j[1] for j in jobs])  # sources and destinations stay alive with the table
+            tables[key] = tab
         with torch.no_grad():
             torch.cat([self.model.pnp_net.fc_r.weight, self.model.pnp_net.fc_t.weight], 0, out=self.w_rt)
             torch.cat([self.model.pnp_net.fc_r.bias, self.model.pnp_net.fc_t.bias], 0, out=self.b_rt)
-        C.gdrn_pack_weight_batched(self._pack_jobs.data_ptr(), self._pack_njobs, self._pack_blocks, _stream())
+        C.gdrn_pack_weight_batched(tab["jobs"].data_ptr(), tab["njobs"], tab["blocks"], _stream())
 
     def _prepare_weights_calls(self, need_dgrad: bool):
-        m, pl = self.model, self.planes
+        m, pl, bpl = self.model, self.planes, self.bplanes
         wf, wd = self.wf, self.wd
         for key, conv in self._conv_modules():
             if key == "backbone.conv1":
                 continue  # the 7x7 stem is a GEMM over its im2col matrix (_pack_stem)
             wf[key] = ops.pack_conv_fwd(conv.weight, pl, out=wf.get(key))
             if need_dgrad:
-                wd[key] = ops.pack_conv_dgrad(conv.weight, pl, out=wd.get(key))
+                wd[key] = ops.pack_conv_dgrad(conv.weight, bpl, out=wd.get(key))
         dc = m.rot_head_net.features[0]
         wf["deconv"] = ops.pack_deconv_fwd(dc.weight, pl, out=wf.get("deconv"))
         if need_dgrad:
-            wd["deconv"] = ops.pack_deconv_dgrad(dc.weight, pl, out=wd.get("deconv"))
+            wd["deconv"] = ops.pack_deconv_dgrad(dc.weight, bpl, out=wd.get("deconv"))
         pn = m.pnp_net
         wf["fc1"] = ops.pack_linear(pn.fc1.weight, pl, out=wf.get("fc1"), nhwc_from=(128, 8, 8))
         wf["fc2"] = ops.pack_linear(pn.fc2.weight, pl, out=wf.get("fc2"))
@@ -164,9 +226,9 @@ class Engine:
             self.b_rt = torch.empty(pn.fc_r.out_features + 3, device=self.dev)
         wf["fc_rt"] = ops.pack_linear(self.w_rt, pl, out=wf.get("fc_rt"))
         if need_dgrad:
-            wd["fc1"] = ops.pack_linear(pn.fc1.weight, pl, out=wd.get("fc1"), nhwc_from=(128, 8, 8), transpose=True)
-            wd["fc2"] = ops.pack_linear(pn.fc2.weight, pl, out=wd.get("fc2"), transpose=True)
-            wd["fc_rt"] = ops.pack_linear(self.w_rt, pl, out=wd.get("fc_rt"), transpose=True)
+            wd["fc1"] = ops.pack_linear(pn.fc1.weight, bpl, out=wd.get("fc1"), nhwc_from=(128, 8, 8), transpose=True)
+            wd["fc2"] = ops.pack_linear(pn.fc2.weight, bpl, out=wd.get("fc2"), transpose=True)
+            wd["fc_rt"] = ops.pack_linear(self.w_rt, bpl, out=wd.get("fc_rt"), transpose=True)
 
     def _pack_stem(self):
         """7x7 stem weight [64][3][7][7] -> [64][192] with k = (r*7+s)*3 + c (matches gdrn_stem_im2col)."""
@@ -210,12 +272,32 @@ class Engine:
                    roi_extents=roi_extents, resize_ratios=resize_ratios, gt_xyz=gt_xyz, gt_mask_trunc=gt_mask_trunc,
                    gt_mask_visib=gt_mask_visib, gt_region=gt_region, gt_ego_rot=gt_ego_rot, gt_points=gt_points,
                    sym_infos=sym_infos, gt_trans=gt_trans, gt_trans_ratio=gt_trans_ratio)
+        B = x.shape[0]
         for k_, v in aux.items():
             if isinstance(v, torch.Tensor):
                 v = v.to(self.dev)
-                aux[k_] = (v if v.dtype == torch.long else v.float()).contiguous()
-        if roi_cams is not None and aux["roi_cams"].dim() == 2:
-            aux["roi_cams"] = aux["roi_cams"].unsqueeze(0).contiguous()
+                # gt_region is handed to the kernels as `const long long*` (the reference calls .long() itself, GDRN.py:393,
+                # and its dataset emits int32): convert ANY label dtype explicitly; everything else is fp32
+                aux[k_] = (v.long() if k_ == "gt_region" else v.float()).contiguous()
+        if roi_cams is not None and aux["roi_cams"].dim() == 2:  # one shared K: broadcast like the reference does
+            aux["roi_cams"] = aux["roi_cams"].unsqueeze(0).expand(B, 3, 3).contiguous()
+        want = dict(roi_coord_2d=(B, 2, 64, 64), roi_cams=(B, 3, 3), roi_centers=(B, 2), roi_whs=(B, 2), roi_extents=(B, 3),
+                    resize_ratios=(B,), gt_xyz=(B, 3, 64, 64), gt_mask_trunc=(B, 64, 64), gt_mask_visib=(B, 64, 64),
+                    gt_region=(B, 64, 64), gt_ego_rot=(B, 3, 3), gt_trans=(B, 3), gt_trans_ratio=(B, 3))
+        for k_, shp in want.items():
+            v = aux.get(k_)
+            if isinstance(v, torch.Tensor):
+                if v.numel() != int(torch.Size(shp).numel()):
+                    raise ValueError(f"{k_}: expected shape {shp} for a batch of {B}, got {tuple(v.shape)}")
+                aux[k_] = v.view(shp)
+        if isinstance(aux.get("gt_points"), torch.Tensor) and (aux["gt_points"].dim() != 3 or aux["gt_points"].shape[0] != B
+                                                               or aux["gt_points"].shape[2] != 3):
+            raise ValueError(f"gt_points: expected [B={B}, n, 3], got {tuple(aux['gt_points'].shape)}")
+        if aux.get("sym_infos") is not None:
+            if len(aux["sym_infos"]) != B:
+                raise ValueError(f"sym_infos: expected a list of {B} entries, got {len(aux['sym_infos'])}")
+            aux["sym_idx"] = self.sym_table.indices(aux["sym_infos"])  # the matrices themselves are already on the device
+        aux.pop("sym_infos", None)
         x = x.to(self.dev).float().contiguous()
         if not do_loss:
             with torch.no_grad():
@@ -285,8 +367,8 @@ class Engine:
 
         # ---- a3 + a4: glue and Patch-PnP (GDRN.py:156-181, conv_pnp_net.py:111-157)
         pnp_in = PT((B, 64, 64, 128), pl, device=dev)
-        C.gdrn_head_glue_fwd(logits.data_ptr(), aux["roi_coord_2d"].data_ptr(), aux["roi_extents"].data_ptr(), pnp_in.hi_ptr,
-                             pnp_in.lo_ptr, B, 4096, _stream())
+        C.gdrn_head_glue_fwd(logits.data_ptr(), ops.ptr(aux.get("roi_coord_2d")), aux["roi_extents"].data_ptr(), pnp_in.hi_ptr,
+                             pnp_in.lo_ptr, B, 4096, self.with_2d, _stream())
         pf = m.pnp_net.features
         cur = pnp_in
         pnp_saved = []
@@ -333,7 +415,7 @@ class Engine:
         C.gdrn_loss_finalize(pix_sums.data_ptr(), S["pose_sums"].data_ptr(), S["vis_ps"].data_ptr(), losses.data_ptr(),
                              vis2.data_ptr(), B, 4096, n_pts, _stream())
         vis = torch.cat([vis2, out_trans_first(S["out_trans"]), pred[0, 6:9], aux["gt_trans"][0], aux["gt_trans_ratio"][0]])
-        res.update(rot=S["out_rot"], trans=S["out_trans"], losses=losses, vis=vis)
+        res.update(rot=S["out_rot"], trans=S["out_trans"], losses=losses, vis=vis, logits=logits)
         return res
 
     def _pose(self, S, gw):
@@ -343,28 +425,18 @@ class Engine:
             S["out_trans"] = torch.empty(B, 3, device=dev)
             S["pose_sums"] = torch.empty(4, dtype=torch.float64, device=dev)
             S["vis_ps"] = torch.empty(B, 2, device=dev)
-            S["dy9"] = PT((B, 64), self.planes, device=dev)
-            syms, offs = None, None
-            if aux.get("sym_infos") is not None:
-                mats, offs_l = [], [0]
-                for s in aux["sym_infos"]:
-                    if s is not None:
-                        s = torch.as_tensor(s, dtype=torch.float32).reshape(-1, 3, 3)
-                        mats.append(s)
-                        offs_l.append(offs_l[-1] + s.shape[0])
-                    else:
-                        offs_l.append(offs_l[-1])
-                if mats:
-                    syms = torch.cat(mats, 0).to(dev).contiguous()
-                    offs = torch.tensor(offs_l, dtype=torch.int32, device=dev)
-            S["syms"], S["sym_off"] = syms, offs
+            S["dy9"] = PT((B, 64), self.bplanes, device=dev)
+        sym_idx = aux.get("sym_idx")
+        if sym_idx is None and aux.get("sym_infos") is not None:  # direct engine.forward callers may pass the raw list
+            sym_idx = aux["sym_idx"] = self.sym_table.indices(aux["sym_infos"])
+        syms = self.sym_table.table if sym_idx is not None else None
         if gw is None:
             gw = torch.ones(3, device=dev)
         n_pts = aux["gt_points"].shape[1]
         C.gdrn_pose_loss(S["pred"].data_ptr(), 16, aux["roi_cams"].data_ptr(), aux["roi_centers"].data_ptr(),
                          aux["roi_whs"].data_ptr(), aux["resize_ratios"].data_ptr(), aux["roi_extents"].data_ptr(),
                          aux["gt_points"].data_ptr(), aux["gt_ego_rot"].data_ptr(), aux["gt_trans"].data_ptr(),
-                         aux["gt_trans_ratio"].data_ptr(), ops.ptr(S["syms"]), ops.ptr(S["sym_off"]), gw.data_ptr(),
+                         aux["gt_trans_ratio"].data_ptr(), ops.ptr(syms), ops.ptr(sym_idx), gw.data_ptr(),
                          S["out_rot"].data_ptr(), S["out_trans"].data_ptr(), S["pose_sums"].data_ptr(), S["vis_ps"].data_ptr(),
                          S["dy9"].hi_ptr, S["dy9"].lo_ptr, B, n_pts, 1, 1e-4, _stream())
 
@@ -395,6 +467,11 @@ class Engine:
         S, m, dev = self.saved, self.model, self.dev
         assert S is not None, "backward called without a do_loss forward"
         B, aux, pn = S["B"], S["aux"], m.pnp_net
+        bp = self.bplanes
+
+        def h(t: PT) -> PT:  # a saved forward tensor as a backward operand
+            return t.as_planes(bp)
+
         self.flat_grad.zero_()
         self.bwd_sums_all.zero_()
         gw = grad_losses.float().contiguous()
@@ -405,20 +482,20 @@ class Engine:
         tmp = torch.empty(1024, device=dev)
 
         # ---- FC stack (conv_pnp_net.py:152-156)
-        buf, ks, kss = ops.gemm_wgrad(dy9, S["h2"], self.ws)
+        buf, ks, kss = ops.gemm_wgrad(dy9, h(S["h2"]), self.ws)
         ops.unpack_wgrad(buf, self.grads["pnp_net.fc_r.weight"], 6, 256, 1, 1, 256, ks, kss, 256, 1, 0, 0)
         ops.unpack_wgrad(buf[6 * 256:], self.grads["pnp_net.fc_t.weight"], 3, 256, 1, 1, 256, ks, kss, 256, 1, 0, 0)
         C.gdrn_colsum(dy9.hi_ptr, dy9.lo_ptr, tmp.data_ptr(), B, 64, _stream())
         self.grads["pnp_net.fc_r.bias"].copy_(tmp[0:6])
         self.grads["pnp_net.fc_t.bias"].copy_(tmp[6:9])
         dh2 = ops.gemm_fwd(dy9, self.wd["fc_rt"], 256)
-        dz2 = self._leaky_bwd(dh2, S["h2"])
-        buf, ks, kss = ops.gemm_wgrad(dz2, S["h1"], self.ws)
+        dz2 = self._leaky_bwd(dh2, h(S["h2"]))
+        buf, ks, kss = ops.gemm_wgrad(dz2, h(S["h1"]), self.ws)
         ops.unpack_wgrad(buf, self.grads["pnp_net.fc2.weight"], 256, 1024, 1, 1, 1024, ks, kss, 1024, 1, 0, 0)
         C.gdrn_colsum(dz2.hi_ptr, dz2.lo_ptr, self.grads["pnp_net.fc2.bias"].data_ptr(), B, 256, _stream())
         dh1 = ops.gemm_fwd(dz2, self.wd["fc2"], 1024)
-        dz1 = self._leaky_bwd(dh1, S["h1"])
-        buf, ks, kss = ops.gemm_wgrad(dz1, S["flat"], self.ws)
+        dz1 = self._leaky_bwd(dh1, h(S["h1"]))
+        buf, ks, kss = ops.gemm_wgrad(dz1, h(S["flat"]), self.ws)
         ops.unpack_wgrad(buf, self.grads["pnp_net.fc1.weight"], 1024, 128, 8, 8, 128, ks, kss, 8192, 64, 8, 1)
         C.gdrn_colsum(dz1.hi_ptr, dz1.lo_ptr, self.grads["pnp_net.fc1.bias"].data_ptr(), B, 1024, _stream())
         g = ops.gemm_fwd(dz1, self.wd["fc1"], 8192).view(B, 8, 8, 128)
@@ -427,21 +504,21 @@ class Engine:
         pf = pn.features
         for L in reversed(S["pnp"]):
             ci, gi = L["ci"], L["gi"]
-            du = ops.gn_relu_bwd(g, L["y"], L["u"], pf[gi].weight, L["gstats"], self.grads[f"pnp_net.features.{gi}.weight"],
+            du = ops.gn_relu_bwd(g, h(L["y"]), h(L["u"]), pf[gi].weight, L["gstats"], self.grads[f"pnp_net.features.{gi}.weight"],
                                  self.grads[f"pnp_net.features.{gi}.bias"], G=pf[gi].num_groups)
-            self._wgrad_conv(du, L["x_in"], pf[ci], f"pnp_net.features.{ci}.weight")
+            self._wgrad_conv(du, h(L["x_in"]), pf[ci], f"pnp_net.features.{ci}.weight")
             g = self._dgrad_conv(du, pf[ci], f"pnp_net.features.{ci}")
         d_pnp_in = g  # [B,64,64,128]
         self._segment_done("pnp_net")
 
         # ---- glue + per-pixel losses backward (one fused pass over the logits)
-        dlog = PT((B * 4096, 128), self.planes, device=dev)
+        dlog = PT((B * 4096, 128), bp, device=dev)
         C.gdrn_head_bwd(S["logits"].data_ptr(), aux["gt_xyz"].data_ptr(), aux["gt_mask_visib"].data_ptr(),
                         aux["gt_mask_trunc"].data_ptr(), aux["gt_region"].data_ptr(), S["pix_sums"].data_ptr(), gw.data_ptr(),
                         d_pnp_in.hi_ptr, d_pnp_in.lo_ptr, aux["roi_extents"].data_ptr(), dlog.hi_ptr, dlog.lo_ptr, B, 4096,
-                        _stream())
+                        self.with_2d, _stream())
         hf = m.rot_head_net.features
-        head_in = S["head_in"]
+        head_in = h(S["head_in"])
         buf, ks, kss = ops.gemm_wgrad(dlog, head_in.view(B * 4096, 256), self.ws)
         ops.unpack_wgrad(buf, self.grads["rot_head_net.features.23.weight"], 69, 256, 1, 1, 256, ks, kss, 256, 1, 0, 0)
         tmp128 = torch.empty(128, device=dev)
@@ -452,14 +529,14 @@ class Engine:
         # ---- head convs (cdpn_rot_head_region.py:95-125)
         for L in reversed(S["head"]):
             ci, bi = L["ci"], L["bi"]
-            du, _ = self._bn_bwd(f"rot_head_net.features.{bi}", g, None, L["y"], L["u"], relu_from_u=True)
-            self._wgrad_conv(du, L["x_in"], hf[ci], f"rot_head_net.features.{ci}.weight")
+            du, _ = self._bn_bwd(f"rot_head_net.features.{bi}", g, None, h(L["y"]), h(L["u"]), relu_from_u=True)
+            self._wgrad_conv(du, h(L["x_in"]), hf[ci], f"rot_head_net.features.{ci}.weight")
             g = self._dgrad_conv(du, hf[ci], f"rot_head_net.features.{ci}")
             if L["up"]:
                 g = ops.upsample2x_bwd(g)
         D = S["deconv"]
-        du, _ = self._bn_bwd("rot_head_net.features.1", g, None, D["y"], D["u"], relu_from_u=True)
-        buf, ks, kss = ops.conv_wgrad(du, D["z"], self.ws, 256, 3, 3, 1, 1)
+        du, _ = self._bn_bwd("rot_head_net.features.1", g, None, h(D["y"]), h(D["u"]), relu_from_u=True)
+        buf, ks, kss = ops.conv_wgrad(du, h(D["z"]), self.ws, 256, 3, 3, 1, 1)
         # ConvTranspose2d weight is IOHW [512][256][3][3] with flipped taps relative to the equivalent conv
         ops.unpack_wgrad(buf, self.grads["rot_head_net.features.0.weight"], 256, 512, 3, 3, 512, ks, kss, 9, 256 * 9, 3, 1, flip=1)
         g = ops.conv_fwd(du, self.wd["deconv"], 512, 3, 3, 2, 1)  # [B,8,8,512]
@@ -469,15 +546,15 @@ class Engine:
         ga, gb = g, None
         for Lb in reversed(S["blocks"]):
             p, blk = Lb["p"], Lb["blk"]
-            du2, gout = self._bn_bwd(p + ".bn2", ga, gb, Lb["out"], Lb["u2"], want_gout=True)
-            self._wgrad_conv(du2, Lb["a1"], blk.conv2, p + ".conv2.weight")
+            du2, gout = self._bn_bwd(p + ".bn2", ga, gb, h(Lb["out"]), h(Lb["u2"]), want_gout=True)
+            self._wgrad_conv(du2, h(Lb["a1"]), blk.conv2, p + ".conv2.weight")
             da1 = self._dgrad_conv(du2, blk.conv2, p + ".conv2")
-            du1, _ = self._bn_bwd(p + ".bn1", da1, None, Lb["a1"], Lb["u1"], relu_from_u=True)
-            self._wgrad_conv(du1, Lb["x_in"], blk.conv1, p + ".conv1.weight")
+            du1, _ = self._bn_bwd(p + ".bn1", da1, None, h(Lb["a1"]), h(Lb["u1"]), relu_from_u=True)
+            self._wgrad_conv(du1, h(Lb["x_in"]), blk.conv1, p + ".conv1.weight")
             dx_main = self._dgrad_conv(du1, blk.conv1, p + ".conv1")
             if blk.downsample is not None:
-                dud, _ = self._bn_bwd(p + ".downsample.1", gout, None, None, Lb["ud"])
-                self._wgrad_conv(dud, Lb["x_in"], blk.downsample[0], p + ".downsample.0.weight")
+                dud, _ = self._bn_bwd(p + ".downsample.1", gout, None, None, h(Lb["ud"]))
+                self._wgrad_conv(dud, h(Lb["x_in"]), blk.downsample[0], p + ".downsample.0.weight")
                 dx_ds = self._dgrad_conv(dud, blk.downsample[0], p + ".downsample.0")
                 ga, gb = dx_main, dx_ds
             else:
@@ -487,8 +564,8 @@ class Engine:
         g_pool = ops.add2(ga, gb)
         St = S["stem"]
         g_a0 = ops.maxpool_bwd(St["pool_arg"], g_pool)
-        du0, _ = self._bn_bwd("backbone.bn1", g_a0, None, St["a0"], St["u0"], relu_from_u=True)
-        buf, ks, kss = ops.gemm_wgrad(du0.view(B * 128 * 128, 64), St["a_col"], self.ws)
+        du0, _ = self._bn_bwd("backbone.bn1", g_a0, None, h(St["a0"]), h(St["u0"]), relu_from_u=True)
+        buf, ks, kss = ops.gemm_wgrad(du0.view(B * 128 * 128, 64), h(St["a_col"]), self.ws)
         # ws rows [64][192] with k = (r*7+s)*3 + c  ->  OIHW [64][3][7][7]
         ops.unpack_wgrad(buf, self.grads["backbone.conv1.weight"], 64, 3, 7, 7, 3, ks, kss, 147, 49, 7, 1, krow=192)
         self._segment_done("backbone.stem")  # layer1 + bn1 + conv1
@@ -527,40 +604,80 @@ def out_trans_first(t):
     return t[0]
 
 
+def _bn_snapshot(engine: "Engine"):
+    """BatchNorm running statistics + counters (graph warm-up iterations must not advance them)."""
+    return [(m, m.running_mean.clone(), m.running_var.clone(),
+             None if m.num_batches_tracked is None else m.num_batches_tracked.clone()) for m in engine._bn_mods.values()]
+
+
+def _bn_restore(snap):
+    with torch.no_grad():
+        for m, rm, rv, nbt in snap:
+            m.running_mean.copy_(rm)
+            m.running_var.copy_(rv)
+            if nbt is not None:
+                m.num_batches_tracked.copy_(nbt)
+
+
+def _capture_mode():
+    # with a process group alive, NCCL's watchdog thread polls CUDA events while we capture: "thread_local" keeps its
+    # calls legal (the collectives themselves are captured into the graph on their side stream)
+    import torch.distributed as dist
+
+    return "thread_local" if (dist.is_available() and dist.is_initialized()) else "global"
+
+
+def _finish_hook(engine: "Engine"):
+    hook = engine.grad_hook
+    if hook is not None and hasattr(hook, "finish"):
+        hook.finish()
+
+
 class GraphedTrainStep:
-    """One CUDA graph for the whole train step (forward + losses + backward [+ bucketed all-reduce]): ~560 kernel
-    launches are replayed with a single cudaGraphLaunch, removing the per-launch host cost of the Python/ctypes
-    orchestration.  Inputs live in static buffers; call with new tensors to copy them in (device-side copies)."""
+    """One CUDA graph for the whole train step (forward + losses + backward + bucketed gradient all-reduce): ~370 kernel
+    launches AND the NCCL collectives of `engine.grad_hook` (issued on its side stream at bucket boundaries, i.e. overlapped
+    with the rest of backward) are replayed with a single cudaGraphLaunch, removing the per-launch host cost of the
+    Python/ctypes orchestration at every world size.  Inputs live in static buffers; call with new tensors to copy
+    them in (device-side copies)."""
 
     def __init__(self, engine: "Engine", x: torch.Tensor, aux: dict, train_bn: bool = True, warmup: int = 2, after_backward=None):
         self.engine = engine
         self.x = x.clone()
         self.aux = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in aux.items()}
-        if self.aux.get("sym_infos") is not None:
-            raise NotImplementedError("graphed step: symmetric PM loss (host-side symmetry packing) is not capturable yet")
+        if self.aux.get("sym_infos") is not None:  # symmetric PM: only the (first row, count) pairs are a per-step input
+            self.aux["sym_idx"] = engine.sym_table.indices(self.aux["sym_infos"])
+        self.aux.pop("sym_infos", None)
         self.gw = torch.ones(8, device=x.device)
+
+        def one_step():
+            res = engine.forward(self.x, self.aux, train_bn=train_bn, do_loss=True)
+            engine.backward(self.gw)
+            _finish_hook(engine)
+            if after_backward is not None:
+                after_backward()
+            return res
+
+        snap = _bn_snapshot(engine)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):  # also sizes the split-K workspace and uploads the pack job table
-                engine.forward(self.x, self.aux, train_bn=train_bn, do_loss=True)
-                engine.backward(self.gw)
-                if after_backward is not None:
-                    after_backward()
+                one_step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        _bn_restore(snap)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            res = engine.forward(self.x, self.aux, train_bn=train_bn, do_loss=True)
-            engine.backward(self.gw)
-            if after_backward is not None:
-                after_backward()
+        with torch.cuda.graph(self.graph, capture_error_mode=_capture_mode()):
+            res = one_step()
         self.losses, self.vis, self.rot, self.trans = res["losses"], res["vis"], res["rot"], res["trans"]
+        self.logits = res["logits"]
 
     def __call__(self, x: Optional[torch.Tensor] = None, aux: Optional[dict] = None, grad_losses: Optional[torch.Tensor] = None):
         if x is not None:
             self.x.copy_(x, non_blocking=True)
         if aux is not None:
+            if aux.get("sym_infos") is not None:
+                self.aux["sym_idx"].copy_(self.engine.sym_table.indices(aux["sym_infos"]), non_blocking=True)
             for k, v in aux.items():
                 if isinstance(v, torch.Tensor):
                     self.aux[k].copy_(v, non_blocking=True)
@@ -572,35 +689,35 @@ class GraphedTrainStep:
 
 class GraphedFwdBwd:
     """Forward and backward captured as TWO CUDA graphs sharing one memory pool, for the public module API
-    (`GDRN.forward(..., do_loss=True)` then `.backward()`): the autograd Function replays them around static buffers."""
+    (`GDRN.forward(..., do_loss=True)` then `.backward()`): the autograd Function replays them around static buffers.
+    The data-parallel all-reduces of `engine.grad_hook` are captured INSIDE the backward graph (side stream, overlapped)."""
 
     def __init__(self, engine: "Engine", x: torch.Tensor, aux: dict, train_bn: bool):
-        if aux.get("sym_infos") is not None:
-            raise NotImplementedError("graphed module path: symmetric PM loss (host-side symmetry packing) is not capturable yet")
         self.engine, self.train_bn = engine, train_bn
         self.x = x.clone()
         self.aux = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in aux.items()}
         self.gw = torch.ones(8, device=x.device)
         self.key = self.signature(x, aux, train_bn)
+        snap = _bn_snapshot(engine)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(2):
                 engine.forward(self.x, self.aux, train_bn=train_bn, do_loss=True)
                 engine.backward(self.gw)
+                _finish_hook(engine)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        hook, engine.grad_hook = engine.grad_hook, None  # collectives are issued by the caller after the replay
-        try:
-            self.g_fwd, self.g_bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            pool = torch.cuda.graph_pool_handle()
-            with torch.no_grad():
-                with torch.cuda.graph(self.g_fwd, pool=pool):
-                    res = engine.forward(self.x, self.aux, train_bn=train_bn, do_loss=True)
-                with torch.cuda.graph(self.g_bwd, pool=pool):
-                    engine.backward(self.gw)
-        finally:
-            engine.grad_hook = hook
+        _bn_restore(snap)
+        self.g_fwd, self.g_bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        pool = torch.cuda.graph_pool_handle()
+        mode = _capture_mode()
+        with torch.no_grad():
+            with torch.cuda.graph(self.g_fwd, pool=pool, capture_error_mode=mode):
+                res = engine.forward(self.x, self.aux, train_bn=train_bn, do_loss=True)
+            with torch.cuda.graph(self.g_bwd, pool=pool, capture_error_mode=mode):
+                engine.backward(self.gw)
+                _finish_hook(engine)
         self.losses, self.vis = res["losses"], res["vis"]
 
     @staticmethod
@@ -617,12 +734,8 @@ class GraphedFwdBwd:
 
     def backward(self, g_losses):
         self.gw.copy_(g_losses)
-        self.g_bwd.replay()
-        eng = self.engine
-        if eng.grad_hook is not None:  # bucketed all-reduce after the replay (no overlap in this mode)
-            for stage in ("pnp_net", "rot_head_net", "backbone.layer4", "backbone.layer3", "backbone.layer2", "backbone.stem"):
-                eng.grad_hook(eng, stage)
-        return eng.grads
+        self.g_bwd.replay()  # includes the bucketed all-reduces and the join of their side stream
+        return self.engine.grads
 
 
 class _GDRNFunction(torch.autograd.Function):
@@ -633,7 +746,7 @@ class _GDRNFunction(torch.autograd.Function):
     def forward(ctx, engine: Engine, x, aux, train_bn, *params):
         ctx.engine = engine
         ctx.graphed = None
-        if engine.use_cuda_graphs and aux.get("sym_infos") is None:
+        if engine.use_cuda_graphs:
             g = engine._graphed
             if g is None or g.key != GraphedFwdBwd.signature(x, aux, train_bn):
                 g = engine._graphed = GraphedFwdBwd(engine, x, aux, train_bn)

@@ -80,6 +80,13 @@ class PT:
             x = x + self.buf[1].float() * (1.0 / storage_format()[1])
         return x
 
+    def as_planes(self, planes: int) -> "PT":
+        """This tensor as a `planes`-plane operand: 2 -> 1 keeps the hi plane (= the value rounded to the 16-bit format)."""
+        if planes == self.planes:
+            return self
+        assert planes == 1 and self.planes == 2, (planes, self.planes)
+        return PT(self.shape, 1, buf=self.buf[0:1])
+
     def view(self, *shape):
         return PT(shape, self.planes, buf=self.buf.view((self.planes,) + tuple(shape)))
 

@@ -120,21 +120,24 @@ int gdrn_f32_to_planes(const float* x, void* y_hi, void* y_lo, long n, void* str
 int gdrn_planes_to_f32(const void* x_hi, const void* x_lo, float* y, long n, void* stream);
 
 /* ---- geometry glue + per-pixel losses (GDRN.py:156-169, 341-400; conv_pnp_net.py:120-125).
- * logits fp32 [B*HW][72] (0 mask | 1..3 xyz | 4 bg | 5..68 regions), Patch-PnP input bf16 [B*HW][128]. */
+ * logits fp32 [B*HW][72] (0 mask | 1..3 xyz | 4 bg | 5..68 regions), Patch-PnP input bf16 [B*HW][128]:
+ * with_2d = 1: xyz | coord2d | softmax64 (69 channels, PNP_NET.WITH_2D_COORD), 0: xyz | softmax64 (67 channels). */
 int gdrn_head_glue_fwd(const float* logits, const float* coord2d, const float* extents, void* out_hi, void* out_lo, int B,
-                       int HW, void* stream);
+                       int HW, int with_2d, void* stream);
 int gdrn_pixel_loss_fwd(const float* logits, const float* gt_xyz, const float* m_visib, const float* m_trunc,
                         const long long* labels, double* sums, int B, int HW, void* stream);
 int gdrn_head_bwd(const float* logits, const float* gt_xyz, const float* m_visib, const float* m_trunc,
                   const long long* labels, const double* sums, const float* gw, const void* din_hi, const void* din_lo,
-                  const float* extents, void* out_hi, void* out_lo, int B, int HW, void* stream);
+                  const float* extents, void* out_hi, void* out_lo, int B, int HW, int with_2d, void* stream);
 
 /* ---- rot6d -> R, SITE translation, allo -> ego, PM loss (+ closest symmetric GT), centroid / z losses, re/te
  * (rot_reps.py:34-49, pose_from_pred_centroid_z.py:144-227, utils.py:208-236, pm_loss.py:82-114,
- *  pose_utils.py:430-482, GDRN.py:439-471, model_utils.py:40-52).  pred [B][ld_pred]: cols 0..5 rot6d, 6..8 t. */
+ *  pose_utils.py:430-482, GDRN.py:439-471, model_utils.py:40-52).  pred [B][ld_pred]: cols 0..5 rot6d, 6..8 t.
+ * syms: device-resident table of symmetry rotations [rows][3][3] (built once per object set), sym_idx [B][2] = (first row,
+ * count) per crop, count 0 = asymmetric; both NULL without PM_LOSS_SYM.  The K candidates are scanned by the whole CTA. */
 int gdrn_pose_loss(const float* pred, int ld_pred, const float* cams, const float* centers, const float* whs,
                    const float* ratios, const float* extents, const float* points, const float* gt_rot,
-                   const float* gt_trans, const float* gt_ratio, const float* syms, const int* sym_off, const float* gw,
+                   const float* gt_trans, const float* gt_ratio, const float* syms, const int* sym_idx, const float* gw,
                    float* out_rot, float* out_trans, double* sums, float* vis, void* dy_hi, void* dy_lo, int B, int n_pts,
                    int do_loss, float eps, void* stream);
 int gdrn_loss_finalize(const double* pix_sums, const double* pose_sums, const float* vis, float* losses, float* vis_out,

@@ -286,7 +286,9 @@ def gdrn_forward(sd: Dict[str, Tensor], batch: dict, train: bool, do_loss: bool,
     x = batch["roi_img"]
     feat = backbone_forward(x, sd, train, update_stats)  # :121
     head = head_forward(feat, sd, train, update_stats)  # :123
-    coor_feat = torch.cat([head[:, 1:4], batch["roi_coord_2d"].to(head.dtype)], dim=1)  # :162-166
+    coor_feat = head[:, 1:4]
+    if sd["pnp_net.features.0.weight"].shape[1] == 69:  # cfg PNP_NET.WITH_2D_COORD (:171-173); 67 input channels without
+        coor_feat = torch.cat([coor_feat, batch["roi_coord_2d"].to(head.dtype)], dim=1)  # :162-166
     region_softmax = F.softmax(head[:, 5:], dim=1)  # :169 (region[:,1:])
     rot6d, pred_t_ = pnp_forward(coor_feat, region_softmax, batch["roi_extent"].to(head.dtype), sd)  # :179-181
     rot_m = ortho6d_to_mat(rot6d)  # :193-194

@@ -1,0 +1,235 @@
+"""GPU parity AT THE BENCHMARK'S CONFIGURATION (BASELINE.json configs[1]: B = 64, 256x256, train-mode BN, all 8 losses) and of
+the precision modes the benchmark reports, against the CPU oracle on the same seeded batch / weights bench.py uses.
+
+The headline mode of bench.py is "mixed": the fp32-faithful three-pass forward (every output inside north_star's 1e-3
+bound) followed by the single-pass fp16 backward.  VERDICT r1 item 1 asked for exactly this check: all 8 losses + the 69-ch
+head + region argmax at B = 64 within 1e-3 of the oracle, in the mode whose throughput is reported.
+"""
+import numpy as np
+import pytest
+import torch
+
+from gdr_net_b200 import synth
+from gdr_net_b200.config import a6_config
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+REL = 1e-3
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _build(precision, sd, **cfg_kw):
+    from gdr_net_b200 import GDRN as G
+
+    model, _ = G.build_model_optimizer(a6_config(device="cuda", **cfg_kw), precision=precision)
+    model.load_state_dict(sd)
+    return model
+
+
+def _aux(b):
+    return dict(roi_coord_2d=b["roi_coord_2d"], roi_cams=b["roi_cam"], roi_centers=b["roi_center"], roi_whs=b["roi_wh"],
+                roi_extents=b["roi_extent"], resize_ratios=b["resize_ratio"], gt_xyz=b["roi_xyz"],
+                gt_mask_trunc=b["roi_mask_trunc"], gt_mask_visib=b["roi_mask_visib"], gt_region=b["roi_region"],
+                gt_ego_rot=b["ego_rot"], gt_points=b["roi_points"], sym_infos=None, gt_trans=b["trans"],
+                gt_trans_ratio=b["roi_trans_ratio"])
+
+
+@pytest.fixture(scope="module")
+def b64():
+    """The bench.py workload (seed 100, seeded Kaiming weights) and the oracle's train-mode forward on it (CPU, seconds)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from oracle import fixtures
+    from oracle import gdrn_oracle as O
+
+    sd = synth.seeded_state_dict(fixtures.template_from_manifest(), 0)
+    batch = synth.make_batch(64, seed=100)
+    with torch.no_grad():
+        o = O.gdrn_forward(O.leaf_state_dict(sd, requires_grad=False), batch, train=True, do_loss=True)
+    return sd, batch, o
+
+
+@pytest.mark.parametrize("precision", ["mixed", "fp32x3"])
+def test_b64_train_forward_matches_oracle(b64, precision):
+    from gdr_net_b200.engine import LOSS_NAMES
+
+    sd, batch, o = b64
+    model = _build(precision, sd)
+    model.train()
+    dev = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+    eng = model.engine
+    aux = {k: (v.float().contiguous() if isinstance(v, torch.Tensor) and v.dtype != torch.long else v) for k, v in _aux(dev).items()}
+    res = eng.forward(dev["roi_img"].float().contiguous(), aux, train_bn=True, do_loss=True)
+    eng.backward(torch.ones(8, device="cuda"))
+    torch.cuda.synchronize()
+    losses = res["losses"].cpu()
+    for i, k in enumerate(LOSS_NAMES):
+        ref = float(o["losses"][k])
+        print(f"[{precision}] B=64 {k}: {float(losses[i]):.6f} vs {ref:.6f} rel {abs(float(losses[i]) - ref) / abs(ref):.2e}")
+        assert abs(float(losses[i]) - ref) <= REL * abs(ref), (k, float(losses[i]), ref)
+    head = res["logits"].view(64, 64, 64, 72)[..., :69].permute(0, 3, 1, 2).cpu()
+    ref = o["head"]
+    r, rmax = _rel(head, ref), float((head.double() - ref.double()).abs().max() / ref.abs().max())
+    print(f"[{precision}] B=64 head rel-L2 {r:.2e} rel-max {rmax:.2e}")
+    assert r < REL and rmax < 2 * REL
+    # region argmax: bit-exact except pixels whose top-2 logits are closer than the parity tolerance itself
+    am, ram = head[:, 4:].argmax(1), ref[:, 4:].argmax(1)
+    top2 = ref[:, 4:].topk(2, dim=1).values
+    margin_ok = (top2[:, 0] - top2[:, 1]) > 2 * REL * ref.abs().max()
+    mism = am != ram
+    print(f"[{precision}] B=64 region argmax agreement {1 - mism.float().mean():.6f}, mismatches outside the tie margin {int((mism & margin_ok).sum())}")
+    assert not (mism & margin_ok).any()
+    assert float(mism.float().mean()) < 5e-3
+    assert all(torch.isfinite(g).all() for g in eng.grads.values())
+
+
+def test_mixed_gradients_b4_vs_oracle():
+    """mixed = fp32x3 forward + single-plane fp16 backward: gradients against the oracle's autograd at the same bound as the
+    fp32x3 mode (the backward is linear given the forward's masks; 11-bit operands there cost ~1e-3, the non-smooth forward
+    decides the rest -- reference fp32-vs-fp64 floor 1.5e-2, tools/noise_floor.py)."""
+    from oracle import fixtures
+    from oracle import gdrn_oracle as O
+
+    sd = fixtures.calibrated_state_dict(0)
+    batch_cpu = synth.make_batch(4, seed=1)
+    leaf = O.leaf_state_dict(sd)
+    o = O.gdrn_forward(leaf, batch_cpu, train=True, do_loss=True, update_stats=True)
+    sum(o["losses"].values()).backward()
+    out = {}
+    for precision in ("fp32x3", "mixed"):
+        model = _build(precision, sd)
+        model.train()
+        batch = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in batch_cpu.items()}
+        _, loss_dict = model(batch["roi_img"], **synth.forward_kwargs(batch, train=True))
+        sum(loss_dict.values()).backward()
+        torch.cuda.synchronize()
+        worst, dot, na, nb = ("", 0.0), 0.0, 0.0, 0.0
+        per = {}
+        for name, p in model.named_parameters():
+            a_, b_ = p.grad.double().cpu().flatten(), leaf[name].grad.double().flatten()
+            dot += float(a_ @ b_)
+            na += float(a_ @ a_)
+            nb += float(b_ @ b_)
+            per[name] = _rel(p.grad, leaf[name].grad)
+            if per[name] > worst[1]:
+                worst = (name, per[name])
+        cos = dot / (na * nb) ** 0.5
+        med = float(np.median(list(per.values())))
+        print(f"[{precision}] grads vs oracle: worst rel-L2 {worst}, median {med:.2e}, cosine {cos:.6f}")
+        out[precision] = (worst, med, cos, {k: float(v) for k, v in loss_dict.items()})
+    for k, v in out["mixed"][3].items():  # the forward IS the fp32x3 forward
+        assert abs(v - float(o["losses"][k])) <= REL * abs(float(o["losses"][k])), k
+    assert out["mixed"][0][1] < 0.06 and out["mixed"][2] > 0.995, out["mixed"][:3]
+    assert out["mixed"][1] < 2e-2, out["mixed"][1]
+
+
+def test_graph_train_eval_train_keeps_pack_tables(b64):
+    """an eager eval forward between graphed train steps must not invalidate the weight-pack job table the
+    captured graphs point at, and graph warm-up must not advance the BatchNorm running statistics."""
+    from oracle import fixtures
+
+    sd = fixtures.calibrated_state_dict(0)
+    model = _build("mixed", sd)
+    model.train()
+    model.use_cuda_graphs = True
+    batch = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in synth.make_batch(4, seed=41).items()}
+
+    def train_step():
+        for p in model.parameters():
+            p.grad = None
+        _, ld = model(batch["roi_img"], **synth.forward_kwargs(batch, train=True))
+        sum(ld.values()).backward()
+        torch.cuda.synchronize()
+        return {k: float(v) for k, v in ld.items()}, model.pnp_net.fc_t.weight.grad.clone()
+
+    l1, g1 = train_step()  # captures (2 warm-up passes) + 1 replay = ONE BatchNorm update
+    assert int(model.backbone.bn1.num_batches_tracked) == 1
+    model.eval()
+    with torch.no_grad():
+        model(batch["roi_img"], **synth.forward_kwargs(batch, train=False))  # eager, need_dgrad=False: builds the other job table
+    torch.cuda.empty_cache()
+    junk = [torch.full((1 << 18,), 7.0, device="cuda") for _ in range(8)]  # churn the allocator over any freed block
+    model.train()
+    l2, g2 = train_step()
+    del junk
+    assert int(model.backbone.bn1.num_batches_tracked) == 2
+    for k in l1:  # same batch, weights unchanged, only the BN running stats moved: identical train-mode losses
+        assert abs(l1[k] - l2[k]) <= 1e-4 * abs(l1[k]) + 1e-7, (k, l1[k], l2[k])
+    assert _rel(g2, g1) < 5e-2
+
+
+def test_symmetric_pm_graph_matches_eager_and_golden(golden_dir):
+    """Config 5 (YCB-V, PM_LOSS_SYM): the symmetry matrices live in a device-resident table, a step only carries (row, count)
+    pairs, so the symmetric PM loss is CUDA-graph capturable; losses equal the reference golden (train_sym_b4)."""
+    import os
+
+    from oracle import fixtures
+
+    g = np.load(os.path.join(golden_dir, "train_sym_b4.npz"))
+    sd = fixtures.calibrated_state_dict(0)
+    batch_cpu = synth.make_batch(4, seed=2, with_sym=True)
+    batch = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in batch_cpu.items()}
+    for graphs in (False, True):
+        model = _build("mixed", sd, pm_loss_sym=True)
+        model.train()
+        model.use_cuda_graphs = graphs
+        for it in range(2):
+            for p in model.parameters():
+                p.grad = None
+            _, ld = model(batch["roi_img"], **synth.forward_kwargs(batch, train=True))
+            sum(ld.values()).backward()
+        torch.cuda.synchronize()
+        for k, v in ld.items():
+            ref = float(g["loss/" + k])
+            assert abs(float(v) - ref) <= REL * abs(ref), (graphs, k, float(v), ref)
+        assert model.engine.sym_table.rows == 2 + 64 + 4  # z2, cont(64), z4 uploaded once each
+
+
+def test_nin67_without_2d_coords_matches_oracle():
+    """PNP_NET.WITH_2D_COORD = False: the Patch-PnP input is xyz + 64 region channels (nIn = 67)."""
+    from gdr_net_b200 import GDRN as G
+    from oracle import gdrn_oracle as O
+
+    cfg = a6_config(device="cuda", with_2d_coord=False)
+    model, _ = G.build_model_optimizer(cfg, precision="mixed")
+    assert model.pnp_net.features[0].in_channels == 67
+    sd = synth.seeded_state_dict(model.state_dict(), seed=3)
+    model.load_state_dict(sd)
+    model.train()
+    batch_cpu = synth.make_batch(3, seed=17)
+    batch = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in batch_cpu.items()}
+    _, ld = model(batch["roi_img"], **synth.forward_kwargs(batch, train=True))
+    sum(ld.values()).backward()
+    torch.cuda.synchronize()
+    leaf = O.leaf_state_dict({k: v.cpu() for k, v in sd.items()})
+    o = O.gdrn_forward(leaf, batch_cpu, train=True, do_loss=True)
+    sum(o["losses"].values()).backward()
+    for k, v in ld.items():
+        ref = float(o["losses"][k])
+        assert abs(float(v) - ref) <= 2e-3 * abs(ref), (k, float(v), ref)
+    gname = "pnp_net.features.0.weight"
+    assert _rel(dict(model.named_parameters())[gname].grad, leaf[gname].grad) < 0.06
+
+
+def test_integer_label_dtypes_and_shared_camera():
+    """gt_region may arrive as int32 / uint8 / float (the reference calls .long() itself) and roi_cams as ONE 3x3."""
+    from oracle import fixtures
+
+    sd = fixtures.calibrated_state_dict(0)
+    model = _build("mixed", sd)
+    model.train()
+    batch = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in synth.make_batch(3, seed=51).items()}
+    kw = synth.forward_kwargs(batch, train=True)
+    _, base = model(batch["roi_img"], **kw)
+    base = {k: float(v) for k, v in base.items()}
+    for dt in (torch.int32, torch.uint8, torch.float32):
+        kw2 = dict(kw, gt_region=kw["gt_region"].to(dt), roi_cams=kw["roi_cams"][0])
+        _, ld = model(batch["roi_img"], **kw2)
+        for k in base:
+            assert abs(float(ld[k]) - base[k]) <= 1e-4 * abs(base[k]) + 1e-7, (dt, k)
+    with pytest.raises(ValueError):
+        model(batch["roi_img"], **dict(kw, roi_extents=kw["roi_extents"][:2]))
