@@ -589,8 +589,7 @@ class Engine:
             names = ("backbone.conv1", "backbone.bn1", "backbone.layer1") if stage == "backbone.stem" else (stage,)
             lo = min(self._seg[n][0] for n in names)
             hi = max(self._seg[n][1] for n in names)
-            # TODO(round 2): fold 1/scale into unpack_wgrad / the BN, GN and bias-gradient kernels
-            self.flat_grad[lo:hi].mul_(1.0 / self.grad_scale)
+            C.gdrn_scale_f32(self.flat_grad.data_ptr() + 4 * lo, hi - lo, 1.0 / self.grad_scale, _stream())
         if self.grad_hook:
             self.grad_hook(self, stage)
 

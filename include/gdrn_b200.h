@@ -143,6 +143,17 @@ int gdrn_pose_loss(const float* pred, int ld_pred, const float* cams, const floa
 int gdrn_loss_finalize(const double* pix_sums, const double* pose_sums, const float* vis, float* losses, float* vis_out,
                        int B, int HW, int n_pts, void* stream);
 
+/* ---- fused Ranger step (gradient centralisation + RAdam + Lookahead), lib/torch_utils/solver/ranger.py:100-200, for all
+ * tensors of a param group in ONE launch.  jobs: device array of 64-byte records {float* p; const float* g; float* m; float* v;
+ * float* slow; long numel; int row_len; int pad[3]} (row_len > 0: centralise rows of that length);
+ * blocks: device array of {int job; int count; long begin} (rows or elements per CTA).  The scalar RAdam rectification
+ * (step_lr = step_size * lr, adaptive = N_sma > threshold) is computed by the host; wd_lr = weight_decay * lr;
+ * grad_scale multiplies every gradient (1/loss-scale). */
+int gdrn_ranger_step(const void* jobs_dev, const void* blocks_dev, int nblocks, float step_lr, float wd_lr, float beta1,
+                     float beta2, float eps, float alpha, float grad_scale, int adaptive, int lookahead, void* stream);
+/* x[i] *= s over an fp32 buffer (loss-scale removal from a slice of the flat gradient buffer) */
+int gdrn_scale_f32(float* x, long n, float s, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -374,3 +374,48 @@ def test_groupnorm_relu(planes):
     tolb = 2e-2 if planes == 1 else 1e-4
     assert _rel(DU.float().permute(0, 3, 1, 2), gu_ref) < tolb
     assert _rel(dgamma, gg_ref) < tolb and _rel(dbeta, gb_ref) < tolb
+
+
+def test_fused_ranger_matches_foreach_reference():
+    """csrc/optim.cu gdrn_ranger_step (gradient centralisation + RAdam + lookahead in one launch per param group) against the
+    torch._foreach restatement of lib/torch_utils/solver/ranger.py:100-200 (itself pinned to a literal per-parameter
+    restatement in tests/test_module_api_cpu.py), over 14 steps (crosses the N_sma threshold and two lookahead syncs)."""
+    from gdr_net_b200.solver import Ranger
+
+    torch.manual_seed(0)
+    shapes = [(64, 3, 7, 7), (128, 64, 3, 3), (16, 4608), (9, 8192), (512,), (69,), (3, 256), (3,), (1024, 128, 1, 1)]
+    ps = [torch.randn(s, device="cuda") * 0.1 for s in shapes]
+    a = [p.clone().requires_grad_(True) for p in ps]
+    b = [p.clone().requires_grad_(True) for p in ps]
+    oa = Ranger([{"params": a[:4], "lr": 1e-2}, {"params": a[4:], "lr": 3e-3, "weight_decay": 1e-2}], fused=True)
+    ob = Ranger([{"params": b[:4], "lr": 1e-2}, {"params": b[4:], "lr": 3e-3, "weight_decay": 1e-2}], fused=False)
+    flat = torch.zeros(sum(p.numel() for p in ps) + 3, device="cuda")[3:]  # deliberately 12-byte misaligned views
+    for it in range(14):
+        off = 0
+        for x, y in zip(a, b):
+            g = torch.randn_like(x)
+            flat[off:off + x.numel()].copy_(g.flatten())
+            x.grad = flat[off:off + x.numel()].view_as(x)
+            y.grad = g.clone()
+            off += x.numel()
+        oa.step()
+        ob.step()
+    torch.cuda.synchronize()
+    for x, y, s in zip(a, b, shapes):
+        assert torch.allclose(x.detach(), y.detach(), rtol=2e-5, atol=2e-6), (s, float((x - y).abs().max()))
+    for x, y in zip(a, b):
+        for k in ("exp_avg", "exp_avg_sq", "slow_buffer"):
+            assert torch.allclose(oa.state[x][k], ob.state[y][k], rtol=2e-5, atol=2e-7), k
+        assert oa.state[x]["step"] == ob.state[y]["step"] == 14
+
+
+def test_scale_f32_unaligned_slices():
+    from gdr_net_b200.capi import C
+
+    buf = torch.arange(1, 10001, device="cuda", dtype=torch.float32)
+    ref = buf.clone()
+    for lo, hi in ((0, 10000), (1, 9999), (3, 7), (5, 6), (2, 4099)):
+        C.gdrn_scale_f32(buf.data_ptr() + 4 * lo, hi - lo, 0.5, torch.cuda.current_stream().cuda_stream)
+        ref[lo:hi] *= 0.5
+    torch.cuda.synchronize()
+    assert torch.equal(buf, ref)
