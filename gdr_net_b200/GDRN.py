@@ -149,6 +149,21 @@ class ConvPnPNet(_ParamsOnly):
                 nn.init.constant_(m.bias, 0.0)
         _normal_init(self.fc_r, 0.01)
         _normal_init(self.fc_t, 0.01)
+        self.precision = "fp32x3"  # stand-alone forward: "fp32x3" (1e-3 parity) | "half"
+        self._runner = None
+
+    def forward(self, coor_feat, region=None, extents=None, mask_attention=None):
+        """Stand-alone Patch-PnP inference with the reference signature (conv_pnp_net.py:111): xyz(+2-D coords) maps
+        [B, 3|5, 64, 64], region attention [B, 64, 64, 64], extents [B, 3] -> (rot [B, rot_dim], t [B, 3]).
+        Runs patch_pnp.PatchPnP (libgdrn_b200.so kernels, one CUDA graph); no autograd, no CPU fallback.  Inside
+        `GDRN.forward` the engine runs the same kernels with the hand-written backward instead."""
+        if mask_attention is not None:
+            raise NotImplementedError("mask attention is 'none' in the a6 configuration")
+        from .patch_pnp import PatchPnP
+
+        if self._runner is None or self._runner.precision != {"mixed": "fp32x3"}.get(self.precision, self.precision):
+            self._runner = PatchPnP(self, self.precision)
+        return self._runner(coor_feat, region, extents)
 
 
 def get_xyz_mask_region_out_dim(cfg):

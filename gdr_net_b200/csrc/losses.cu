@@ -90,6 +90,40 @@ __global__ void __launch_bounds__(128) head_glue_fwd_kernel(const float* __restr
     }
 }
 
+// Patch-PnP input packing for the STANDALONE ConvPnPNet.forward (conv_pnp_net.py:111-125): coor_feat [B][c_feat][HW] fp32
+// (xyz [+ 2-D coords]) and region [B][c_reg][HW] fp32 (NCHW, the reference's layout) -> NHWC 16-bit planes [B*HW][128];
+// xyz is de-normalised by the extents when c_feat is 3 or 5 (:120-122).  One thread per pixel: the per-channel reads are
+// coalesced across the warp (consecutive pixels), each thread emits its pixel's 256-byte row.
+__global__ void __launch_bounds__(128) pnp_pack_input_kernel(const float* __restrict__ coor, int c_feat,
+                                                             const float* __restrict__ region, int c_reg,
+                                                             const float* __restrict__ extents, bf16* __restrict__ out_hi,
+                                                             bf16* __restrict__ out_lo, int B, int HW) {
+    const long total = (long)B * HW;
+    const bool denorm = (c_feat == 3 || c_feat == 5) && extents != nullptr;
+    for (long pix = blockIdx.x * (long)blockDim.x + threadIdx.x; pix < total; pix += (long)gridDim.x * blockDim.x) {
+        const int b = (int)(pix / HW);
+        const int hw = (int)(pix - (long)b * HW);
+        float o[72];
+#pragma unroll
+        for (int k = 0; k < 72; ++k) {
+            float v = 0.f;
+            if (k < c_feat) {
+                v = __ldg(coor + ((long)b * c_feat + k) * HW + hw);
+                if (denorm && k < 3) v = (v - 0.5f) * __ldg(extents + b * 3 + k);
+            } else if (k < c_feat + c_reg) {
+                v = __ldg(region + ((long)b * c_reg + (k - c_feat)) * HW + hw);
+            }
+            o[k] = v;
+        }
+        store_row_bf16(out_hi, out_lo, pix, kPnpLd, o, 72);
+        const uint4 zz = make_uint4(0, 0, 0, 0);
+        for (int j = 72; j < kPnpLd; j += 8) {
+            *reinterpret_cast<uint4*>(out_hi + pix * kPnpLd + j) = zz;
+            if (out_lo != nullptr) *reinterpret_cast<uint4*>(out_lo + pix * kPnpLd + j) = zz;
+        }
+    }
+}
+
 // sums (double[6]): |dx|, |dy|, |dz| (masked), |mask - trunc|, CE, sum(mask_visib)
 __global__ void __launch_bounds__(128) pixel_loss_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ gt_xyz,
                                                              const float* __restrict__ m_visib, const float* __restrict__ m_trunc,
@@ -643,6 +677,19 @@ extern "C" int gdrn_head_glue_fwd(const float* logits, const float* coord2d, con
         head_glue_fwd_kernel<true><<<px_grid((long)B * HW), 128, 0, stream>>>(logits, coord2d, extents, (bf16*)out_hi, (bf16*)out_lo, B, HW);
     else
         head_glue_fwd_kernel<false><<<px_grid((long)B * HW), 128, 0, stream>>>(logits, coord2d, extents, (bf16*)out_hi, (bf16*)out_lo, B, HW);
+    GDRN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int gdrn_pnp_pack_input(const float* coor_feat, int c_feat, const float* region, int c_reg, const float* extents,
+                                   void* out_hi, void* out_lo, int B, int HW, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (c_feat < 0 || c_reg < 0 || c_feat + c_reg > 72 || c_feat + c_reg < 1)
+        return set_error(GDRN_ERR_ARG, "pnp_pack_input: %d + %d channels unsupported (1..72)", c_feat, c_reg);
+    if (c_reg > 0 && region == nullptr) return set_error(GDRN_ERR_ARG, "pnp_pack_input: region missing");
+    pnp_pack_input_kernel<<<px_grid((long)B * HW), 128, 0, stream>>>(coor_feat, c_feat, region, c_reg, extents, (bf16*)out_hi,
+                                                                    (bf16*)out_lo, B, HW);
     GDRN_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;

@@ -124,6 +124,10 @@ int gdrn_planes_to_f32(const void* x_hi, const void* x_lo, float* y, long n, voi
  * with_2d = 1: xyz | coord2d | softmax64 (69 channels, PNP_NET.WITH_2D_COORD), 0: xyz | softmax64 (67 channels). */
 int gdrn_head_glue_fwd(const float* logits, const float* coord2d, const float* extents, void* out_hi, void* out_lo, int B,
                        int HW, int with_2d, void* stream);
+/* standalone ConvPnPNet.forward input (conv_pnp_net.py:111-125): NCHW fp32 coor_feat [B][c_feat][HW] (+ region
+ * [B][c_reg][HW]) -> NHWC planes [B*HW][128]; xyz de-normalised by extents when c_feat is 3 or 5. */
+int gdrn_pnp_pack_input(const float* coor_feat, int c_feat, const float* region, int c_reg, const float* extents,
+                        void* out_hi, void* out_lo, int B, int HW, void* stream);
 int gdrn_pixel_loss_fwd(const float* logits, const float* gt_xyz, const float* m_visib, const float* m_trunc,
                         const long long* labels, double* sums, int B, int HW, void* stream);
 int gdrn_head_bwd(const float* logits, const float* gt_xyz, const float* m_visib, const float* m_trunc,
