@@ -93,12 +93,15 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+WITH_SYM = False  # "ycbv" for --config ycbv (BASELINE.json configs[4]): PM_LOSS_SYM with a 21-object symmetry set
+
+
 def build(precision: str, device: str = "cuda"):
     from gdr_net_b200 import GDRN as G
     from gdr_net_b200 import synth
     from gdr_net_b200.config import a6_config
 
-    cfg = a6_config(device=device)
+    cfg = a6_config(device=device, pm_loss_sym=bool(WITH_SYM))
     model, opt = G.build_model_optimizer(cfg, precision=precision)
     # seeded Kaiming-scale weights (the reference's std=1e-3 init is degenerate without ImageNet weights)
     sd = synth.seeded_state_dict(model.state_dict(), seed=0)
@@ -115,11 +118,15 @@ def aux_from_batch(b):
     return dict(roi_coord_2d=b["roi_coord_2d"], roi_cams=b["roi_cam"], roi_centers=b["roi_center"], roi_whs=b["roi_wh"],
                 roi_extents=b["roi_extent"], resize_ratios=b["resize_ratio"], gt_xyz=b["roi_xyz"],
                 gt_mask_trunc=b["roi_mask_trunc"], gt_mask_visib=b["roi_mask_visib"], gt_region=b["roi_region"],
-                gt_ego_rot=b["ego_rot"], gt_points=b["roi_points"], sym_infos=None, gt_trans=b["trans"],
+                gt_ego_rot=b["ego_rot"], gt_points=b["roi_points"], sym_infos=b.get("sym_info"), gt_trans=b["trans"],
                 gt_trans_ratio=b["roi_trans_ratio"])
 
 
 def run_ours(args):
+    global BATCH_PER_GPU, WITH_SYM, METRIC
+    if args.config == "ycbv":
+        BATCH_PER_GPU, WITH_SYM = 32, "ycbv"
+        METRIC = "crops/sec (fwd+bwd, 256x256, bs32 per GPU, YCB-V symmetric PM loss)"
     from gdr_net_b200 import synth
     from gdr_net_b200.capi import launch_count
     from gdr_net_b200.dist import GradAllReducer
@@ -141,7 +148,7 @@ def run_ours(args):
         eng = model.engine
         reducer = GradAllReducer(eng.flat_grad, eng.named_params) if world > 1 else None
         eng.grad_hook = reducer
-        batch = device_batch(synth.make_batch(B, seed=100 + rank), dev)
+        batch = device_batch(synth.make_batch(B, seed=100 + rank, with_sym=WITH_SYM), dev)
         x = batch["roi_img"].float().contiguous()
         aux = {k: (v.float().contiguous() if isinstance(v, torch.Tensor) and v.dtype != torch.long else v)
                for k, v in aux_from_batch(batch).items()}
@@ -222,8 +229,10 @@ def run_ours(args):
         "vs_baseline": None,
         "dtype": {"mixed": "fp16x3 fwd / fp16 bwd, f32 accumulate", "fp32x3": "fp16x3, f32 accumulate", "half": "fp16, f32 accumulate"}[HEADLINE_MODE],
         "data": "synthetic",
-        "config": {"workload": "configs[1]: ResNet-34 GDR-Net (a6_cPnP shapes) full fwd+bwd incl. all 8 losses, train-mode BN, "
-                               "batch 64/GPU, 256x256 synthetic crops, seeded Kaiming weights",
+        "config": {"workload": ("configs[1]: ResNet-34 GDR-Net (a6_cPnP shapes) full fwd+bwd incl. all 8 losses, train-mode BN, "
+                                "batch 64/GPU, 256x256 synthetic crops, seeded Kaiming weights") if not WITH_SYM else
+                               ("configs[4]: YCB-V 21-object config (PM_LOSS_SYM: closest symmetric GT among up to 628 candidates per "
+                                "crop, device-resident table), ResNet-34 GDR-Net full fwd+bwd incl. all 8 losses, batch 32/GPU, 256x256 synthetic crops"),
                    "precision_mode": HEADLINE_MODE + ": " + mode_desc[HEADLINE_MODE],
                    "global_batch": world * B, "parallelism": f"dp{world}",
                    "l2": "activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
@@ -244,7 +253,7 @@ def run_ours(args):
         model = main["model"]
         model.engine.grad_hook = main["eng"].grad_hook
         model.use_cuda_graphs = args.graph  # forward / backward graphs (incl. the all-reduces) behind the public module API
-        host = synth.make_batch(B, seed=200 + rank)
+        host = synth.make_batch(B, seed=200 + rank, with_sym=WITH_SYM)
         pinned = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
         h2d = sum(v.numel() * v.element_size() for v in pinned.values() if isinstance(v, torch.Tensor))
         reducer = main["eng"].grad_hook
@@ -490,6 +499,143 @@ def roofline_live(main, peaks):
     }
 
 
+def run_pnp(args):
+    """BASELINE.json configs[3]: stand-alone Patch-PnP, [512, nIn, 64, 64] correspondence maps -> rot6d | t (inference)."""
+    from gdr_net_b200 import synth
+    from gdr_net_b200.capi import launch_count
+    from gdr_net_b200.GDRN import ConvPnPNet
+    from oracle import gdrn_oracle as O
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    B, nin = 512, args.nin
+    c_feat = nin - 64
+    peaks = load_peaks()
+    net = ConvPnPNet(nIn=nin).to(dev)
+    sd = synth.seeded_state_dict({"pnp_net." + k: v for k, v in net.state_dict().items()}, seed=11)
+    net.load_state_dict({k[len("pnp_net."):]: v for k, v in sd.items()})
+    g = synth._gen(7 + rank, "pnp_bench")
+    coor_h = torch.rand(B, c_feat, 64, 64, generator=g).pin_memory()
+    reg_h = torch.softmax(2.0 * torch.randn(B, 64, 64, 64, generator=g), dim=1).pin_memory()
+    ext_h = (0.05 + 0.25 * torch.rand(B, 3, generator=g)).pin_memory()
+    coor, reg, ext = coor_h.to(dev), reg_h.to(dev), ext_h.to(dev)
+    out = {}
+    results = {}
+    for precision in ("fp32x3", "half"):
+        net.precision = precision
+        for _ in range(max(3, args.warmup)):
+            rot, t = net(coor, reg, ext)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local) if (rank == 0 and precision == "fp32x3") else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            rot, t = net(coor, reg, ext)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt)
+        # e2e: host buffers in, host results out, every step
+        e0.record()
+        n_e2e = max(3, args.steps // 4)
+        for _ in range(n_e2e):
+            r_, t_ = net(coor_h.to(dev, non_blocking=True), reg_h.to(dev, non_blocking=True), ext_h.to(dev, non_blocking=True))
+            r_host, t_host = r_.cpu(), t_.cpu()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_e2e = e0.elapsed_time(e1) / n_e2e
+        if world > 1:
+            tt = torch.tensor([ms_e2e], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_e2e = float(tt)
+        results[precision] = dict(ms=ms, ms_e2e=ms_e2e, rot=rot.cpu(), t=t.cpu(), clocks=clocks)
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    main = results["fp32x3"]
+    # algorithmic work (SURVEY 8d config 4): Conv / Linear MACs x 2 with the true nIn; bytes = fp32 input maps + fp32 weights
+    flops = 2.0 * B * (1024 * 128 * 9 * nin + 256 * 128 * 9 * 128 + 64 * 128 * 9 * 128 + 8192 * 1024 + 1024 * 256 + 256 * 9)
+    wbytes = 4.0 * sum(p.numel() for p in net.parameters())
+    abytes = 4.0 * B * nin * 4096 + wbytes
+    l0 = launch_count()
+    net._runner.use_cuda_graphs = False
+    net(coor, reg, ext)
+    launches = launch_count() - l0
+    net._runner.use_cuda_graphs = True
+    # parity (the oracle as checker) + CPU baseline on a bounded sample
+    cores = min(os.cpu_count() or 1, 32)
+    torch.set_num_threads(cores)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        rot_ref, t_ref = O.pnp_forward(coor_h, reg_h, ext_h, sd)
+        t_cpu = time.perf_counter() - t0
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())  # noqa: E731
+    parity = {p_: {"rot_rel_l2": float(f"{rel(results[p_]['rot'], rot_ref):.3e}"), "t_rel_l2": float(f"{rel(results[p_]['t'], t_ref):.3e}")} for p_ in results}
+    assert parity["fp32x3"]["rot_rel_l2"] <= 1e-3 and parity["fp32x3"]["t_rel_l2"] <= 1e-3, parity
+    # the reference nn.Conv2d / GroupNorm / Linear stack on this GPU (cuDNN, TF32 default, cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    sd_dev = {k: v.to(dev) for k, v in sd.items()}
+    with torch.no_grad():
+        for _ in range(3):
+            O.pnp_forward(coor, reg, ext, sd_dev)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            O.pnp_forward(coor, reg, ext, sd_dev)
+        e1.record()
+        torch.cuda.synchronize()
+    ms_cudnn = e0.elapsed_time(e1) / 10
+    ms = main["ms"]
+    line = {
+        "metric": "crops/sec (stand-alone Patch-PnP forward, 64x64 maps, bs512 per GPU)", "value": round(world * B / ms * 1e3, 1), "unit": "crops/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp16x3, f32 accumulate", "data": "synthetic",
+        "config": {"workload": f"configs[3]: Patch-PnP isolation, [512, {nin}, 64, 64] correspondence maps (xyz{'+2D' if c_feat == 5 else ''} + 64 region "
+                               "channels) + extents -> rot6d | t; NCHW fp32 inputs resident in HBM; one CUDA graph per step "
+                               "(pack -> 3x(conv3x3 s2 + GN + ReLU) -> fc1 -> fc2 -> fc_r|fc_t)",
+                   "global_batch": world * B, "parallelism": f"replicas x{world}", "l2": "input maps (580 MB) exceed the 126 MB L2"},
+        "clocks": main["clocks"], "gpu_launches": int(launches),
+        "e2e": {"value": round(world * B / main["ms_e2e"] * 1e3, 1), "unit": "crops/s", "ms_per_step": round(main["ms_e2e"], 3),
+                "h2d_bytes_per_step": int(coor_h.numel() * 4 + reg_h.numel() * 4 + ext_h.numel() * 4), "d2h_bytes_per_step": B * 9 * 4,
+                "api": "ConvPnPNet.forward(coor_feat, region, extents) with pinned host tensors in, host rot/t out, every step"},
+        "roofline": {"bound": "hbm", "achieved": round(abytes / (ms * 1e-3) / 1e9, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                     "frac": round(abytes / (ms * 1e-3) / 1e9 / peaks["hbm"], 4), "traffic": None,
+                     "algorithmic_bytes_per_step": abytes,
+                     "tensor_bound": {"achieved": round(flops / (ms * 1e-3) / 1e12, 1), "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                                      "frac": round(flops / (ms * 1e-3) / 1e12 / peaks["bf16_burst"], 4),
+                                      "algorithmic_gflop_per_step": round(flops / 1e9, 1)},
+                     "note": "the path sits at the ridge (SURVEY 8d: ~229 FLOP/B): both bounds reported; whole graph (7 GEMM + 4 HBM-bound launches), not one kernel"},
+        "modes": {"half": {"value": round(world * B / results["half"]["ms"] * 1e3, 1), "unit": "crops/s", "ms_per_step": round(results["half"]["ms"], 4)}},
+        "parity_b512": dict(parity, tolerance=1e-3, checker="oracle pnp_forward (conv_pnp_net.py:111-157 restated) on the same maps / weights"),
+        "cpu_baseline": {"value": round(B / t_cpu, 1), "unit": "crops/s", "cores": cores, "kind": "port",
+                         "sample": f"one forward of the {B}-crop batch, torch CPU fp32, {cores} threads"},
+        "cudnn_same_gpu": {"value": round(B / ms_cudnn * 1e3, 1), "unit": "crops/s", "ms_per_step": round(ms_cudnn, 3),
+                           "what": "the reference nn stack restated (F.conv2d / group_norm / linear, NCHW fp32, TF32 convs, cudnn.benchmark) on this GPU"},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def cudnn_same_gpu(B, dev, steps=8, warm=4):
     """The reference algorithm as plain PyTorch ops (cuDNN / cuBLAS / ATen library kernels) on THIS GPU -- what the reference's
     own nn.Modules dispatch to on the box (the reference package itself needs detectron2 / mmcv and cannot travel): the oracle
@@ -502,7 +648,7 @@ def cudnn_same_gpu(B, dev, steps=8, warm=4):
 
     torch.backends.cudnn.benchmark = True
     sd = synth.seeded_state_dict(fixtures.template_from_manifest(), 0)
-    batch = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in synth.make_batch(B, seed=100).items()}
+    batch = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in synth.make_batch(B, seed=100, with_sym=WITH_SYM).items()}
     res = {}
     for name, cl, amp in (("tf32", False, False), ("tf32_channels_last", True, False), ("amp_fp16_channels_last", True, True)):
         leaf = {}
@@ -520,7 +666,7 @@ def cudnn_same_gpu(B, dev, steps=8, warm=4):
                 if v.requires_grad:
                     v.grad = None
             with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
-                o = O.gdrn_forward(leaf, b, train=True, do_loss=True)
+                o = O.gdrn_forward(leaf, b, train=True, do_loss=True, pm_sym=bool(WITH_SYM))
             sum(o["losses"].values()).backward()
 
         for _ in range(warm):
@@ -573,10 +719,10 @@ def cpu_baseline(sample_batch: int = 8, iters: int = 2, check=None):
     if check is not None:
         from gdr_net_b200.engine import LOSS_NAMES
 
-        b64 = synth.make_batch(BATCH_PER_GPU, seed=100)  # rank 0's benchmark batch
+        b64 = synth.make_batch(BATCH_PER_GPU, seed=100, with_sym=WITH_SYM)  # rank 0's benchmark batch
         t0 = time.perf_counter()
         with torch.no_grad():
-            o = O.gdrn_forward(O.leaf_state_dict(sd, requires_grad=False), b64, train=True, do_loss=True)
+            o = O.gdrn_forward(O.leaf_state_dict(sd, requires_grad=False), b64, train=True, do_loss=True, pm_sym=bool(WITH_SYM))
         t_fwd = time.perf_counter() - t0
         worst = 0.0
         for i, k in enumerate(LOSS_NAMES):
@@ -651,6 +797,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--cpu-iters", type=int, default=1)
+    ap.add_argument("--config", default="train", choices=["train", "ycbv", "pnp"],
+                    help="train = BASELINE configs[1] (the headline; default), ycbv = configs[4] (B=32, symmetric PM), "
+                         "pnp = configs[3] (stand-alone Patch-PnP, B=512)")
+    ap.add_argument("--nin", type=int, default=69, choices=[67, 69], help="--config pnp: Patch-PnP input channels")
     ap.add_argument("--quick", action="store_true", help="device-timed value only (for profiler runs)")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel from Python instead of one CUDA graph")
     args = ap.parse_args()
@@ -660,7 +810,10 @@ def main():
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
-        run_ours(args)
+        if args.config == "pnp":
+            run_pnp(args)
+        else:
+            run_ours(args)
 
 
 if __name__ == "__main__":

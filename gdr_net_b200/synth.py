@@ -52,6 +52,28 @@ def discrete_symmetries(kind: str) -> torch.Tensor | None:
     raise ValueError(kind)
 
 
+_YCBV_SYMS: list = []
+
+
+def ycbv_like_symmetries() -> list:
+    """21 entries: None (asymmetric) or a [K,3,3] float32 tensor of model-to-model symmetry rotations; built once."""
+    if not _YCBV_SYMS:
+        def rot(axis, a):
+            c, s = math.cos(a), math.sin(a)
+            if axis == "z":
+                return [[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]]
+            if axis == "x":
+                return [[1.0, 0.0, 0.0], [0.0, c, -s], [0.0, s, c]]
+            return [[c, 0.0, s], [0.0, 1.0, 0.0], [-s, 0.0, c]]
+
+        def cyc(axis, n):
+            return torch.tensor([rot(axis, 2 * math.pi * i / n) for i in range(n)], dtype=torch.float32)
+
+        table = {0: cyc("z", 628), 12: cyc("z", 628), 15: cyc("x", 2), 17: cyc("y", 2), 18: cyc("z", 4), 19: cyc("y", 2), 20: cyc("x", 4)}
+        _YCBV_SYMS.extend(table.get(i) for i in range(21))
+    return _YCBV_SYMS
+
+
 def make_batch(bs: int, seed: int = 0, n_points: int = 3000, with_sym: bool = False, dtype=torch.float32) -> dict:
     """Synthetic batch with the reference field names (CPU tensors)."""
     g = _gen(seed, "batch")
@@ -112,7 +134,14 @@ def make_batch(bs: int, seed: int = 0, n_points: int = 3000, with_sym: bool = Fa
     ).to(dtype)
 
     sym_infos = None
-    if with_sym:
+    if with_sym == "ycbv":
+        # a YCB-V-like object set (reference configs/gdrn/ycbv/*: 21 objects, PM_LOSS_SYM; ref/ycbv.py lists 5 symmetric
+        # ones): per crop one of 21 objects, the arrays SHARED per object like the per-dataset `sym_infos` dict of the
+        # reference data loader (so the device table is filled once); K up to 628 (continuous axis at 0.01 rad steps)
+        objs = ycbv_like_symmetries()
+        ids = torch.randint(0, len(objs), (bs,), generator=g).tolist()
+        sym_infos = [objs[i] for i in ids]
+    elif with_sym:
         kinds = ["none", "z2", "cont", "z4"]
         sym_infos = [discrete_symmetries(kinds[i % len(kinds)]) for i in range(bs)]
 

