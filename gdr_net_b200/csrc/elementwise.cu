@@ -94,6 +94,30 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
     }
 }
 
+// Eval-mode BatchNorm folding for ALL layers in one launch: scale = gamma / sqrt(running_var + eps), shift = beta -
+// running_mean * scale.  The scales are multiplied into the packed conv weights (pack.cu row_scale), the shifts become
+// the conv epilogue's bias: inference runs conv + BN + (residual) + ReLU as ONE kernel per layer (north_star "fused
+// conv+BN+ReLU epilogues"; reference inference caller gdrn_evaluator.py:568-580).
+struct BnFoldJob {  // 64 bytes
+    const float* gamma;
+    const float* beta;
+    const float* mean;
+    const float* var;
+    float* scale;
+    float* shift;
+    int C;
+    float eps;
+    long pad;
+};
+__global__ void bn_fold_batched_kernel(const BnFoldJob* __restrict__ jobs) {
+    const BnFoldJob J = jobs[blockIdx.x];
+    for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < J.C; c += gridDim.y * blockDim.x) {
+        const float sc = J.gamma[c] * rsqrtf(J.var[c] + J.eps);
+        J.scale[c] = sc;
+        J.shift[c] = J.beta[c] - J.mean[c] * sc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // BatchNorm forward.  Design notes (ncu, profiles/r1_bn_kernels.txt): the first version kept unpacked fp32 arrays live
 // across the loads (115 registers -> 2 blocks/SM -> 24 % warps active -> 29 % of DRAM peak).  Now the 16-byte loads
@@ -113,11 +137,13 @@ __device__ __forceinline__ void unpack8_lo(const uint4& q, float (&f)[8]) {  // 
 }
 
 // y = [relu](x * sc[c] + sh[c] [+ res]);  s_sc / s_sh: shared memory [C]
+// mask_out (optional, with relu): one byte per 8-channel group, bit j = [pre-activation of channel j > 0].  BatchNorm
+// backward reads this byte instead of the 16-byte activation group to rebuild the ReLU mask (3.75 of its 14 B / element).
 template <bool LO, bool RES>
 __device__ __forceinline__ void bn_apply_loop(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo,
                                               const bf16* __restrict__ r_hi, const bf16* __restrict__ r_lo,
                                               bf16* __restrict__ y_hi, bf16* __restrict__ y_lo, const float* s_sc,
-                                              const float* s_sh, long total, int cg, int relu) {
+                                              const float* s_sh, long total, int cg, int relu, uint8_t* __restrict__ mask_out) {
     const long stride = (long)gridDim.x * blockDim.x;
     const long first = blockIdx.x * (long)blockDim.x + threadIdx.x;
     const int c0 = (int)(first % cg) * 8;
@@ -152,6 +178,12 @@ __device__ __forceinline__ void bn_apply_loop(const bf16* __restrict__ x_hi, con
                     for (int j = 0; j < 8; ++j) v[j] += r[j];
                 }
                 if (relu) {
+                    if (mask_out != nullptr) {
+                        uint32_t bits = 0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+                        mask_out[it] = (uint8_t)bits;
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
@@ -173,7 +205,7 @@ __global__ void __launch_bounds__(256, 4) bn_act_kernel(const bf16* __restrict__
         s_sh[c] = shift[c];
     }
     __syncthreads();
-    bn_apply_loop<LO, RES>(x_hi, x_lo, r_hi, r_lo, y_hi, y_lo, s_sc, s_sh, rows * (C / 8), C / 8, relu);
+    bn_apply_loop<LO, RES>(x_hi, x_lo, r_hi, r_lo, y_hi, y_lo, s_sc, s_sh, rows * (C / 8), C / 8, relu, nullptr);
 }
 
 // finalize + apply in one kernel: scale/shift from the conv epilogue's (sum, sum^2) (train) or the running statistics
@@ -185,7 +217,8 @@ __global__ void __launch_bounds__(256, 4) bn_fwd_kernel(const bf16* __restrict__
                                                         const float* __restrict__ stats, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float* running_mean, float* running_var,
                                                         float* __restrict__ mean_out, float* __restrict__ invstd_out, long rows,
-                                                        int C, float eps, float momentum, int train, int relu) {
+                                                        int C, float eps, float momentum, int train, int relu,
+                                                        uint8_t* __restrict__ mask_out) {
     __shared__ float s_sc[512], s_sh[512];
     const float count = (float)rows;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -217,7 +250,7 @@ __global__ void __launch_bounds__(256, 4) bn_fwd_kernel(const bf16* __restrict__
         }
     }
     __syncthreads();
-    bn_apply_loop<LO, RES>(x_hi, x_lo, r_hi, r_lo, y_hi, y_lo, s_sc, s_sh, rows * (C / 8), C / 8, relu);
+    bn_apply_loop<LO, RES>(x_hi, x_lo, r_hi, r_lo, y_hi, y_lo, s_sc, s_sh, rows * (C / 8), C / 8, relu, mask_out);
 }
 
 
@@ -467,7 +500,7 @@ constexpr int kBnBwdThreads = 256;
 // masked gradient of one 8-channel group: g = (ga [+ gb]) * [y > 0]
 template <bool LO>
 __device__ __forceinline__ void masked_grad(const uint4& gah, const uint4& gal, const uint4& gbh, const uint4& gbl, const uint4& yh,
-                                            bool has_gb, bool has_y, float (&g)[8]) {
+                                            bool has_gb, bool has_y, float (&g)[8], bool has_bits = false, uint32_t bits = 0) {
     unpack8(gah, g);
     if (LO) unpack8_lo(gal, g);
     if (has_gb) {
@@ -477,7 +510,10 @@ __device__ __forceinline__ void masked_grad(const uint4& gah, const uint4& gal, 
 #pragma unroll
         for (int j = 0; j < 8; ++j) g[j] += t[j];
     }
-    if (has_y) {
+    if (has_bits) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = ((bits >> j) & 1u) ? g[j] : 0.f;
+    } else if (has_y) {
         float y[8];
         unpack8(yh, y);
 #pragma unroll
@@ -505,7 +541,8 @@ __global__ void __launch_bounds__(kBnBwdThreads, 3) bn_bwd_reduce_kernel(
     const bf16* __restrict__ ga_hi, const bf16* __restrict__ ga_lo, const bf16* __restrict__ gb_hi,
     const bf16* __restrict__ gb_lo, const bf16* __restrict__ y_hi, const bf16* __restrict__ u_hi,
     const bf16* __restrict__ u_lo, const float* __restrict__ mean, const float* __restrict__ invstd,
-    const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ sums, long rows, int C) {
+    const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ sums, long rows, int C,
+    const uint8_t* __restrict__ mask_in) {
     // block = (C/8) channel groups x rpb row lanes
     const int cg = C / 8;
     const int rpb = kBnBwdThreads / cg;  // cg in {8,16,32,64}: always divides 256
@@ -523,13 +560,15 @@ __global__ void __launch_bounds__(kBnBwdThreads, 3) bn_bwd_reduce_kernel(
         }
     }
     __syncthreads();
-    const bool has_gb = gb_hi != nullptr, has_y = !MASKU && y_hi != nullptr;
+    const bool has_bits = !MASKU && mask_in != nullptr;
+    const bool has_gb = gb_hi != nullptr, has_y = !MASKU && !has_bits && y_hi != nullptr;
     float s0[8], s1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
     const long rstride = (long)gridDim.x * rpb;
     for (long r0 = (long)blockIdx.x * rpb + rl; r0 < rows; r0 += 2 * rstride) {
         uint4 gah[2], gal[2], gbh[2], gbl[2], yh[2], uh[2], ul[2];
+        uint32_t mb[2] = {0, 0};
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
             const long r = r0 + t * rstride;
@@ -537,6 +576,7 @@ __global__ void __launch_bounds__(kBnBwdThreads, 3) bn_bwd_reduce_kernel(
                 const long off = r * cg + g;
                 gah[t] = ld16(ga_hi, off);
                 uh[t] = ld16(u_hi, off);
+                if (has_bits) mb[t] = __ldg(mask_in + off);
                 if (has_y) yh[t] = ld16(y_hi, off);
                 if (has_gb) gbh[t] = ld16(gb_hi, off);
                 if (LO) {
@@ -551,7 +591,7 @@ __global__ void __launch_bounds__(kBnBwdThreads, 3) bn_bwd_reduce_kernel(
             const long r = r0 + t * rstride;
             if (r < rows) {
                 float gv[8], u[8];
-                masked_grad<LO>(gah[t], gal[t], gbh[t], gbl[t], yh[t], has_gb, has_y, gv);
+                masked_grad<LO>(gah[t], gal[t], gbh[t], gbl[t], yh[t], has_gb, has_y, gv, has_bits, mb[t]);
                 unpack8(uh[t], u);
                 if (LO) unpack8_lo(ul[t], u);
                 if (MASKU) mask_from_u(u, s_sc + g * 8, s_sh + g * 8, gv);
@@ -589,7 +629,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(
     const bf16* __restrict__ u_lo, const float* __restrict__ mean, const float* __restrict__ invstd,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ sums, bf16* __restrict__ du_hi,
     bf16* __restrict__ du_lo, bf16* __restrict__ gout_hi, bf16* __restrict__ gout_lo, float* __restrict__ dgamma,
-    float* __restrict__ dbeta, long rows, int C, int train) {
+    float* __restrict__ dbeta, long rows, int C, int train, const uint8_t* __restrict__ mask_in) {
     __shared__ __align__(16) float s_k1[512], s_k2[512], s_k3[512], s_sc[512], s_sh[512];
     const int cg = C / 8;
     const long total = rows * cg;
@@ -616,18 +656,21 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(
         }
     }
     __syncthreads();
-    const bool has_gb = gb_hi != nullptr, has_y = !MASKU && y_hi != nullptr, has_gout = gout_hi != nullptr;
+    const bool has_bits = !MASKU && mask_in != nullptr;
+    const bool has_gb = gb_hi != nullptr, has_y = !MASKU && !has_bits && y_hi != nullptr, has_gout = gout_hi != nullptr;
     const long stride = (long)gridDim.x * blockDim.x;
     const long first = blockIdx.x * (long)blockDim.x + threadIdx.x;
     const int c0 = (int)(first % cg) * 8;
     for (long idx = first; idx < total; idx += 2 * stride) {
         uint4 gah[2], gal[2], gbh[2], gbl[2], yh[2], uh[2], ul[2];
+        uint32_t mb[2] = {0, 0};
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
             const long it = idx + t * stride;
             if (it < total) {
                 gah[t] = ld16(ga_hi, it);
                 uh[t] = ld16(u_hi, it);
+                if (has_bits) mb[t] = __ldg(mask_in + it);
                 if (has_y) yh[t] = ld16(y_hi, it);
                 if (has_gb) gbh[t] = ld16(gb_hi, it);
                 if (LO) {
@@ -642,7 +685,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(
             const long it = idx + t * stride;
             if (it < total) {
                 float gv[8], u[8], o[8];
-                masked_grad<LO>(gah[t], gal[t], gbh[t], gbl[t], yh[t], has_gb, has_y, gv);
+                masked_grad<LO>(gah[t], gal[t], gbh[t], gbl[t], yh[t], has_gb, has_y, gv, has_bits, mb[t]);
                 unpack8(uh[t], u);
                 if (LO) unpack8_lo(ul[t], u);
                 if (MASKU) mask_from_u(u, s_sc + c0, s_sh + c0, gv);
@@ -916,6 +959,14 @@ extern "C" int gdrn_bn_finalize(const float* stats, const float* gamma, const fl
     LAUNCH_DONE();
 }
 
+extern "C" int gdrn_bn_fold_batched(const void* jobs_dev, int njobs, void* stream_) {
+    STREAM;
+    static_assert(sizeof(BnFoldJob) == 64, "BnFoldJob layout is mirrored by the host (gdr_net_b200/engine.py)");
+    if (njobs <= 0) return 0;
+    bn_fold_batched_kernel<<<dim3(njobs, 2), 256, 0, stream>>>(reinterpret_cast<const BnFoldJob*>(jobs_dev));
+    LAUNCH_DONE();
+}
+
 extern "C" int gdrn_bn_act(const void* x_hi, const void* x_lo, const void* r_hi, const void* r_lo, void* y_hi, void* y_lo,
                            const float* scale, const float* shift, long rows, int C, int relu, void* stream_) {
     STREAM;
@@ -972,8 +1023,10 @@ extern "C" int gdrn_zero_insert(const void* x_hi, const void* x_lo, void* y_hi, 
 extern "C" int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_hi, const void* gb_lo, const void* y_hi,
                            const void* u_hi, const void* u_lo, const float* mean, const float* invstd, const float* gamma,
                            const float* beta, float* sums, void* du_hi, void* du_lo, void* gout_hi, void* gout_lo,
-                           float* dgamma, float* dbeta, long rows, int C, int train, int flags, void* stream_) {
+                           float* dgamma, float* dbeta, const void* relu_mask, long rows, int C, int train, int flags,
+                           void* stream_) {
     STREAM;
+    const uint8_t* mask_in = reinterpret_cast<const uint8_t*>(relu_mask);
     if (C % 64 || C > 512) return set_error(GDRN_ERR_ARG, "bn_bwd: unsupported C=%d", C);
     const int mask_u = flags & 1;
     if (mask_u && (y_hi != nullptr || beta == nullptr)) return set_error(GDRN_ERR_ARG, "bn_bwd: mask-from-u needs beta and no y");
@@ -987,7 +1040,7 @@ extern "C" int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_
 #define GDRN_BN_RED(LO, MU)                                                                                                   \
     bn_bwd_reduce_kernel<LO, MU><<<(int)blocks, kBnBwdThreads, 0, stream>>>(CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo),       \
                                                                             CBF(y_hi), CBF(u_hi), CBF(u_lo), mean, invstd, gamma, \
-                                                                            beta, sums, rows, C)
+                                                                            beta, sums, rows, C, mask_in)
         if (u_lo != nullptr) {
             if (mask_u) GDRN_BN_RED(true, true); else GDRN_BN_RED(true, false);
         } else {
@@ -1001,7 +1054,7 @@ extern "C" int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_
 #define GDRN_BN_APP(LO, MU)                                                                                                      \
     bn_bwd_apply_kernel<LO, MU><<<agrid, 256, 0, stream>>>(CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo), CBF(y_hi), CBF(u_hi),    \
                                                            CBF(u_lo), mean, invstd, gamma, beta, sums, BF(du_hi), BF(du_lo),       \
-                                                           BF(gout_hi), BF(gout_lo), dgamma, dbeta, rows, C, train)
+                                                           BF(gout_hi), BF(gout_lo), dgamma, dbeta, rows, C, train, mask_in)
     if (u_lo != nullptr) {
         if (mask_u) GDRN_BN_APP(true, true); else GDRN_BN_APP(true, false);
     } else {
@@ -1065,15 +1118,16 @@ extern "C" int gdrn_leaky_bwd(const void* g_hi, const void* g_lo, const void* y_
 
 extern "C" int gdrn_bn_fwd(const void* x_hi, const void* x_lo, const void* r_hi, const void* r_lo, void* y_hi, void* y_lo,
                            const float* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
-                           float* mean_out, float* invstd_out, long rows, int C, float eps, float momentum, int train, int relu,
-                           void* stream_) {
+                           float* mean_out, float* invstd_out, void* relu_mask_out, long rows, int C, float eps, float momentum,
+                           int train, int relu, void* stream_) {
     STREAM;
     if (C % 8 || C > 512 || 256 % (C / 8)) return set_error(GDRN_ERR_ARG, "bn_fwd: unsupported C=%d", C);
     if (train && stats == nullptr) return set_error(GDRN_ERR_ARG, "bn_fwd: batch statistics missing");
     const int grid = ew_grid_amortised(rows * (C / 8), 256, 4);
 #define GDRN_BN_FWD(LO, RES)                                                                                                  \
     bn_fwd_kernel<LO, RES><<<grid, 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), CBF(r_hi), CBF(r_lo), BF(y_hi), BF(y_lo), stats, gamma, beta, \
-                                                     running_mean, running_var, mean_out, invstd_out, rows, C, eps, momentum, train, relu)
+                                                     running_mean, running_var, mean_out, invstd_out, rows, C, eps, momentum, train, relu,  \
+                                                     reinterpret_cast<uint8_t*>(relu_mask_out))
     if (x_lo != nullptr) {
         if (r_hi != nullptr) GDRN_BN_FWD(true, true); else GDRN_BN_FWD(true, false);
     } else {

@@ -314,6 +314,12 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
             // one constant OR-ed with (address >> 4) and advanced by +2 (32 bytes) per 16-wide k-step -- the generic loop
             // rebuilt eight descriptors per k-block (126 instructions on this single thread).
             constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N, 0, 0);
+            // 3-pass mode: the w_hi and w_lo tiles of a stage are CONTIGUOUS in shared memory (BLOCK_N rows each, same
+            // K-major swizzled layout) and the main / cross accumulators are ADJACENT in TMEM, so a_hi x [w_hi; w_lo] is ONE
+            // MMA of width 2*BLOCK_N writing main | cross.  The kernel is shared-memory-bandwidth bound (TMA writes + MMA
+            // operand reads exceed 128 B/clk): this reads a_hi once instead of twice per k-step (24 -> 20 KB per k-step).
+            constexpr uint32_t idesc_wide = make_idesc(kBlockM, (NSPLIT == 3 ? 2 : 1) * BLOCK_N, 0, 0);
+            static_assert(NSPLIT != 3 || (Cfg::NMAIN == 1 && 2 * BLOCK_N <= 256), "stacked hi|lo MMA needs adjacent accumulators");
             const uint64_t desc_const = make_smem_desc(0, 16, 1024);
             const uint32_t smem_base = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
             const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
@@ -344,9 +350,8 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
                         for (int k = 0; k < kBlockK / 16; ++k) {
                             const uint32_t ac = (k == 0) ? accum : 1u;
                             if (NSPLIT == 3) {
-                                umma_bf16(d_main, da + 2 * k, db + 2 * k, idesc, ac);
-                                umma_bf16(d_cross, da + 2 * k, db + (Cfg::B_BYTES >> 4) + 2 * k, idesc, ac);
-                                umma_bf16(d_cross, da + (Cfg::A_BYTES >> 4) + 2 * k, db + 2 * k, idesc, 1u);
+                                umma_bf16(d_main, da + 2 * k, db + 2 * k, idesc_wide, ac);                    // a_hi x [w_hi; w_lo] -> main | cross
+                                umma_bf16(d_cross, da + (Cfg::A_BYTES >> 4) + 2 * k, db + 2 * k, idesc, 1u);  // a_lo x w_hi -> cross
                             } else {
                                 umma_bf16(d_main, da + 2 * k, db + 2 * k, idesc, ac);
                             }
@@ -480,9 +485,40 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
                     for (int j = 0; j < 32; ++j)
                         if (full_chunk || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
                 }
+                if (p.res_hi != nullptr && row_ok && full_chunk) {
+                    // folded eval epilogue: + residual (the block's identity / downsample branch, same [rows][ldc] planes)
+                    const __nv_bfloat16* rh = reinterpret_cast<const __nv_bfloat16*>(p.res_hi) + grow * p.ldc + col0;
+                    const __nv_bfloat16* rl = p.res_lo ? reinterpret_cast<const __nv_bfloat16*>(p.res_lo) + grow * p.ldc + col0 : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 q = __ldg(reinterpret_cast<const uint4*>(rh) + j);
+                        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            float a, b;
+                            unpack_hi2(w[t], a, b);
+                            f[8 * j + 2 * t] += a;
+                            f[8 * j + 2 * t + 1] += b;
+                        }
+                        if (rl != nullptr) {
+                            const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(rl) + j);
+                            const uint32_t w2[4] = {q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                float a, b;
+                                unpack_lo2(w2[t], a, b);
+                                f[8 * j + 2 * t] += a;
+                                f[8 * j + 2 * t + 1] += b;
+                            }
+                        }
+                    }
+                }
                 if (p.act == 1) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : 0.1f * f[j];
+                } else if (p.act == 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
                 }
                 if (row_ok) {
                     if (p.out_f32 != nullptr) {
@@ -688,9 +724,9 @@ extern "C" int gdrn_set_2cta(int on) {
 }
 
 extern "C" int gdrn_conv_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, void* y_hi,
-                             void* y_lo, float* y_f32, const float* bias, float* stats, int N, int H, int W, int Cin,
-                             int Cout, int Cout_pad, int KH, int KW, int stride, int pad, int ldc, int act, int nsplit,
-                             void* stream_) {
+                             void* y_lo, float* y_f32, const float* bias, const void* res_hi, const void* res_lo, float* stats,
+                             int N, int H, int W, int Cin, int Cout, int Cout_pad, int KH, int KW, int stride, int pad, int ldc,
+                             int act, int nsplit, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (nsplit != 1 && nsplit != 3) return set_error(GDRN_ERR_ARG, "conv_fwd: nsplit must be 1 or 3");
     if (nsplit == 3 && (x_lo == nullptr || w_lo == nullptr)) return set_error(GDRN_ERR_ARG, "conv_fwd: lo planes missing");
@@ -698,6 +734,9 @@ extern "C" int gdrn_conv_fwd(const void* x_hi, const void* x_lo, const void* w_h
     if (stride != 1 && stride != 2) return set_error(GDRN_ERR_ARG, "conv_fwd: stride must be 1 or 2");
     if (H % stride || W % stride) return set_error(GDRN_ERR_ARG, "conv_fwd: H, W must be divisible by stride");
     if (ldc % 8 != 0 || ldc < Cout) return set_error(GDRN_ERR_ARG, "conv_fwd: bad ldc=%d", ldc);
+    if (res_hi != nullptr && (Cout % 32 != 0 || y_hi == nullptr))
+        return set_error(GDRN_ERR_ARG, "conv_fwd: a residual needs Cout %% 32 == 0 and a 16-bit output");
+    if (act < 0 || act > 2) return set_error(GDRN_ERR_ARG, "conv_fwd: act must be 0 (none), 1 (LeakyReLU 0.1) or 2 (ReLU)");
     const int Ho = H / stride, Wo = W / stride;
     if (Wo > 128 || 128 % Wo != 0) return set_error(GDRN_ERR_ARG, "conv_fwd: unsupported output width %d", Wo);
     int TH = 128 / Wo;
@@ -749,6 +788,8 @@ extern "C" int gdrn_conv_fwd(const void* x_hi, const void* x_lo, const void* w_h
     p.out_f32 = y_f32;
     p.ldc = ldc;
     p.bias = bias;
+    p.res_hi = res_hi;
+    p.res_lo = res_lo;
     p.act = act;
     p.stats = stats;
     if (two_cta) return launch_gemm_2cta(p, nsplit, stream);

@@ -17,7 +17,9 @@ struct GemmParams {
     float* out_f32;
     int ldc;
     const float* bias;
-    int act;       // 0 none, 1 LeakyReLU(0.1)
+    const void* res_hi;  // optional residual [rows][ldc] (16-bit planes like the output) added before the activation:
+    const void* res_lo;  // the eval-mode folded conv + BN + (identity) + ReLU epilogue of a BasicBlock's second conv
+    int act;       // 0 none, 1 LeakyReLU(0.1), 2 ReLU
     float* stats;  // [2][N]: sum, sum of squares (accumulated with atomics) or nullptr
     int cluster;   // 1, or 2: CTA pairs share one n_tile and each TMA-multicasts half of the weight tile to both
     // Stride-2 dgrad by output-parity phases (mode 1, nphase > 0): rows index the (n, i, j) lattice of dY; phase ph writes

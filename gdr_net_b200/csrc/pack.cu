@@ -49,6 +49,8 @@ struct PackJob {
     long so, si, sr, ss;
     long elem_begin;  // prefix sum of the job's tile counts: ceil(opad/16) * ceil(ipad/64) * ceil(taps/9)
     int O, I, KH, KW, opad, ipad, krow, flip;
+    const float* row_scale;  // optional [O]: dst row o is multiplied by row_scale[o] -- the eval-mode BatchNorm scale
+                             // gamma / sqrt(running_var + eps) folded into the conv weights (NS-1: folded conv+BN+ReLU)
 };
 
 constexpr int kPackDR = 16;  // dst rows per tile
@@ -103,7 +105,10 @@ __global__ void __launch_bounds__(256) pack_weight_batched_kernel(const PackJob*
             const int dr = chan_fast ? (q / kPackDC) : (q % kPackDR);
             const int o = dr0 + dr, i = dc0 + dc;
             float v = 0.f;
-            if (o < job.O && i < job.I) v = __ldg(job.src + o * job.so + i * job.si + tapoff[tl]);
+            if (o < job.O && i < job.I) {
+                v = __ldg(job.src + o * job.so + i * job.si + tapoff[tl]);
+                if (job.row_scale != nullptr) v *= __ldg(job.row_scale + o);
+            }
             tile[(dr * kPackTC + tl) * kPackLD + dc] = v;
         }
         __syncthreads();
@@ -265,28 +270,37 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
     }
     __syncthreads();
     const long row0 = ((long)b * Ho + oh) * Wo;
-    for (int item = threadIdx.x; item < Wo * 24; item += 256) {
-        const int ow = item / 24, g = item - ow * 24;
-        float v[8];
+    // thread = (k-group g of 8 consecutive k, lane l over output columns): the eight (c, r, s) tile offsets of a group are
+    // computed ONCE (the first version redid two integer divisions per element: ALU-bound at 2.3x the store time); a warp
+    // still writes 32 consecutive 16-byte groups = 512 contiguous bytes per plane.
+    if (threadIdx.x < 240) {
+        const int g = threadIdx.x % 24, l = threadIdx.x / 24;
+        int off[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int k = g * 8 + j;
-            float val = 0.f;
             if (k < 147) {
                 const int tap = k / 3, c = k - tap * 3;
                 const int r = tap / 7, s2 = tap - r * 7;
-                val = tile[c][r][2 * ow + s2];
+                off[j] = (c * 7 + r) * WP + s2;
+            } else {
+                off[j] = -1;
             }
-            v[j] = val;
         }
-        uint32_t hi[4], lo[4];
+        const float* tf = &tile[0][0][0];
+        for (int ow = l; ow < Wo; ow += 10) {
+            float v[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+            for (int j = 0; j < 8; ++j) v[j] = off[j] >= 0 ? tf[off[j] + 2 * ow] : 0.f;
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+            }
+            const long idx = (row0 + ow) * 24 + g;
+            reinterpret_cast<uint4*>(a_hi)[idx] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (a_lo != nullptr) reinterpret_cast<uint4*>(a_lo)[idx] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-        const long idx = (row0 + ow) * 24 + g;
-        reinterpret_cast<uint4*>(a_hi)[idx] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        if (a_lo != nullptr) reinterpret_cast<uint4*>(a_lo)[idx] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
@@ -365,7 +379,7 @@ extern "C" int gdrn_stem_im2col(const float* x, void* a_hi, void* a_lo, int B, i
 
 extern "C" int gdrn_pack_weight_batched(const void* jobs_dev, int njobs, long total_blocks, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    static_assert(sizeof(PackJob) == 96, "PackJob layout is mirrored by the host (gdr_net_b200/engine.py)");
+    static_assert(sizeof(PackJob) == 104, "PackJob layout is mirrored by the host (gdr_net_b200/engine.py)");
     if (njobs <= 0) return 0;
     long grid = total_blocks;
     const long cap = (long)num_sms() * 16;

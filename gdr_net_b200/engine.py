@@ -30,6 +30,8 @@ _DGRAD_ZERO_INSERT = os.environ.get("GDRN_DGRAD_ZERO_INSERT") == "1"  # A/B swit
 # MEASURED (same box, graphed step): 11.39-11.47 ms with the recompute vs 11.11-11.33 ms reading y -- 2 B/element less HBM
 # traffic does not pay for the extra per-element FMA + compare + shared-memory constants, so it is off.
 _BN_MASK_FROM_U = os.environ.get("GDRN_BN_MASK_FROM_U") == "1"
+# A/B switch: BatchNorm forward emits the ReLU mask as a bitmap that backward reads instead of the activation (default on)
+_BN_BITMASK = os.environ.get("GDRN_BN_BITMASK", "1") == "1"
 
 LOSS_NAMES = ["loss_coor_x", "loss_coor_y", "loss_coor_z", "loss_mask", "loss_region", "loss_PM_R", "loss_centroid", "loss_z"]
 HEAD_CONVS = [(3, 4, False), (6, 7, False), (10, 11, True), (13, 14, False), (17, 18, True), (20, 21, False)]
@@ -111,6 +113,7 @@ class Engine:
             raise RuntimeError("gdr_net_b200 engine needs CUDA parameters (model.to('cuda')); no CPU fallback exists")
         self.ws = ops.Workspace(self.dev)
         self.sym_table = SymTable(self.dev)
+        self.fold_eval = os.environ.get("GDRN_NO_FOLD_EVAL") != "1"  # A/B switch: eval forward through the unfused train-path kernels
         self.with_2d = int(model.pnp_net.features[0].in_channels == 69)  # 69 = xyz + coord2d + regions, 67 without coords
         assert model.pnp_net.features[0].in_channels in (67, 69), model.pnp_net.features[0].in_channels
         self.named_params = list(model.named_parameters())
@@ -190,12 +193,12 @@ class Engine:
                 ops._pack_recorder = None
             dt = np.dtype([("src", "<u8"), ("hi", "<u8"), ("lo", "<u8"), ("so", "<i8"), ("si", "<i8"), ("sr", "<i8"), ("ss", "<i8"),
                            ("begin", "<i8"), ("O", "<i4"), ("I", "<i4"), ("KH", "<i4"), ("KW", "<i4"), ("opad", "<i4"),
-                           ("ipad", "<i4"), ("krow", "<i4"), ("flip", "<i4")])
-            assert dt.itemsize == 96
+                           ("ipad", "<i4"), ("krow", "<i4"), ("flip", "<i4"), ("row_scale", "<u8")])
+            assert dt.itemsize == 104
             arr = np.zeros(len(jobs), dtype=dt)
             begin = 0
             for n, (src, out, O, I, KH, KW, opad, ipad, krow, so, si, sr, ss, flip) in enumerate(jobs):
-                arr[n] = (src.data_ptr(), out.hi_ptr, out.lo_ptr or 0, so, si, sr, ss, begin, O, I, KH, KW, opad, ipad, krow, flip)
+                arr[n] = (src.data_ptr(), out.hi_ptr, out.lo_ptr or 0, so, si, sr, ss, begin, O, I, KH, KW, opad, ipad, krow, flip, 0)
                 begin += -(-opad // 16) * -(-ipad // 64) * -(-(KH * KW) // 9)  # tiles of 16 rows x 64 channels x 9 taps (pack.cu)
             tab = dict(jobs=torch.from_numpy(arr.view(np.uint8).copy()).to(self.dev), njobs=len(jobs), blocks=begin,
                        keep=[j[0] for j in jobs] + [j[1] for j in jobs])  # sources and destinations stay alive with the table
@@ -204,6 +207,146 @@ class Engine:
             torch.cat([self.model.pnp_net.fc_r.weight, self.model.pnp_net.fc_t.weight], 0, out=self.w_rt)
             torch.cat([self.model.pnp_net.fc_r.bias, self.model.pnp_net.fc_t.bias], 0, out=self.b_rt)
         C.gdrn_pack_weight_batched(tab["jobs"].data_ptr(), tab["njobs"], tab["blocks"], _stream())
+
+    # ------------------------------------------------------------------------------------------ eval: folded conv+BN+ReLU
+    # (conv key, BatchNorm key) of every conv that is followed by a BatchNorm, in forward order
+    def _conv_bn_pairs(self):
+        m = self.model
+        out = [("stem", "backbone.bn1")]
+        for li in range(1, 5):
+            for bi, blk in enumerate(getattr(m.backbone, f"layer{li}")):
+                p = f"backbone.layer{li}.{bi}"
+                out += [(p + ".conv1", p + ".bn1"), (p + ".conv2", p + ".bn2")]
+                if blk.downsample is not None:
+                    out.append((p + ".downsample.0", p + ".downsample.1"))
+        out.append(("deconv", "rot_head_net.features.1"))
+        out += [(f"rot_head_net.features.{ci}", f"rot_head_net.features.{bi}") for ci, bi, _u in HEAD_CONVS]
+        return out
+
+    def prepare_weights_folded(self):
+        """Inference operands: eval-mode BatchNorm folded into the conv weights (scale, at pack time) and the conv epilogue
+        (shift as bias), so conv + BN (+ identity) + ReLU is ONE kernel per layer.  Two launches per forward:
+        gdrn_bn_fold_batched (all layers' scale / shift from the running statistics) and one batched weight pack."""
+        import numpy as np
+
+        key = tuple(p.data_ptr() for _, p in self.named_params)
+        fold = getattr(self, "_fold", None)
+        if fold is None or fold["key"] != key:
+            pl = self.planes
+            pairs = self._conv_bn_pairs()
+            convs = dict(self._conv_modules())
+            wfe, sc, sh = {}, {}, {}
+            fdt = np.dtype([("gamma", "<u8"), ("beta", "<u8"), ("mean", "<u8"), ("var", "<u8"), ("scale", "<u8"), ("shift", "<u8"),
+                            ("C", "<i4"), ("eps", "<f4"), ("pad", "<i8")])
+            assert fdt.itemsize == 64
+            farr = np.zeros(len(pairs), dtype=fdt)
+            for n, (ck, bk) in enumerate(pairs):
+                mod = self._bn_mods[bk]
+                sc[bk] = torch.empty(mod.num_features, device=self.dev)
+                sh[bk] = torch.empty(mod.num_features, device=self.dev)
+                farr[n] = (mod.weight.data_ptr(), mod.bias.data_ptr(), mod.running_mean.data_ptr(), mod.running_var.data_ptr(),
+                           sc[bk].data_ptr(), sh[bk].data_ptr(), mod.num_features, float(mod.eps), 0)
+            ops._pack_recorder = []
+            try:
+                scales = []
+                for ck, bk in pairs:
+                    if ck == "stem":
+                        w = self.model.backbone.conv1.weight
+                        wfe[ck] = PT((64, 192), pl, device=self.dev, zero=True)
+                        ops._pack(w, wfe[ck], 64, 3, 7, 7, 64, 3, 192, 147, 49, 7, 1, 0)
+                    elif ck == "deconv":
+                        wfe[ck] = ops.pack_deconv_fwd(self.model.rot_head_net.features[0].weight, pl)
+                    else:
+                        wfe[ck] = ops.pack_conv_fwd(convs[ck].weight, pl)
+                    scales.append(sc[bk])
+                jobs = ops._pack_recorder
+            finally:
+                ops._pack_recorder = None
+            dt = np.dtype([("src", "<u8"), ("hi", "<u8"), ("lo", "<u8"), ("so", "<i8"), ("si", "<i8"), ("sr", "<i8"), ("ss", "<i8"),
+                           ("begin", "<i8"), ("O", "<i4"), ("I", "<i4"), ("KH", "<i4"), ("KW", "<i4"), ("opad", "<i4"),
+                           ("ipad", "<i4"), ("krow", "<i4"), ("flip", "<i4"), ("row_scale", "<u8")])
+            assert dt.itemsize == 104
+            arr = np.zeros(len(jobs), dtype=dt)
+            begin = 0
+            for n, (src, out, O, I, KH, KW, opad, ipad, krow, so, si, sr, ss, flip) in enumerate(jobs):
+                arr[n] = (src.data_ptr(), out.hi_ptr, out.lo_ptr or 0, so, si, sr, ss, begin, O, I, KH, KW, opad, ipad, krow, flip,
+                          scales[n].data_ptr())
+                begin += -(-opad // 16) * -(-ipad // 64) * -(-(KH * KW) // 9)
+            fold = self._fold = dict(key=key, wf=wfe, scale=sc, shift=sh, njobs=len(jobs), blocks=begin, nfold=len(pairs),
+                                     fjobs=torch.from_numpy(farr.view(np.uint8).copy()).to(self.dev),
+                                     jobs=torch.from_numpy(arr.view(np.uint8).copy()).to(self.dev), keep=[j[0] for j in jobs])
+        C.gdrn_bn_fold_batched(fold["fjobs"].data_ptr(), fold["nfold"], _stream())
+        C.gdrn_pack_weight_batched(fold["jobs"].data_ptr(), fold["njobs"], fold["blocks"], _stream())
+        return fold
+
+    def forward_eval_folded(self, x: torch.Tensor, aux: dict, want_maps: bool = False) -> dict:
+        """Inference forward (reference caller gdrn_evaluator.py:568-580) with every conv + BatchNorm (+ residual) + ReLU
+        fused into the GEMM epilogue: no BatchNorm pass, no pre-activation tensor in HBM."""
+        m, pl, dev = self.model, self.planes, self.dev
+        B = x.shape[0]
+        assert x.shape[1:] == (3, 256, 256), x.shape
+        self.prepare_weights(need_dgrad=False)  # head 1x1 / Patch-PnP / FC operands (no BatchNorm behind them)
+        F = self.prepare_weights_folded()
+        wfe, shift = F["wf"], F["shift"]
+
+        def cbr(xin, ck, bk, conv, relu=True, res=None, kind="conv"):
+            if kind == "deconv":
+                return ops.conv_fwd(xin, wfe[ck], conv.out_channels, 3, 3, 1, 1, bias=shift[bk], act=2 if relu else 0, res=res,
+                                    algo_scale=0.25)
+            k, stride, pad = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+            return ops.conv_fwd(xin, wfe[ck], conv.out_channels, k, k, stride, pad, bias=shift[bk], act=2 if relu else 0, res=res)
+
+        a_col = PT((B * 128 * 128, 192), pl, device=dev)
+        C.gdrn_stem_im2col(x.data_ptr(), a_col.hi_ptr, a_col.lo_ptr, B, 256, 256, _stream())
+        a0 = ops.gemm_fwd(a_col, wfe["stem"], 64, bias=shift["backbone.bn1"], act=2).view(B, 128, 128, 64)
+        cur = ops.maxpool_fwd(a0)
+        for li in range(1, 5):
+            for bi, blk in enumerate(getattr(m.backbone, f"layer{li}")):
+                p = f"backbone.layer{li}.{bi}"
+                a1 = cbr(cur, p + ".conv1", p + ".bn1", blk.conv1)
+                idn = cur
+                if blk.downsample is not None:
+                    idn = cbr(cur, p + ".downsample.0", p + ".downsample.1", blk.downsample[0], relu=False)
+                cur = cbr(a1, p + ".conv2", p + ".bn2", blk.conv2, res=idn)
+        hf = m.rot_head_net.features
+        cur = cbr(ops.zero_insert(cur), "deconv", "rot_head_net.features.1", hf[0], kind="deconv")
+        for ci, bi, up in HEAD_CONVS:
+            if up:
+                cur = ops.upsample2x_fwd(cur)
+            cur = cbr(cur, f"rot_head_net.features.{ci}", f"rot_head_net.features.{bi}", hf[ci])
+        return self._tail_inference(cur, aux, want_maps)
+
+    def _tail_inference(self, head_in: PT, aux: dict, want_maps: bool) -> dict:
+        """1x1 output conv -> glue -> Patch-PnP -> test-time pose decode (shared by the folded and the plain eval forward)."""
+        m, pl, dev = self.model, self.planes, self.dev
+        B = head_in.shape[0]
+        hf, pn, pf = m.rot_head_net.features, m.pnp_net, m.pnp_net.features
+        logits = torch.empty(B * 4096, 72, device=dev)
+        ops.conv_fwd(head_in, self.wf["rot_head_net.features.23"], 69, 1, 1, 1, 0, out_f32=logits, bias=hf[23].bias, ldc=72,
+                     want_planes=False)
+        pnp_in = PT((B, 64, 64, 128), pl, device=dev)
+        C.gdrn_head_glue_fwd(logits.data_ptr(), ops.ptr(aux.get("roi_coord_2d")), aux["roi_extents"].data_ptr(), pnp_in.hi_ptr,
+                             pnp_in.lo_ptr, B, 4096, self.with_2d, _stream())
+        cur = pnp_in
+        for ci, gi in ((0, 1), (3, 4), (6, 7)):
+            u = ops.conv_fwd(cur, self.wf[f"pnp_net.features.{ci}"], 128, 3, 3, 2, 1)
+            gstats = torch.empty(B, 32, 2, device=dev)
+            cur = ops.gn_relu_fwd(u, pf[gi].weight, pf[gi].bias, gstats, G=pf[gi].num_groups, eps=pf[gi].eps)
+        h1 = ops.gemm_fwd(cur.view(B, 8192), self.wf["fc1"], 1024, bias=pn.fc1.bias, act=1)
+        h2 = ops.gemm_fwd(h1, self.wf["fc2"], 256, bias=pn.fc2.bias, act=1)
+        pred = torch.zeros(B, 16, device=dev)
+        ops.gemm_fwd(h2, self.wf["fc_rt"], 9, out_f32=pred, bias=self.b_rt, ldc=16, want_planes=False)
+        out_rot = torch.empty(B, 3, 3, device=dev)
+        out_trans = torch.empty(B, 3, device=dev)
+        C.gdrn_pose_loss(pred.data_ptr(), 16, aux["roi_cams"].data_ptr(), aux["roi_centers"].data_ptr(),
+                         aux["roi_whs"].data_ptr(), aux["resize_ratios"].data_ptr(), aux["roi_extents"].data_ptr(), None,
+                         None, None, None, None, None, None, out_rot.data_ptr(), out_trans.data_ptr(), None, None, None,
+                         None, B, 0, 0, 0.0, _stream())
+        res = dict(rot=out_rot, trans=out_trans, pred=pred, logits=logits)
+        if want_maps:
+            maps = logits.view(B, 64, 64, 72).permute(0, 3, 1, 2)
+            res.update(mask=maps[:, 0:1], coor_x=maps[:, 1:2], coor_y=maps[:, 2:3], coor_z=maps[:, 3:4], region=maps[:, 4:69])
+        return res
 
     def _prepare_weights_calls(self, need_dgrad: bool):
         m, pl, bpl = self.model, self.planes, self.bplanes
@@ -239,6 +382,9 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------ building blocks
     def _bn_fwd(self, key: str, u: PT, relu: bool, train_bn: bool, res: Optional[PT] = None) -> PT:
+        """y = [relu](bn(u) [+ res]).  When the step keeps activations for backward (`self._want_masks`) and relu is set, the
+        kernel also emits the ReLU mask as one BIT per element (self._last_mask): BatchNorm backward then reads 1/8 byte
+        instead of the 2-byte activation per element in both of its passes."""
         mod, st = self._bn_mods[key], self.bn[key]
         Cc = mod.num_features
         count = u.numel() // Cc
@@ -246,10 +392,14 @@ class Engine:
         if train_bn and mod.num_batches_tracked is not None:
             self._nbt.append(mod.num_batches_tracked)
         y = ops.like(u)
+        mask = None
+        if relu and getattr(self, "_want_masks", False) and _BN_BITMASK:
+            mask = torch.empty(u.numel() // 8, dtype=torch.uint8, device=self.dev)
+        self._last_mask = mask
         C.gdrn_bn_fwd(u.hi_ptr, u.lo_ptr, res.hi_ptr if res else None, res.lo_ptr if res else None, y.hi_ptr, y.lo_ptr,
                       ops.ptr(st.stats) if train_bn else None, mod.weight.data_ptr(), mod.bias.data_ptr(),
-                      mod.running_mean.data_ptr(), mod.running_var.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), count, Cc,
-                      float(mod.eps), float(mom), int(train_bn), int(relu), _stream())
+                      mod.running_mean.data_ptr(), mod.running_var.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
+                      ops.ptr(mask), count, Cc, float(mod.eps), float(mom), int(train_bn), int(relu), _stream())
         return y
 
     def _conv_bn(self, x: PT, ckey: str, conv, bkey: str, relu: bool, train_bn: bool, res: Optional[PT] = None,
@@ -301,6 +451,8 @@ class Engine:
         x = x.to(self.dev).float().contiguous()
         if not do_loss:
             with torch.no_grad():
+                if not train_bn and self.fold_eval:  # inference: conv + BN (+ identity) + ReLU fused per layer
+                    return self.forward_eval_folded(x, aux, want_maps=want_maps)
                 return self.forward(x, aux, train_bn=train_bn, do_loss=False, want_maps=want_maps)
         params = [p for _, p in self.named_params]
         losses, vis = _GDRNFunction.apply(self, x, aux, train_bn, *params)
@@ -315,6 +467,7 @@ class Engine:
         if train_bn:
             self.stats_all.zero_()
         S = dict(B=B, train_bn=train_bn) if do_loss else None
+        self._want_masks = do_loss
 
         # ---- a1: backbone (resnet_backbone.py:69-76)
         a_col = PT((B * 128 * 128, 192), pl, device=dev)
@@ -324,7 +477,7 @@ class Engine:
         a0 = self._bn_fwd("backbone.bn1", u0, True, train_bn)
         if S is not None:
             cur, pool_arg = ops.maxpool_fwd(a0, want_arg=True)
-            S["stem"] = dict(a_col=a_col, u0=u0, a0=a0, pool_arg=pool_arg)
+            S["stem"] = dict(a_col=a_col, u0=u0, a0=a0, pool_arg=pool_arg, m0=self._last_mask)
             S["blocks"] = []
         else:
             cur = ops.maxpool_fwd(a0)
@@ -332,6 +485,7 @@ class Engine:
             for bi, blk in enumerate(getattr(m.backbone, f"layer{li}")):
                 p = f"backbone.layer{li}.{bi}"
                 u1, a1 = self._conv_bn(cur, p + ".conv1", blk.conv1, p + ".bn1", True, train_bn)
+                m1 = self._last_mask
                 ud = None
                 if blk.downsample is not None:
                     ud, idn = self._conv_bn(cur, p + ".downsample.0", blk.downsample[0], p + ".downsample.1", False, train_bn)
@@ -339,7 +493,7 @@ class Engine:
                     idn = cur
                 u2, out = self._conv_bn(a1, p + ".conv2", blk.conv2, p + ".bn2", True, train_bn, res=idn)
                 if S is not None:
-                    S["blocks"].append(dict(p=p, blk=blk, x_in=cur, u1=u1, a1=a1, u2=u2, out=out, ud=ud))
+                    S["blocks"].append(dict(p=p, blk=blk, x_in=cur, u1=u1, a1=a1, u2=u2, out=out, ud=ud, m1=m1, m2=self._last_mask))
                 cur = out
         feat = cur  # [B,8,8,512]
 
@@ -348,7 +502,7 @@ class Engine:
         z = ops.zero_insert(feat)
         u, y = self._conv_bn(z, "deconv", hf[0], "rot_head_net.features.1", True, train_bn, kind="deconv")
         if S is not None:
-            S["deconv"] = dict(z=z, u=u, y=y)
+            S["deconv"] = dict(z=z, u=u, y=y, m=self._last_mask)
             S["head"] = []
         cur = y
         for ci, bi, up in HEAD_CONVS:
@@ -356,7 +510,7 @@ class Engine:
                 cur = ops.upsample2x_fwd(cur)
             u, y = self._conv_bn(cur, f"rot_head_net.features.{ci}", hf[ci], f"rot_head_net.features.{bi}", True, train_bn)
             if S is not None:
-                S["head"].append(dict(ci=ci, bi=bi, up=up, x_in=cur, u=u, y=y))
+                S["head"].append(dict(ci=ci, bi=bi, up=up, x_in=cur, u=u, y=y, m=self._last_mask))
             cur = y
         head_in = cur  # [B,64,64,256]
         if self._nbt:
@@ -454,13 +608,14 @@ class Engine:
         z = ops.zero_insert(du) if stride == 2 else du
         return ops.conv_fwd(z, self.wd[wkey], conv.in_channels, k, k, 1, k - 1 - pad, algo_scale=0.25 if stride == 2 else 1.0)
 
-    def _bn_bwd(self, bkey: str, ga: PT, gb: Optional[PT], y: Optional[PT], u: PT, want_gout=False, relu_from_u=False):
-        """relu_from_u: conv-BN-ReLU without a residual -- the mask is recomputed from u (y is not read)."""
+    def _bn_bwd(self, bkey: str, ga: PT, gb: Optional[PT], y: Optional[PT], u: PT, want_gout=False, relu_from_u=False, mask=None):
+        """mask: the forward's ReLU bitmap (preferred); else the mask comes from the activation y, or (relu_from_u, A/B
+        switch) is recomputed from u for conv-BN-ReLU without a residual."""
         mod, st = self._bn_mods[bkey], self.bn[bkey]
-        relu_from_u = relu_from_u and _BN_MASK_FROM_U
-        return ops.bn_bwd(ga, gb, None if relu_from_u else y, u, st.mean, st.invstd, mod.weight, st.sums,
+        relu_from_u = relu_from_u and _BN_MASK_FROM_U and mask is None
+        return ops.bn_bwd(ga, gb, None if (relu_from_u or mask is not None) else y, u, st.mean, st.invstd, mod.weight, st.sums,
                           self.grads[bkey + ".weight"], self.grads[bkey + ".bias"], self.saved["train_bn"], want_gout=want_gout,
-                          beta=mod.bias, relu_from_u=relu_from_u, sums_zeroed=True)
+                          beta=mod.bias, relu_from_u=relu_from_u, sums_zeroed=True, relu_mask=mask)
 
     def backward(self, grad_losses: torch.Tensor):
         """grad_losses: [8] upstream gradients of LOSS_NAMES.  Fills self.grads (views of self.flat_grad)."""
@@ -529,13 +684,13 @@ class Engine:
         # ---- head convs (cdpn_rot_head_region.py:95-125)
         for L in reversed(S["head"]):
             ci, bi = L["ci"], L["bi"]
-            du, _ = self._bn_bwd(f"rot_head_net.features.{bi}", g, None, h(L["y"]), h(L["u"]), relu_from_u=True)
+            du, _ = self._bn_bwd(f"rot_head_net.features.{bi}", g, None, h(L["y"]), h(L["u"]), relu_from_u=True, mask=L["m"])
             self._wgrad_conv(du, h(L["x_in"]), hf[ci], f"rot_head_net.features.{ci}.weight")
             g = self._dgrad_conv(du, hf[ci], f"rot_head_net.features.{ci}")
             if L["up"]:
                 g = ops.upsample2x_bwd(g)
         D = S["deconv"]
-        du, _ = self._bn_bwd("rot_head_net.features.1", g, None, h(D["y"]), h(D["u"]), relu_from_u=True)
+        du, _ = self._bn_bwd("rot_head_net.features.1", g, None, h(D["y"]), h(D["u"]), relu_from_u=True, mask=D["m"])
         buf, ks, kss = ops.conv_wgrad(du, h(D["z"]), self.ws, 256, 3, 3, 1, 1)
         # ConvTranspose2d weight is IOHW [512][256][3][3] with flipped taps relative to the equivalent conv
         ops.unpack_wgrad(buf, self.grads["rot_head_net.features.0.weight"], 256, 512, 3, 3, 512, ks, kss, 9, 256 * 9, 3, 1, flip=1)
@@ -546,10 +701,10 @@ class Engine:
         ga, gb = g, None
         for Lb in reversed(S["blocks"]):
             p, blk = Lb["p"], Lb["blk"]
-            du2, gout = self._bn_bwd(p + ".bn2", ga, gb, h(Lb["out"]), h(Lb["u2"]), want_gout=True)
+            du2, gout = self._bn_bwd(p + ".bn2", ga, gb, h(Lb["out"]), h(Lb["u2"]), want_gout=True, mask=Lb["m2"])
             self._wgrad_conv(du2, h(Lb["a1"]), blk.conv2, p + ".conv2.weight")
             da1 = self._dgrad_conv(du2, blk.conv2, p + ".conv2")
-            du1, _ = self._bn_bwd(p + ".bn1", da1, None, h(Lb["a1"]), h(Lb["u1"]), relu_from_u=True)
+            du1, _ = self._bn_bwd(p + ".bn1", da1, None, h(Lb["a1"]), h(Lb["u1"]), relu_from_u=True, mask=Lb["m1"])
             self._wgrad_conv(du1, h(Lb["x_in"]), blk.conv1, p + ".conv1.weight")
             dx_main = self._dgrad_conv(du1, blk.conv1, p + ".conv1")
             if blk.downsample is not None:
@@ -564,7 +719,7 @@ class Engine:
         g_pool = ops.add2(ga, gb)
         St = S["stem"]
         g_a0 = ops.maxpool_bwd(St["pool_arg"], g_pool)
-        du0, _ = self._bn_bwd("backbone.bn1", g_a0, None, h(St["a0"]), h(St["u0"]), relu_from_u=True)
+        du0, _ = self._bn_bwd("backbone.bn1", g_a0, None, h(St["a0"]), h(St["u0"]), relu_from_u=True, mask=St["m0"])
         buf, ks, kss = ops.gemm_wgrad(du0.view(B * 128 * 128, 64), h(St["a_col"]), self.ws)
         # ws rows [64][192] with k = (r*7+s)*3 + c  ->  OIHW [64][3][7][7]
         ops.unpack_wgrad(buf, self.grads["backbone.conv1.weight"], 64, 3, 7, 7, 3, ks, kss, 147, 49, 7, 1, krow=192)

@@ -201,16 +201,18 @@ def pack_linear(w: torch.Tensor, planes: int, out: PT | None = None, nhwc_from: 
 # ---------------------------------------------------------------------------------------------
 def conv_fwd(x: PT, wp: PT, Cout: int, KH: int, KW: int, stride: int, pad: int, *, out: PT | None = None,
              out_f32: torch.Tensor | None = None, bias=None, stats=None, act: int = 0, ldc: int | None = None,
-             want_planes: bool = True, algo_scale: float = 1.0) -> PT | None:
-    """algo_scale: fraction of the launched MACs that are algorithmic (0.25 for zero-inserted inputs); bookkeeping only."""
+             want_planes: bool = True, algo_scale: float = 1.0, res: PT | None = None) -> PT | None:
+    """algo_scale: fraction of the launched MACs that are algorithmic (0.25 for zero-inserted inputs); bookkeeping only.
+    res: residual planes added in the epilogue before the activation (act 2 = ReLU): the folded eval-mode conv+BN+add+ReLU."""
     N, H, W, Cin = x.shape
     Ho, Wo = H // stride, W // stride
     ldc = ldc or _round_up(Cout, 64)
     if want_planes and out is None:
         out = PT((N, Ho, Wo, ldc), x.planes, device=x.buf.device, zero=(ldc != Cout))
     C.gdrn_conv_fwd(x.hi_ptr, x.lo_ptr, wp.hi_ptr, wp.lo_ptr, out.hi_ptr if out is not None else None,
-                    out.lo_ptr if out is not None else None, ptr(out_f32), ptr(bias), ptr(stats), N, H, W, Cin, Cout,
-                    wp.shape[0], KH, KW, stride, pad, ldc, act, x.nsplit, _stream())
+                    out.lo_ptr if out is not None else None, ptr(out_f32), ptr(bias), res.hi_ptr if res is not None else None,
+                    res.lo_ptr if res is not None else None, ptr(stats), N, H, W, Cin, Cout, wp.shape[0], KH, KW, stride, pad,
+                    ldc, act, x.nsplit, _stream())
     return out
 
 
@@ -307,7 +309,7 @@ def bn_act(x: PT, scale, shift, relu: bool, res: PT | None = None, out: PT | Non
 
 
 def bn_bwd(ga: PT, gb: PT | None, y: PT | None, u: PT, mean, invstd, gamma, sums, dgamma, dbeta, train: bool,
-           want_gout: bool = False, beta=None, relu_from_u: bool = False, sums_zeroed: bool = False):
+           want_gout: bool = False, beta=None, relu_from_u: bool = False, sums_zeroed: bool = False, relu_mask=None):
     """y: activation whose sign gives the ReLU mask (needed when a residual was added before the ReLU); relu_from_u: plain
     conv-BN-ReLU, the mask is recomputed from u and beta and y is not read."""
     du = like(u)
@@ -317,8 +319,8 @@ def bn_bwd(ga: PT, gb: PT | None, y: PT | None, u: PT, mean, invstd, gamma, sums
     assert not (relu_from_u and y is not None)
     C.gdrn_bn_bwd(ga.hi_ptr, ga.lo_ptr, gb.hi_ptr if gb else None, gb.lo_ptr if gb else None, y.hi_ptr if y else None,
                   u.hi_ptr, u.lo_ptr, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), ptr(beta), sums.data_ptr(), du.hi_ptr,
-                  du.lo_ptr, gout.hi_ptr if gout else None, gout.lo_ptr if gout else None, ptr(dgamma), ptr(dbeta), rows, Cc,
-                  int(train), (1 if relu_from_u else 0) | (2 if sums_zeroed else 0), _stream())
+                  du.lo_ptr, gout.hi_ptr if gout else None, gout.lo_ptr if gout else None, ptr(dgamma), ptr(dbeta), ptr(relu_mask),
+                  rows, Cc, int(train), (1 if relu_from_u else 0) | (2 if sums_zeroed else 0), _stream())
     return du, gout
 
 

@@ -37,12 +37,16 @@ int gdrn_last_gemm_variant(void); /* BLOCK_N*10 + nsplit of this thread's last c
  * replaces nn.Conv2d / nn.ConvTranspose2d forward: resnet_backbone.py:21-49,69-76 (torchvision BasicBlock),
  * cdpn_rot_head_region.py:82-135, conv_pnp_net.py:76-80.
  * x [N,H,W,Cin] (Cin % 64 == 0), w packed [Cout_pad][KH*KW*Cin] (gdrn_pack_weight), outputs row-major
- * [N*Ho*Wo][ldc]: bf16 planes (y_hi/y_lo) and/or fp32 (y_f32).  bias[Cout] / act (1 = LeakyReLU 0.1) optional.
+ * [N*Ho*Wo][ldc]: bf16 planes (y_hi/y_lo) and/or fp32 (y_f32).  bias[Cout] / act (1 = LeakyReLU 0.1, 2 = ReLU) optional;
+ * res_hi/res_lo: optional residual planes [N*Ho*Wo][ldc] added before the activation.  With BatchNorm folded into the
+ * weights (gdrn_bn_fold_batched + row_scale of the pack jobs) and bias = the folded shift this is the eval-mode fused
+ * conv + BN (+ identity) + ReLU of resnet_backbone.py:69-76 / torchvision BasicBlock / cdpn_rot_head_region.py:82-125.
  * stats (optional) [2][Cout] fp32 += per-channel sum and sum of squares of the fp32 accumulators
  * (BatchNorm batch statistics, reference get_norm("BN") layers). */
 int gdrn_conv_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, void* y_hi, void* y_lo,
-                  float* y_f32, const float* bias, float* stats, int N, int H, int W, int Cin, int Cout, int Cout_pad,
-                  int KH, int KW, int stride, int pad, int ldc, int act, int nsplit, void* stream);
+                  float* y_f32, const float* bias, const void* res_hi, const void* res_lo, float* stats, int N, int H, int W,
+                  int Cin, int Cout, int Cout_pad, int KH, int KW, int stride, int pad, int ldc, int act, int nsplit,
+                  void* stream);
 
 /* Data gradient of a stride-2 conv (k3 p1 / k1 p0) by output-parity phases over the un-dilated dY: replaces the reference's
  * cuDNN conv-backward-data for the stride-2 layers (resnet_backbone.py layerN.0.conv1 / downsample, conv_pnp_net.py:76-80).
@@ -69,7 +73,8 @@ int gdrn_gemm_wgrad(const void* dy_hi, const void* dy_lo, const void* x_hi, cons
  * Source layouts: Conv2d OIHW, ConvTranspose2d IOHW, Linear [out][in] (state_dict of the reference). */
 int gdrn_pack_weight(const float* src, void* dst_hi, void* dst_lo, int O, int I, int KH, int KW, int opad, int ipad,
                      int krow, long so, long si, long sr, long ss, int flip, void* stream);
-/* all per-step re-packs in one launch; jobs_dev = device array of 96-byte PackJob records (csrc/pack.cu) */
+/* all per-step re-packs in one launch; jobs_dev = device array of 104-byte PackJob records (csrc/pack.cu), each with an
+ * optional per-output-row scale (eval-mode BatchNorm folding) */
 int gdrn_pack_weight_batched(const void* jobs_dev, int njobs, long total_blocks, void* stream);
 int gdrn_unpack_wgrad(const float* ws, float* grad, int O, int I, int KH, int KW, int ipad, int krow, int ksplit, long ks_stride,
                       long so, long si, long sr, long ss, int flip, int accumulate, void* stream);
@@ -78,14 +83,19 @@ int gdrn_stem_im2col(const float* x, void* a_hi, void* a_lo, int B, int H, int W
 
 /* ---- BatchNorm2d(eps, momentum) train/eval (+ReLU, + residual add) and backward -- detectron2/torch
  * BatchNorm2d via core/utils/layer_utils.py:17-39; torchvision BasicBlock residual. */
+/* eval-mode folding of ALL BatchNorm layers in one launch: jobs = device array of 64-byte records {gamma, beta,
+ * running_mean, running_var, scale_out, shift_out (pointers); int C; float eps; long pad} */
+int gdrn_bn_fold_batched(const void* jobs_dev, int njobs, void* stream);
 int gdrn_bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
                      float* scale, float* shift, float* mean_out, float* invstd_out, int C, float count, float eps,
                      float momentum, int train, void* stream);
-/* finalize + apply in one kernel (what the engine uses): batch statistics from the conv epilogue -> y, running stats */
+/* finalize + apply in one kernel (what the engine uses): batch statistics from the conv epilogue -> y, running stats.
+ * relu_mask_out (optional, with relu): uint8 [rows*C/8], bit j of byte i = [pre-activation of element 8i+j > 0]; BatchNorm
+ * backward (relu_mask) reads it instead of the activation to rebuild the ReLU mask (1/8 B instead of 2 B per element). */
 int gdrn_bn_fwd(const void* x_hi, const void* x_lo, const void* r_hi, const void* r_lo, void* y_hi, void* y_lo,
                 const float* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
-                float* mean_out, float* invstd_out, long rows, int C, float eps, float momentum, int train, int relu,
-                void* stream);
+                float* mean_out, float* invstd_out, void* relu_mask_out, long rows, int C, float eps, float momentum, int train,
+                int relu, void* stream);
 int gdrn_bn_act(const void* x_hi, const void* x_lo, const void* r_hi, const void* r_lo, void* y_hi, void* y_lo,
                 const float* scale, const float* shift, long rows, int C, int relu, void* stream);
 /* flags: bit 0 = the ReLU mask is recomputed from u (plain conv-BN-ReLU: pass y_hi = NULL and beta); bit 1 = `sums` is
@@ -93,7 +103,7 @@ int gdrn_bn_act(const void* x_hi, const void* x_lo, const void* r_hi, const void
 int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_hi, const void* gb_lo, const void* y_hi,
                 const void* u_hi, const void* u_lo, const float* mean, const float* invstd, const float* gamma,
                 const float* beta, float* sums, void* du_hi, void* du_lo, void* gout_hi, void* gout_lo, float* dgamma,
-                float* dbeta, long rows, int C, int train, int flags, void* stream);
+                float* dbeta, const void* relu_mask, long rows, int C, int train, int flags, void* stream);
 
 /* ---- MaxPool2d(3,2,1) resnet_backbone.py:72; UpsamplingBilinear2d(x2) cdpn_rot_head_region.py:102;
  * zero insertion (stride-2 transposed convs); GroupNorm(32)+ReLU conv_pnp_net.py:76-80 */

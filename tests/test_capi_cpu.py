@@ -32,7 +32,7 @@ def test_abi_version_and_error_channel(dll):
 
 def test_argument_errors_do_not_need_a_gpu(dll):
     # argument validation happens on the host before any CUDA call: Cin not a multiple of 64
-    rc = dll.gdrn_conv_fwd(None, None, None, None, None, None, None, None, None, 1, 8, 8, 3, 64, 64, 3, 3, 1, 1, 64, 0, 1, None)
+    rc = dll.gdrn_conv_fwd(None, None, None, None, None, None, None, None, None, None, None, 1, 8, 8, 3, 64, 64, 3, 3, 1, 1, 64, 0, 1, None)
     assert rc == -1 and b"Cin" in dll.gdrn_last_error()
     rc = dll.gdrn_gemm_fwd(None, None, None, None, None, None, None, None, None, 4, 4, 64, 100, 8, 0, 1, None)
     assert rc == -1 and b"K=" in dll.gdrn_last_error()

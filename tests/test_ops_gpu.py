@@ -419,3 +419,44 @@ def test_scale_f32_unaligned_slices():
         ref[lo:hi] *= 0.5
     torch.cuda.synchronize()
     assert torch.equal(buf, ref)
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_bn_relu_bitmask_roundtrip(planes, with_res):
+    """bn_fwd emits the ReLU mask as one bit per element; bn_bwd fed with the bitmap (no activation read) gives the same du /
+    dgamma / dbeta as the path that re-derives the mask from the stored activation."""
+    from gdr_net_b200.capi import C
+
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(77)
+    N, H, C_ = 4, 16, 128
+    U = _nhwc(torch.randn(N, C_, H, H, device="cuda", generator=g) * 2 + 0.3, planes)
+    R = _nhwc(torch.randn(N, C_, H, H, device="cuda", generator=g), planes) if with_res else None
+    gamma = torch.rand(C_, device="cuda", generator=g) + 0.5
+    beta = torch.randn(C_, device="cuda", generator=g) * 0.3
+    rm, rv = torch.zeros(C_, device="cuda"), torch.ones(C_, device="cuda")
+    flat = U.float().reshape(-1, C_)
+    stats = torch.stack([flat.sum(0), (flat * flat).sum(0)]).contiguous()
+    mean, invstd = torch.empty(C_, device="cuda"), torch.empty(C_, device="cuda")
+    Y = ops.like(U)
+    mask = torch.zeros(U.numel() // 8, dtype=torch.uint8, device="cuda")
+    C.gdrn_bn_fwd(U.hi_ptr, U.lo_ptr, R.hi_ptr if R else None, R.lo_ptr if R else None, Y.hi_ptr, Y.lo_ptr, stats.data_ptr(),
+                  gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                  mask.data_ptr(), flat.shape[0], C_, 1e-5, 0.1, 1, 1, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    bits = ((mask.view(-1, 1) >> torch.arange(8, device="cuda", dtype=torch.uint8)) & 1).reshape(-1)
+    pos = (Y.float().reshape(-1) > 0)
+    # the bitmap is taken from the fp32 pre-activation: it can only differ where a tiny positive value rounds to a 16-bit zero
+    assert int((bits.bool() != pos).sum()) <= 2
+    GY = _nhwc(torch.randn(N, C_, H, H, device="cuda", generator=g), planes)
+    outs = []
+    for use_bits in (False, True):
+        sums = torch.zeros(2, C_, device="cuda")
+        dgamma, dbeta = torch.zeros(C_, device="cuda"), torch.zeros(C_, device="cuda")
+        DU, GOUT = ops.bn_bwd(GY, None, None if use_bits else Y, U, mean, invstd, gamma, sums, dgamma, dbeta, True, want_gout=True,
+                              sums_zeroed=True, relu_mask=mask if use_bits else None)
+        torch.cuda.synchronize()
+        outs.append((DU.float(), GOUT.float(), dgamma.clone(), dbeta.clone()))
+    assert int(((outs[0][0] - outs[1][0]).abs() > 1e-4).sum()) <= 4
+    assert _rel(outs[1][1], outs[0][1]) < 1e-3 and _rel(outs[1][2], outs[0][2]) < 5e-2 and _rel(outs[1][3], outs[0][3]) < 5e-2

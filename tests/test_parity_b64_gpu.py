@@ -279,3 +279,29 @@ def test_ycbv_b32_symmetric_pm_and_adds_parity():
         worst = max(worst, abs(a - b) / max(b, 1e-6))
     print(f"ycbv B=32 ADD(-S) worst relative deviation from the oracle: {worst:.2e}")
     assert worst <= 1e-3
+
+
+def test_eval_folded_bn_matches_unfused_and_oracle():
+    """NS-1: the inference path fuses conv + eval-BatchNorm (+ identity) + ReLU into the GEMM epilogue (BatchNorm scale folded
+    into the packed weights, shift as bias).  Same outputs as the unfused kernels and as the oracle (1e-3)."""
+    from oracle import fixtures
+    from oracle import gdrn_oracle as O
+
+    sd = fixtures.calibrated_state_dict(0)
+    batch_cpu = synth.make_batch(3, seed=61)
+    batch = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in batch_cpu.items()}
+    with torch.no_grad():
+        o = O.gdrn_forward(O.leaf_state_dict(sd, requires_grad=False), batch_cpu, train=False, do_loss=False)
+    outs = {}
+    for fold in (True, False):
+        model = _build("mixed", sd, use_pnp_test=True)
+        model.eval()
+        model.engine.fold_eval = fold
+        with torch.no_grad():
+            out = model(batch["roi_img"], **synth.forward_kwargs(batch, train=False))
+        torch.cuda.synchronize()
+        head = torch.cat([out["mask"], out["coor_x"], out["coor_y"], out["coor_z"], out["region"]], dim=1).cpu()
+        outs[fold] = (head, out["rot"].cpu(), out["trans"].cpu())
+        print(f"[fold={fold}] eval B=3 head rel-L2 vs oracle {_rel(head, o['head']):.2e} rot {_rel(out['rot'], o['rot']):.2e} trans {_rel(out['trans'], o['trans']):.2e}")
+        assert _rel(head, o["head"]) < REL and _rel(out["rot"], o["rot"]) < 2e-3 and _rel(out["trans"], o["trans"]) < 2e-3
+    assert _rel(outs[True][0], outs[False][0]) < 3e-4

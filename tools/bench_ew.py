@@ -28,7 +28,7 @@ for name, H, Cc in [("stem 128x128x64", 128, 64), ("layer1 64x64x64", 64, 64), (
     rows = B * H * H
     nbytes = u.numel() * 2
     t_fwd = timeit(lambda: C.gdrn_bn_fwd(u.hi_ptr, None, None, None, y.hi_ptr, None, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                        rm.data_ptr(), rv.data_ptr(), mean.data_ptr(), invstd.data_ptr(), rows, Cc, 1e-5, 0.1, 1, 1, _stream()))
+                                        rm.data_ptr(), rv.data_ptr(), mean.data_ptr(), invstd.data_ptr(), None, rows, Cc, 1e-5, 0.1, 1, 1, _stream()))
     scale = torch.ones(Cc, device="cuda"); shift = torch.zeros(Cc, device="cuda")
     t_act = timeit(lambda: ops.bn_act(u, scale, shift, True, out=y))
     t_bwd = timeit(lambda: ops.bn_bwd(g, None, y, u, mean, invstd, gamma, sums, dg, db, True))
