@@ -36,6 +36,26 @@ BATCH_PER_GPU = 64
 HEADLINE_MODE = os.environ.get("GDRN_BENCH_MODE", "mixed")  # the mode `value` / `e2e` are measured in
 
 
+def finish_distributed(world):
+    """End of a multi-rank run: one last barrier, then leave WITHOUT tearing the process group down.  The step graphs hold
+    captured NCCL kernels; destroy_process_group() with them alive was observed to hang the ranks after the result line had
+    been printed (r2, N=2), which would turn a finished run into a driver-side timeout.  A watchdog ends the process even if
+    the barrier itself stalls."""
+    sys.stdout.flush()
+    if world <= 1:
+        return
+    import torch.distributed as dist
+
+    threading.Timer(45.0, lambda: os._exit(0)).start()
+    try:
+        dist.barrier()
+        torch.cuda.synchronize()
+    except Exception:
+        pass
+    sys.stdout.flush()
+    os._exit(0)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -244,9 +264,7 @@ def run_ours(args):
     if args.quick:
         if rank == 0:
             print(json.dumps(out), flush=True)
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        finish_distributed(world)
         return
     if rank == 0 or world > 1:
         # ---- e2e through the public module API with pinned host inputs (H2D + D2H inside the timed region)
@@ -363,9 +381,7 @@ def run_ours(args):
             except Exception as e:  # pragma: no cover
                 out["cudnn_same_gpu"] = {"error": str(e)[:300]}
         print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    finish_distributed(world)
 
 
 def roofline_live(main, peaks):
@@ -569,9 +585,7 @@ def run_pnp(args):
             ms_e2e = float(tt)
         results[precision] = dict(ms=ms, ms_e2e=ms_e2e, rot=rot.cpu(), t=t.cpu(), clocks=clocks)
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        finish_distributed(world)
         return
     main = results["fp32x3"]
     # algorithmic work: Conv / Linear MACs x 2 with the true nIn; bytes = fp32 input maps + fp32 weights
@@ -635,9 +649,7 @@ def run_pnp(args):
                            "what": "the reference nn stack restated (F.conv2d / group_norm / linear, NCHW fp32, TF32 convs, cudnn.benchmark) on this GPU"},
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    finish_distributed(world)
 
 
 def inference_bench(B, dev, peaks, steps=20, warm=5):

@@ -23,7 +23,10 @@
 //     hi*hi + hi*lo + lo*hi (the lo*lo term, 2^-22 relative with fp16 planes, is dropped).
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "gdrn_internal.h"
+#include "gemm_epilogue.cuh"
 #include "gemm_params.h"
 #include "ptx.cuh"
 
@@ -423,8 +426,6 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
         const int grp = (warp - 4) >> 2;
         const int row = q * 32 + lane;
         float* tr = s_tr + (warp - 4) * (32 * 17);
-        __nv_bfloat16* out_hi = reinterpret_cast<__nv_bfloat16*>(p.out_hi);
-        __nv_bfloat16* out_lo = reinterpret_cast<__nv_bfloat16*>(p.out_lo);
         // One tile per CTA (small-M layers: 16x16 / 8x8 maps, FC): there is no second tile to overlap with, so both
         // warpgroups share the single tile's epilogue, each draining half of its column chunks.
         constexpr int NCH = BLOCK_N / 32;
@@ -444,154 +445,8 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const long mrow = (long)m_tile * kBlockM + row;
-            const bool row_ok = mrow < p.M;
-            const bool all_rows = (long)(m_tile + 1) * kBlockM <= p.M;
-            long grow = mrow;  // output row
-            if (p.nphase) {    // (n, i, j) of the dY lattice -> pixel (2i + a, 2j + b) of the 2x larger dX
-                const long j = mrow & ((1L << p.pw_log2) - 1);
-                const long t = mrow >> p.pw_log2;
-                const long i = t & ((1L << p.ph_log2) - 1);
-                const long n = t >> p.ph_log2;
-                grow = (((n << (p.ph_log2 + 1)) + 2 * i + p.ph_a[ph]) << (p.pw_log2 + 1)) + 2 * j + p.ph_b[ph];
-            }
-#pragma unroll 1
-            for (int c = c_begin; c < c_end; ++c) {
-                const int col0 = n_tile * BLOCK_N + c * 32;
-                if (col0 >= p.N) continue;  // warp-uniform
-                float f[32];
-                {
-                    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::NACC * BLOCK_N + c * 32;
-                    uint32_t raw[32];
-                    tmem_ld_32x32(t0, raw);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(raw[j]);
-                    if (NSPLIT == 3) {
-                        const int nmain = p.num_kb < Cfg::NMAIN ? p.num_kb : Cfg::NMAIN;
-                        for (int a2 = 1; a2 <= Cfg::NMAIN; ++a2) {
-                            if (a2 < Cfg::NMAIN && a2 >= nmain) continue;  // partial never written (tiny K)
-                            tmem_ld_32x32(t0 + a2 * BLOCK_N, raw);
-                            tmem_ld_wait();
-                            const float sc = (a2 == Cfg::NMAIN) ? kLoInvScale : 1.f;  // cross terms carry the lo-plane scale
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(raw[j]), sc, f[j]);
-                        }
-                    }
-                }
-                const bool full_chunk = (col0 + 32 <= p.N);
-                if (p.bias != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (full_chunk || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
-                }
-                if (p.res_hi != nullptr && row_ok && full_chunk) {
-                    // folded eval epilogue: + residual (the block's identity / downsample branch, same [rows][ldc] planes)
-                    const __nv_bfloat16* rh = reinterpret_cast<const __nv_bfloat16*>(p.res_hi) + grow * p.ldc + col0;
-                    const __nv_bfloat16* rl = p.res_lo ? reinterpret_cast<const __nv_bfloat16*>(p.res_lo) + grow * p.ldc + col0 : nullptr;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint4 q = __ldg(reinterpret_cast<const uint4*>(rh) + j);
-                        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            float a, b;
-                            unpack_hi2(w[t], a, b);
-                            f[8 * j + 2 * t] += a;
-                            f[8 * j + 2 * t + 1] += b;
-                        }
-                        if (rl != nullptr) {
-                            const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(rl) + j);
-                            const uint32_t w2[4] = {q2.x, q2.y, q2.z, q2.w};
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                float a, b;
-                                unpack_lo2(w2[t], a, b);
-                                f[8 * j + 2 * t] += a;
-                                f[8 * j + 2 * t + 1] += b;
-                            }
-                        }
-                    }
-                }
-                if (p.act == 1) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : 0.1f * f[j];
-                } else if (p.act == 2) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-                }
-                if (row_ok) {
-                    if (p.out_f32 != nullptr) {
-                        float* dst = p.out_f32 + grow * p.ldc + col0;
-                        if (full_chunk) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < p.ldc) dst[j] = (col0 + j < p.N) ? f[j] : 0.f;
-                        }
-                    }
-                    if (out_hi != nullptr) {
-                        uint32_t hi[16], lo[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float a = f[2 * j], b = f[2 * j + 1];
-                            if (!full_chunk) {
-                                if (col0 + 2 * j >= p.N) a = 0.f;
-                                if (col0 + 2 * j + 1 >= p.N) b = 0.f;
-                            }
-                            // single-plane outputs skip the residual (lo) plane arithmetic: the epilogue warps run alone on
-                            // their schedulers, so every instruction here is on the critical path of the small-K layers
-                            if (out_lo != nullptr) split2(a, b, hi[j], lo[j]); else hi[j] = pack_hi2(a, b);
-                        }
-                        const int ncopy = full_chunk ? 4 : ((min(p.ldc, col0 + 32) - col0) / 8);
-                        uint4* dh = reinterpret_cast<uint4*>(out_hi + grow * p.ldc + col0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (j < ncopy) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                        if (out_lo != nullptr) {
-                            uint4* dl = reinterpret_cast<uint4*>(out_lo + grow * p.ldc + col0);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (j < ncopy)
-                                    dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-                        }
-                    }
-                }
-                if (p.stats != nullptr) {
-                    // per-channel sum / sum of squares over this warp's 32 rows: transpose 16 columns at a time through a
-                    // padded smem tile (conflict-free), lane l then adds column (l & 15) over row half (l >> 4).
-                    // (A shuffle butterfly was latency-bound: ~60 dependent shuffles per chunk.)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (all_rows) {  // warp-uniform: every row of the tile is a valid pixel (no per-element select)
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) tr[lane * 17 + j] = f[h * 16 + j];
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) tr[lane * 17 + j] = row_ok ? f[h * 16 + j] : 0.f;
-                        }
-                        __syncwarp();
-                        float s1 = 0.f, s2 = 0.f;
-                        const int col = lane & 15, r0 = (lane >> 4) * 16;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float v = tr[(r0 + i) * 17 + col];
-                            s1 += v;
-                            s2 = fmaf(v, v, s2);
-                        }
-                        s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-                        s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-                        __syncwarp();
-                        if (lane < 16) {
-                            atomicAdd(&s_stats[c * 32 + h * 16 + lane], s1);
-                            atomicAdd(&s_stats[BLOCK_N + c * 32 + h * 16 + lane], s2);
-                        }
-                    }
-                }
-            }
+            gemm_epilogue_tile<BLOCK_N, NSPLIT, Cfg::NMAIN>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::NACC * BLOCK_N, lane, row,
+                                                            m_tile, n_tile, ph, c_begin, c_end, tr, s_stats);
             tc_fence_before();
             __syncwarp();
             if (lane == 0 && !(split_epi && grp == 1)) mbar_arrive(&tempty_bar[acc]);
@@ -688,19 +543,19 @@ static int pick_block_n(int n_pad, int nsplit, int num_m_tiles) {
     return -1;
 }
 
-// Optional CTA pairs (cluster of 2) that TMA-multicast the weight tile.  MEASURED SLOWER on B200 (64x64 256->256 conv:
-// 1250 -> 1066 TFLOP/s; whole step 12.36 -> 12.75 ms): the two CTAs' stage rings become coupled and the halved TMA boxes
-// cost more than the saved L2 traffic, so it is off unless GDRN_CLUSTER=2 is set (kept for round-2 experiments).
-// 2-CTA (cta_group::2) 256x256 tiles for wide layers (gemm_fwd2.cu); GDRN_2CTA=0 disables
-// MEASURED (B=64): no gain over the 1-CTA kernel (64x64 256->256: 1217 vs 1204 TFLOP/s; 16x16 and 32x32 layers slower),
-// so it is off by default -- the big layers already run at ~84 % of the measured sustained cuBLAS rate.
+// 2-CTA (cta_group::2) pair tiles (gemm_fwd2.cu): 256 x 256 (1 pass) / 256 x 128 (3 pass).  Each CTA stages only half of the
+// weight tile, which takes the kernel off its shared-memory-bandwidth limit (see the header of gemm_fwd2.cu).
+// GDRN_2CTA=0 disables (A/B); layers with an odd tile count or less than half a wave of pair tiles keep the 1-CTA kernel.
 static int g_2cta_mode = -1;
-static bool want_2cta(int nsplit, int block_n, int num_m_tiles) {
+static std::atomic<long> g_2cta_launches{0};
+static bool want_2cta(int nsplit, int block_n, int num_m_tiles, int num_n_tiles) {
     if (g_2cta_mode < 0) {
         const char* e = getenv("GDRN_2CTA");
-        g_2cta_mode = e ? atoi(e) : 0;
+        g_2cta_mode = e ? atoi(e) : 1;
     }
-    return g_2cta_mode == 1 && nsplit == 1 && block_n == 256 && num_m_tiles % 2 == 0 && num_m_tiles >= 2;
+    if (g_2cta_mode != 1 || (num_m_tiles & 1)) return false;
+    if (!((nsplit == 1 && block_n == 256) || (nsplit == 3 && block_n == 128))) return false;
+    return (num_m_tiles / 2) * num_n_tiles * 4 >= num_sms();
 }
 
 static int pick_cluster(int num_m_tiles) {
@@ -717,11 +572,12 @@ static int pick_cluster(int num_m_tiles) {
 
 using namespace gdrn;
 
-// experiment switch: 1 = use the cta_group::2 256x256-tile kernel (gemm_fwd2.cu) for eligible layers
+// A/B switch: 1 = cta_group::2 pair tiles (gemm_fwd2.cu) for eligible layers (default), 0 = 1-CTA kernel everywhere
 extern "C" int gdrn_set_2cta(int on) {
     g_2cta_mode = on ? 1 : 0;
     return 0;
 }
+extern "C" long gdrn_2cta_launch_count() { return gdrn::g_2cta_launches.load(); }
 
 extern "C" int gdrn_conv_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, void* y_hi,
                              void* y_lo, float* y_f32, const float* bias, const void* res_hi, const void* res_lo, float* stats,
@@ -748,7 +604,7 @@ extern "C" int gdrn_conv_fwd(const void* x_hi, const void* x_lo, const void* w_h
 
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    const bool two_cta = want_2cta(nsplit, block_n, (N * Ho * Wo + 127) / 128);
+    const bool two_cta = want_2cta(nsplit, block_n, (N * Ho * Wo + 127) / 128, Cout_pad / block_n);
     const int cluster = two_cta ? 2 : pick_cluster((N * Ho * Wo + 127) / 128);  // weight box = block_n / cluster rows
     const int npl = nsplit == 1 ? 1 : 2;
     const void* xs[2] = {x_hi, x_lo};
@@ -792,7 +648,11 @@ extern "C" int gdrn_conv_fwd(const void* x_hi, const void* x_lo, const void* w_h
     p.res_lo = res_lo;
     p.act = act;
     p.stats = stats;
-    if (two_cta) return launch_gemm_2cta(p, nsplit, stream);
+    if (two_cta) {
+        g_2cta_launches.fetch_add(1, std::memory_order_relaxed);
+        g_last_variant = block_n * 10 + nsplit;
+        return launch_gemm_2cta(p, block_n, nsplit, stream);
+    }
     return dispatch_gemm(p, block_n, nsplit, stream);
 }
 

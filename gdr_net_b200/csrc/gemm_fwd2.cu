@@ -1,18 +1,25 @@
-// 2-CTA (tcgen05 cta_group::2) variant of the implicit-GEMM forward kernel: one 256 x 256 output tile per CTA PAIR.
+// 2-CTA (tcgen05 cta_group::2) variant of the implicit-GEMM forward kernel: one 256-row x BLOCK_N output tile per CTA PAIR.
 //
-// Why: with 128 x 256 tiles a single CTA must pull 16 KB (A) + 32 KB (B) per 64-deep k-block while the tensor core
-// needs only 512 cycles for it = 96 B/cycle/SM, more than an SM's ~64 B/cycle L2->smem ingress: the 1-CTA kernel tops
-// out at ~2/3 of the MMA rate (measured 57 % tensor-pipe, profiles/r1_ncu_full_kernel_metrics.txt).  In cta_group::2
-// mode the pair issues ONE 256x256x16 MMA whose A rows and B rows are split across the two CTAs' shared memories:
-// each CTA loads its own 128 pixels of A (16 KB) and only HALF of the weight tile (128 of 256 output channels, 16 KB)
-// = 64 B/cycle/SM.  Each CTA's TMEM receives the accumulator rows of its own 128 pixels, so the epilogue is unchanged.
+// Why: the 1-CTA kernel is SHARED-MEMORY-BANDWIDTH bound, not tensor-bound.  Per 64-deep k-block an SM's shared memory
+// serves the TMA writes of the stage AND the operand reads of every MMA (A 4 KB + B BLOCK_N*32 B per 16-wide k-step):
+//   1 pass, 128x256 tile : 48 KB written + 4 x 12 KB read  =  96 KB per 512 MMA cycles = 187 B/clk  (limit 128 B/clk)
+//   3 pass, 128x128 tile : 64 KB written + 4 x 24 KB read  = 160 KB per 768 MMA cycles = 208 B/clk
+// which is exactly what round 1 measured (tensor pipe 70 % / the 3-pass kernel at 0.66 of peak).  In cta_group::2 mode the
+// pair issues ONE 256 x BLOCK_N x 16 MMA whose A rows AND B rows are split across the two CTAs' shared memories: each CTA
+// stages (and its tensor core reads) its own 128 pixels of A but only HALF of the weight tile:
+//   1 pass, pair 256x256 : 32 KB written + 4 x  8 KB read  =  64 KB per 512 MMA cycles = 125 B/clk
+//   3 pass, pair 256x128 : 48 KB written + 4 x 18 KB read  = 120 KB per 768 MMA cycles = 156 B/clk
+// (Round 1's first 2-CTA experiment showed no gain because it still had the slow single-lane producer / issuer loops; this
+// version has the warp-uniform lean loops of gemm_fwd.cu.)
 //
-//   * both CTAs: TMA producer (own A box, own half of B) -- complete_tx lands on the LEADER's full barrier
-//   * leader CTA only: MMA issuer (tcgen05.mma.cta_group::2), commits are multicast to both CTAs' barriers
-//   * both CTAs: epilogue warpgroups; the peer's warps arrive remotely on the leader's tmem-empty barrier
+//   * both CTAs : TMA producer warp (own A box, own half of B; complete_tx lands on the LEADER's full barrier)
+//   * leader CTA: MMA issuer warp (tcgen05.mma.cta_group::2); commits are multicast to both CTAs' barriers
+//   * both CTAs : two epilogue warpgroups (shared code: gemm_epilogue.cuh); peers arrive remotely on the leader's
+//                 tmem-empty barrier.  Each CTA's TMEM receives the accumulator rows of its own 128 pixels.
 #include <stdlib.h>
 
 #include "gdrn_internal.h"
+#include "gemm_epilogue.cuh"
 #include "gemm_params.h"
 #include "ptx.cuh"
 
@@ -20,41 +27,40 @@ namespace gdrn {
 
 namespace {
 
-constexpr int kBM = 128;       // rows per CTA (256 per pair)
-constexpr int kBN = 256;       // tile width (128 weight rows per CTA)
+constexpr int kBM = 128;  // rows per CTA (256 per pair)
 constexpr int kBK = 64;
-constexpr int kEpi = 8;        // epilogue warps per CTA
+constexpr int kEpi = 8;  // epilogue warps per CTA
 constexpr int kTr = kEpi * 32 * 17 * 4;
 constexpr int kAux = 4096 + kTr;
 
-template <int NSPLIT>
+template <int BLOCK_N, int NSPLIT>
 struct Cfg2 {
     static constexpr int NPL = (NSPLIT == 1) ? 1 : 2;
-    static constexpr int A_BYTES = kBM * kBK * 2;        // 16 KB
-    static constexpr int B_BYTES = (kBN / 2) * kBK * 2;  // 16 KB: this CTA's half of the weight tile
+    static constexpr int A_BYTES = kBM * kBK * 2;            // 16 KB per plane
+    static constexpr int B_BYTES = (BLOCK_N / 2) * kBK * 2;  // this CTA's half of the weight tile, per plane
     static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
     static constexpr int STAGES_RAW = (227 * 1024 - kAux - 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kAux + 1024;
-    static constexpr int TMEM_COLS = 512;  // two 256-column accumulator buffers
-    static_assert(NSPLIT == 1, "2-CTA tiles are used by the single-plane mode only (TMEM: 2 x 256 columns)");
+    static constexpr int NACC = (NSPLIT == 3) ? 2 : 1;  // main (+ cross-term) accumulator
+    static constexpr int TMEM_COLS = 2 * NACC * BLOCK_N;
+    static_assert(TMEM_COLS == 512, "two accumulator sets fill the 512 TMEM columns");
+    static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
-__device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* leader_bar, int c0, int c1) {
-    // executed by both CTAs of the pair; clearing the peer bit of the barrier address makes the bytes count on CTA 0's barrier
-    const uint32_t bar = smem_u32(leader_bar) & 0xFEFFFFFFu;
+// cp.async.bulk.tensor issued by EITHER CTA of the pair; the transaction bytes are counted on the LEADER's barrier
+// (`bar` = shared::cluster address of CTA 0's mbarrier)
+__device__ __forceinline__ void tma2_load_2d_u32(uint32_t dst, uint64_t tmap, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
-__device__ __forceinline__ void tma2_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* leader_bar, int c0, int c1, int c2,
-                                             int c3) {
-    const uint32_t bar = smem_u32(leader_bar) & 0xFEFFFFFFu;
+__device__ __forceinline__ void tma2_load_4d_u32(uint32_t dst, uint64_t tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
         "[%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 __device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -65,9 +71,8 @@ __device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t desc_a, uint64_t
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void umma2_commit(uint64_t* bar) {  // arrives on this barrier offset in BOTH CTAs
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                     smem_u32(bar)),
+__device__ __forceinline__ void umma2_commit_u32(uint32_t bar) {  // arrives on this barrier offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                  "h"((uint16_t)3)
                  : "memory");
 }
@@ -79,18 +84,24 @@ __device__ __forceinline__ void mbar_arrive_cta0(uint64_t* bar) {  // arrive on 
         ::"r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ uint32_t mapa_cta0(uint32_t saddr) {  // shared::cluster address of the same offset in CTA 0
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(saddr));
+    return r;
+}
 
-template <int NSPLIT>
+template <int BLOCK_N, int NSPLIT>
 __global__ void __launch_bounds__(128 + 32 * kEpi, 1) gemm_fwd2_kernel(const __grid_constant__ GemmParams p) {
-    using Cfg = Cfg2<NSPLIT>;
+    using Cfg = Cfg2<BLOCK_N, NSPLIT>;
+    constexpr int NPL = Cfg::NPL;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);  // used in the leader only
     uint64_t* empty_bar = full_bar + STAGES;                // per CTA: "this stage may be refilled"
     uint64_t* tfull_bar = empty_bar + STAGES;               // per CTA: accumulator buffer complete
-    uint64_t* tempty_bar = tfull_bar + 2;                   // leader only: both CTAs drained the buffer (8 warps)
+    uint64_t* tempty_bar = tfull_bar + 2;                   // leader only: both CTAs drained the buffer (2 x 4 warps)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     float* s_stats = reinterpret_cast<float*>(aux + 512);
     float* s_tr = reinterpret_cast<float*>(aux + 4096);
@@ -103,8 +114,10 @@ __global__ void __launch_bounds__(128 + 32 * kEpi, 1) gemm_fwd2_kernel(const __g
     const int num_groups = (p.num_m_tiles / 2) * p.num_n_tiles;  // (pair of m_tiles, n_tile)
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&p.tmB[0]);
-        tma_prefetch_desc(&p.tmA[0][0]);
+        for (int pl = 0; pl < NPL; ++pl) {
+            tma_prefetch_desc(&p.tmB[pl]);
+            tma_prefetch_desc(&p.tmA[pl][0]);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -122,7 +135,7 @@ __global__ void __launch_bounds__(128 + 32 * kEpi, 1) gemm_fwd2_kernel(const __g
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < 2 * kBN; i += blockDim.x) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) s_stats[i] = 0.f;
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
@@ -130,42 +143,76 @@ __global__ void __launch_bounds__(128 + 32 * kEpi, 1) gemm_fwd2_kernel(const __g
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer (both CTAs)
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int grp = my_pair; grp < num_groups; grp += num_pairs) {
-                const int n_tile = grp % p.num_n_tiles;
-                const int m_tile = (grp / p.num_n_tiles) * 2 + (int)crank;
+        // ------------------------------------------------------------------ TMA producer (both CTAs, whole warp, one lane issues)
+        const uint32_t smem_base = smem_u32(smem), empty0 = smem_u32(empty_bar);
+        const uint32_t full0_local = smem_u32(full_bar);
+        const uint32_t full0 = mapa_cta0(full0_local);  // the LEADER's full barriers, as shared::cluster addresses
+        const uint64_t tmB0 = reinterpret_cast<uint64_t>(&p.tmB[0]), tmB1 = reinterpret_cast<uint64_t>(&p.tmB[1]);
+        const int cch = p.cchunks, mode = p.mode, KWv = p.KW, padv = p.pad, stride2 = (p.stride == 2);
+        const int ntap = mode == 1 ? p.num_kb / (cch > 0 ? cch : 1) : 0;
+        const int brow = (int)crank * (BLOCK_N / 2);  // this CTA's half of the weight tile
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int grp = my_pair; grp < num_groups; grp += num_pairs) {
+            const int n_tile = grp % p.num_n_tiles;
+            const int m_tile = (grp / p.num_n_tiles) * 2 + (int)crank;
+            const int bn0 = n_tile * BLOCK_N + brow;
+            if (mode == 1) {
                 int n0 = 0, h0 = 0;
-                if (p.mode == 1) {
-                    if (p.TN == 1) {
-                        n0 = m_tile / p.tiles_per_img;
-                        h0 = (m_tile % p.tiles_per_img) * p.TH;
-                    } else {
-                        n0 = m_tile * p.TN;
+                if (p.TN == 1) {
+                    n0 = m_tile / p.tiles_per_img;
+                    h0 = (m_tile - n0 * p.tiles_per_img) * p.TH;
+                } else {
+                    n0 = m_tile * p.TN;
+                }
+                int r = 0, s2 = 0;
+                for (int t = 0; t < ntap; ++t) {
+                    int dh = r - padv, dw = s2 - padv, map = 0;
+                    if (stride2) {
+                        map = ((dh & 1) << 1) | (dw & 1);
+                        dh >>= 1;  // arithmetic shift == floor division
+                        dw >>= 1;
+                    }
+                    if (++s2 == KWv) {
+                        s2 = 0;
+                        ++r;
+                    }
+                    const uint64_t tmA0 = reinterpret_cast<uint64_t>(&p.tmA[0][map]);
+                    const uint64_t tmA1 = reinterpret_cast<uint64_t>(&p.tmA[1][map]);
+                    const int hh = h0 + dh;
+                    int kw = t * cch * kBK;
+                    for (int cc = 0; cc < cch; ++cc, kw += kBK) {
+                        const uint32_t fb = full0 + stage * 8, dst = smem_base + stage * Cfg::STAGE_BYTES;
+                        mbar_wait_u32(empty0 + stage * 8, phase ^ 1);
+                        if (elect_one()) {
+                            if (leader) mbar_arrive_expect_tx_u32(full0_local + stage * 8, 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes
+                            tma2_load_4d_u32(dst, tmA0, fb, cc * kBK, dw, hh, n0);
+                            if (NPL == 2) tma2_load_4d_u32(dst + Cfg::A_BYTES, tmA1, fb, cc * kBK, dw, hh, n0);
+                            tma2_load_2d_u32(dst + NPL * Cfg::A_BYTES, tmB0, fb, kw, bn0);
+                            if (NPL == 2) tma2_load_2d_u32(dst + NPL * Cfg::A_BYTES + Cfg::B_BYTES, tmB1, fb, kw, bn0);
+                        }
+                        __syncwarp();
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
                     }
                 }
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes
-                    uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
-                    if (p.mode == 1) {
-                        const int tap = kb / p.cchunks;
-                        const int cc = kb - tap * p.cchunks;
-                        const int r = tap / p.KW;
-                        const int s = tap - r * p.KW;
-                        int dh = r - p.pad, dw = s - p.pad, map = 0;
-                        if (p.stride == 2) {
-                            map = ((dh & 1) << 1) | (dw & 1);
-                            dh >>= 1;
-                            dw >>= 1;
-                        }
-                        tma2_load_4d(st, &p.tmA[0][map], &full_bar[stage], cc * kBK, dw, h0 + dh, n0);
-                    } else {
-                        tma2_load_2d(st, &p.tmA[0][0], &full_bar[stage], kb * kBK, m_tile * kBM);
+            } else {
+                const uint64_t tmA0 = reinterpret_cast<uint64_t>(&p.tmA[0][0]);
+                const uint64_t tmA1 = reinterpret_cast<uint64_t>(&p.tmA[1][0]);
+                const int row0 = m_tile * kBM;
+                for (int kb = 0, kc = 0; kb < p.num_kb; ++kb, kc += kBK) {
+                    const uint32_t fb = full0 + stage * 8, dst = smem_base + stage * Cfg::STAGE_BYTES;
+                    mbar_wait_u32(empty0 + stage * 8, phase ^ 1);
+                    if (elect_one()) {
+                        if (leader) mbar_arrive_expect_tx_u32(full0_local + stage * 8, 2 * Cfg::STAGE_BYTES);
+                        tma2_load_2d_u32(dst, tmA0, fb, kc, row0);
+                        if (NPL == 2) tma2_load_2d_u32(dst + Cfg::A_BYTES, tmA1, fb, kc, row0);
+                        tma2_load_2d_u32(dst + NPL * Cfg::A_BYTES, tmB0, fb, kc, bn0);
+                        if (NPL == 2) tma2_load_2d_u32(dst + NPL * Cfg::A_BYTES + Cfg::B_BYTES, tmB1, fb, kc, bn0);
                     }
-                    tma2_load_2d(st + Cfg::A_BYTES, &p.tmB[0], &full_bar[stage], kb * kBK, n_tile * kBN + (int)crank * (kBN / 2));
+                    __syncwarp();
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -174,36 +221,52 @@ __global__ void __launch_bounds__(128 + 32 * kEpi, 1) gemm_fwd2_kernel(const __g
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
-        if (leader && lane == 0) {
-            constexpr uint32_t idesc = make_idesc(256, kBN, 0, 0);
+        // ------------------------------------------------------------------ MMA issuer (leader CTA, whole warp, one lane issues)
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc(256, BLOCK_N, 0, 0);
+            const uint64_t desc_const = make_smem_desc(0, 16, 1024);
+            const uint32_t smem_base = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+            const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
+            const int nkb = p.num_kb;
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
             for (int grp = my_pair; grp < num_groups; grp += num_pairs, ++it) {
                 const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                mbar_wait_u32(tempty0 + acc * 8, ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * kBN;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                const uint32_t d_main = tmem_base + acc * Cfg::NACC * BLOCK_N;
+                const uint32_t d_cross = d_main + BLOCK_N;
+                uint32_t accum = 0;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint64_t da = desc_const | (uint64_t)(a_addr >> 4);
+                    const uint64_t db = da + ((NPL * Cfg::A_BYTES) >> 4);
+                    mbar_wait_u32(full0 + stage * 8, phase);
                     tc_fence_after();
-                    const uint32_t a_s = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint32_t b_s = a_s + Cfg::A_BYTES;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < kBK / 16; ++k) {
-                        const uint64_t da = make_smem_desc(a_s + k * 32, 16, 1024);
-                        const uint64_t db = make_smem_desc(b_s + k * 32, 16, 1024);
-                        umma2(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < kBK / 16; ++k) {
+                            const uint32_t ac = (k == 0) ? accum : 1u;
+                            if (NSPLIT == 3) {
+                                umma2(d_main, da + 2 * k, db + 2 * k, idesc, ac);                                // hi x hi
+                                umma2(d_cross, da + 2 * k, db + (Cfg::B_BYTES >> 4) + 2 * k, idesc, ac);          // hi x lo
+                                umma2(d_cross, da + (Cfg::A_BYTES >> 4) + 2 * k, db + 2 * k, idesc, 1u);          // lo x hi
+                            } else {
+                                umma2(d_main, da + 2 * k, db + 2 * k, idesc, ac);
+                            }
+                        }
+                        umma2_commit_u32(empty0 + stage * 8);  // stage free in BOTH CTAs once these MMAs retire
                     }
-                    umma2_commit(&empty_bar[stage]);  // stage free in both CTAs once these MMAs retire
+                    __syncwarp();
+                    accum = 1u;
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma2_commit(&tfull_bar[acc]);  // accumulator complete -> both CTAs' epilogues
+                if (elect_one()) umma2_commit_u32(tfull0 + acc * 8);  // accumulator complete -> both CTAs' epilogues
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
@@ -212,7 +275,6 @@ __global__ void __launch_bounds__(128 + 32 * kEpi, 1) gemm_fwd2_kernel(const __g
         const int grp2 = (warp - 4) >> 2;
         const int row = q * 32 + lane;
         float* tr = s_tr + (warp - 4) * (32 * 17);
-        __nv_bfloat16* out_hi = reinterpret_cast<__nv_bfloat16*>(p.out_hi);
         for (int tg = my_pair + grp2 * num_pairs, it = grp2; tg < num_groups; tg += 2 * num_pairs, it += 2) {
             const int n_tile = tg % p.num_n_tiles;
             const int m_tile = (tg / p.num_n_tiles) * 2 + (int)crank;
@@ -220,85 +282,8 @@ __global__ void __launch_bounds__(128 + 32 * kEpi, 1) gemm_fwd2_kernel(const __g
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const long grow = (long)m_tile * kBM + row;
-            const bool row_ok = grow < p.M;
-#pragma unroll 1
-            for (int c = 0; c < kBN / 32; ++c) {
-                const int col0 = n_tile * kBN + c * 32;
-                if (col0 >= p.N) continue;
-                float f[32];
-                {
-                    uint32_t raw[32];
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kBN + c * 32, raw);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(raw[j]);
-                }
-                const bool full_chunk = (col0 + 32 <= p.N);
-                if (p.bias != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (full_chunk || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
-                }
-                if (p.act == 1) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : 0.1f * f[j];
-                }
-                if (row_ok) {
-                    if (p.out_f32 != nullptr) {
-                        float* dst = p.out_f32 + grow * p.ldc + col0;
-                        if (full_chunk) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < p.ldc) dst[j] = (col0 + j < p.N) ? f[j] : 0.f;
-                        }
-                    }
-                    if (out_hi != nullptr) {
-                        uint32_t hi[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float a = f[2 * j], b = f[2 * j + 1];
-                            if (!full_chunk) {
-                                if (col0 + 2 * j >= p.N) a = 0.f;
-                                if (col0 + 2 * j + 1 >= p.N) b = 0.f;
-                            }
-                            hi[j] = pack_hi2(a, b);
-                        }
-                        const int ncopy = full_chunk ? 4 : ((min(p.ldc, col0 + 32) - col0) / 8);
-                        uint4* dh = reinterpret_cast<uint4*>(out_hi + grow * p.ldc + col0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (j < ncopy) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                    }
-                }
-                if (p.stats != nullptr) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) tr[lane * 17 + j] = row_ok ? f[h * 16 + j] : 0.f;
-                        __syncwarp();
-                        float s1 = 0.f, s2 = 0.f;
-                        const int col = lane & 15, r0 = (lane >> 4) * 16;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float v = tr[(r0 + i) * 17 + col];
-                            s1 += v;
-                            s2 = fmaf(v, v, s2);
-                        }
-                        s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-                        s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-                        __syncwarp();
-                        if (lane < 16) {
-                            atomicAdd(&s_stats[c * 32 + h * 16 + lane], s1);
-                            atomicAdd(&s_stats[kBN + c * 32 + h * 16 + lane], s2);
-                        }
-                    }
-                }
-            }
+            gemm_epilogue_tile<BLOCK_N, NSPLIT, 1>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::NACC * BLOCK_N, lane, row, m_tile,
+                                                   n_tile, 0, 0, BLOCK_N / 32, tr, s_stats);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -308,11 +293,11 @@ __global__ void __launch_bounds__(128 + 32 * kEpi, 1) gemm_fwd2_kernel(const __g
         if (p.stats != nullptr) {
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const int n_tile = my_pair % p.num_n_tiles;  // fixed per pair (num_pairs % num_n_tiles == 0)
-            for (int i = threadIdx.x - 128; i < kBN; i += 256) {
-                const int col = n_tile * kBN + i;
+            for (int i = threadIdx.x - 128; i < BLOCK_N; i += 256) {
+                const int col = n_tile * BLOCK_N + i;
                 if (col < p.N) {
                     atomicAdd(p.stats + col, s_stats[i]);
-                    atomicAdd(p.stats + p.N + col, s_stats[kBN + i]);
+                    atomicAdd(p.stats + p.N + col, s_stats[BLOCK_N + i]);
                 }
             }
         }
@@ -327,12 +312,10 @@ __global__ void __launch_bounds__(128 + 32 * kEpi, 1) gemm_fwd2_kernel(const __g
     }
 }
 
-}  // namespace
-
-int launch_gemm_2cta(const GemmParams& p, int nsplit, cudaStream_t stream) {
-    if (nsplit != 1) return set_error(GDRN_ERR_ARG, "2-CTA tiles: single-plane mode only");
-    using Cfg = Cfg2<1>;
-    auto kern = gemm_fwd2_kernel<1>;
+template <int BLOCK_N, int NSPLIT>
+int launch2(const GemmParams& p, cudaStream_t stream) {
+    using Cfg = Cfg2<BLOCK_N, NSPLIT>;
+    auto kern = gemm_fwd2_kernel<BLOCK_N, NSPLIT>;
     static bool attr_set = false;
     if (!attr_set) {
         GDRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -358,6 +341,17 @@ int launch_gemm_2cta(const GemmParams& p, int nsplit, cudaStream_t stream) {
     GDRN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
     count_launch();
     return 0;
+}
+
+}  // namespace
+
+// block_n is the PAIR tile width: 256 (1 pass) or 128 (3 pass); p.num_n_tiles = Cout_pad / block_n, p.num_m_tiles even,
+// weight tensor maps with boxes of block_n / 2 rows (each CTA loads its half), p.nphase == 0.
+int launch_gemm_2cta(const GemmParams& p, int block_n, int nsplit, cudaStream_t stream) {
+    if (p.nphase != 0 || (p.num_m_tiles & 1)) return set_error(GDRN_ERR_ARG, "2-CTA tiles: even tile count, no phase decomposition");
+    if (nsplit == 1 && block_n == 256) return launch2<256, 1>(p, stream);
+    if (nsplit == 3 && block_n == 128) return launch2<128, 3>(p, stream);
+    return set_error(GDRN_ERR_ARG, "2-CTA tiles: unsupported block_n=%d nsplit=%d", block_n, nsplit);
 }
 
 }  // namespace gdrn

@@ -34,6 +34,6 @@ struct GemmParams {
 };
 
 
-int launch_gemm_2cta(const GemmParams& p, int nsplit, cudaStream_t stream);  // gemm_fwd2.cu
+int launch_gemm_2cta(const GemmParams& p, int block_n, int nsplit, cudaStream_t stream);  // gemm_fwd2.cu (block_n = pair tile width)
 
 }  // namespace gdrn

@@ -30,7 +30,8 @@ long gdrn_launch_count(void); /* kernels launched by this library since load */
 int gdrn_abi_version(void);
 int gdrn_storage_format(void); /* 0: bf16 (hi, lo) planes; 1: fp16 planes, lo = fp16((x - hi) * gdrn_lo_scale()) */
 float gdrn_lo_scale(void);
-int gdrn_set_2cta(int on); /* experiment: cta_group::2 256x256 tiles for wide layers (default off: measured no faster) */
+int gdrn_set_2cta(int on); /* A/B: cta_group::2 pair tiles (256x256 1-pass / 256x128 3-pass) for eligible conv layers; default on */
+long gdrn_2cta_launch_count(void); /* launches of the 2-CTA kernel since load */
 int gdrn_last_gemm_variant(void); /* BLOCK_N*10 + nsplit of this thread's last conv/gemm forward launch */
 
 /* ---- tcgen05 implicit-GEMM convolution, forward (and dgrad with flipped/transposed weights) ------------

@@ -226,7 +226,7 @@ def closest_rot_batch(pred_rots: Tensor, gt_rots: Tensor, sym_infos: List[Option
             if e < best:
                 best, best_R = e, cand
         out[i] = best_R
-    return torch.tensor(out, dtype=gt_rots.dtype)
+    return torch.tensor(out, dtype=gt_rots.dtype, device=gt_rots.device)  # pose_utils.py:481
 
 
 # --------------------------------------------------------------------------------------

@@ -104,27 +104,39 @@ def test_conv_fwd(planes, case):
         assert _rel(stats[1], s2) < 1e-4
 
 
-def test_conv_fwd_2cta_variant():
-    """The cta_group::2 kernel (256x256 tile per CTA pair) on a layer wide and large enough to select it."""
+@pytest.mark.parametrize("planes,case", [(1, (8, 64, 256, 256, 1)), (2, (8, 64, 256, 256, 1)), (1, (16, 32, 128, 256, 1)),
+                                         (2, (16, 32, 128, 128, 1)), (2, (16, 64, 64, 128, 2)), (1, (64, 32, 256, 512, 2))])
+def test_conv_fwd_2cta_variant(planes, case):
+    """The cta_group::2 kernel (one 256 x 256 [1 pass] / 256 x 128 [3 pass] tile per CTA pair) on layers that select it,
+    against the 1-CTA kernel's reference AND bit-compared with the 1-CTA kernel itself (same MMAs, same accumulation order)."""
     ops = _ops()
     from gdr_net_b200.capi import C
 
-    g = torch.Generator(device="cuda").manual_seed(77)
-    N, H, Cin, Cout = 8, 64, 256, 256
+    dll = C.load()
+    N, H, Cin, Cout, stride = case
+    g = torch.Generator(device="cuda").manual_seed(77 + sum(case))
     x = torch.randn(N, Cin, H, H, device="cuda", generator=g)
-    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / 48
-    X, Wp = _nhwc(x, 1), ops.pack_conv_fwd(w, 1)
-    out32 = torch.zeros(N, H, H, Cout, device="cuda")
-    stats = torch.zeros(2, Cout, device="cuda")
-    C.gdrn_set_2cta(1)
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / math.sqrt(9 * Cin)
+    X, Wp = _nhwc(x, planes), ops.pack_conv_fwd(w, planes)
+    Ho = H // stride
+    outs = []
     try:
-        ops.conv_fwd(X, Wp, Cout, 3, 3, 1, 1, out_f32=out32, stats=stats, want_planes=False)
-        torch.cuda.synchronize()
+        for mode in (1, 0):
+            C.gdrn_set_2cta(mode)
+            out32 = torch.zeros(N, Ho, Ho, Cout, device="cuda")
+            stats = torch.zeros(2, Cout, device="cuda")
+            n0 = dll.gdrn_2cta_launch_count()
+            Y = ops.conv_fwd(X, Wp, Cout, 3, 3, stride, 1, out_f32=out32, stats=stats)
+            torch.cuda.synchronize()
+            if mode == 1:
+                assert dll.gdrn_2cta_launch_count() == n0 + 1, "the shape did not select the 2-CTA kernel"
+            outs.append((out32, stats, Y.float()))
     finally:
-        C.gdrn_set_2cta(0)
-    ref = F.conv2d(_operand(x, 1), _operand(w, 1), None, padding=1).permute(0, 2, 3, 1)
-    assert _rel(out32, ref) < TOL[1]
-    assert _rel(stats[1], (ref.reshape(-1, Cout) ** 2).sum(0)) < 1e-4
+        C.gdrn_set_2cta(1)
+    ref = F.conv2d(_operand(x, planes), _operand(w, planes), None, stride=stride, padding=1).permute(0, 2, 3, 1)
+    assert _rel(outs[0][0], ref) < TOL[planes]
+    assert _rel(outs[0][1][1], (ref.reshape(-1, Cout) ** 2).sum(0)) < 1e-4
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][2], outs[1][2])  # identical arithmetic in both kernels
 
 
 @pytest.mark.parametrize("planes", [1, 2])

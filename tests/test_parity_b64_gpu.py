@@ -264,7 +264,8 @@ def test_ycbv_b32_symmetric_pm_and_adds_parity():
         print(f"ycbv B=32 {k}: {float(v):.6f} vs {ref:.6f}")
         assert abs(float(v) - ref) <= REL * abs(ref), (k, float(v), ref)
     assert model.engine.sym_table.rows == 628 + 628 + 2 + 2 + 4 + 2 + 4 or model.engine.sym_table.rows <= 1270  # each object uploaded once
-    # ADD(-S) of the eval-mode poses
+    # ADD(-S) of the eval-mode poses (a fresh model: the two train steps above moved the BatchNorm running statistics)
+    model = _build("mixed", sd, pm_loss_sym=True)
     model.eval()
     with torch.no_grad():
         out = model(batch["roi_img"], **synth.forward_kwargs(batch, train=False))
