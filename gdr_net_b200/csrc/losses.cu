@@ -46,104 +46,47 @@ __device__ __forceinline__ void load_logits(const float* __restrict__ logits, lo
 }
 
 // ------------------------------------------------------------------------------------------------
-// Coalesced access to the per-pixel rows (north_star: "coalesced/vectorised HBM reads").  A CTA of 128 threads owns 128
-// consecutive pixels.  Their logit rows (128 x 72 fp32 = 36.9 KB, contiguous in HBM) are copied into shared memory with
-// float4 loads whose addresses are consecutive ACROSS the warp (4 x 128-byte lines per load instruction instead of 32
-// different lines with one thread per row), each thread then reads ITS row from shared memory with conflict-free LDS.128
-// (row pitch 76 words: a quarter-warp's eight 16-byte accesses fall into eight different bank groups), and 16-bit output
-// rows go back the same way: written into the tile, then stored with 16-byte accesses consecutive across the warp.
-constexpr int kPixPerCta = 128;
-constexpr int kTilePitch = 76;  // floats per staged row (72 + 4)
-
-__device__ __forceinline__ void stage_logit_rows(const float* __restrict__ logits, long pix0, int npix, float* tile) {
-    const float4* src = reinterpret_cast<const float4*>(logits + pix0 * kLogitLd);
-    const int n4 = npix * (kLogitLd / 4);
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-        const int row = i / (kLogitLd / 4), c4 = i - row * (kLogitLd / 4);
-        *reinterpret_cast<float4*>(tile + row * kTilePitch + c4 * 4) = __ldg(src + i);
-    }
-}
-__device__ __forceinline__ void read_staged_row(const float* tile, int row, float (&z)[kLogitLd]) {
-#pragma unroll
-    for (int j = 0; j < kLogitLd / 4; ++j) {
-        const float4 q = *reinterpret_cast<const float4*>(tile + row * kTilePitch + 4 * j);
-        z[4 * j] = q.x;
-        z[4 * j + 1] = q.y;
-        z[4 * j + 2] = q.z;
-        z[4 * j + 3] = q.w;
-    }
-}
-__device__ __forceinline__ void write_staged_row(float* tile, int row, const float (&v)[kLogitLd]) {
-#pragma unroll
-    for (int j = 0; j < kLogitLd / 4; ++j)
-        *reinterpret_cast<float4*>(tile + row * kTilePitch + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-}
-// rows of 72 fp32 in the tile -> 128-channel 16-bit rows (channels >= 72 zero), 16-byte stores consecutive across the warp
-__device__ __forceinline__ void store_staged_rows_bf16(const float* tile, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
-                                                       long pix0, int npix) {
-    const int n16 = npix * (kPnpLd / 8);
-    for (int i = threadIdx.x; i < n16; i += blockDim.x) {
-        const int row = i / (kPnpLd / 8), g = i - row * (kPnpLd / 8);
-        uint4 h = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
-        if (g < kLogitLd / 8) {
-            const float4 a = *reinterpret_cast<const float4*>(tile + row * kTilePitch + 8 * g);
-            const float4 b = *reinterpret_cast<const float4*>(tile + row * kTilePitch + 8 * g + 4);
-            split2(a.x, a.y, h.x, l.x);
-            split2(a.z, a.w, h.y, l.y);
-            split2(b.x, b.y, h.z, l.z);
-            split2(b.z, b.w, h.w, l.w);
-        }
-        reinterpret_cast<uint4*>(out_hi + pix0 * kPnpLd)[i] = h;
-        if (out_lo != nullptr) reinterpret_cast<uint4*>(out_lo + pix0 * kPnpLd)[i] = l;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // W2D: the Patch-PnP input carries the 2-D crop coordinates (cfg PNP_NET.WITH_2D_COORD: 3 + 2 + 64 = 69 channels, region at
 // 5..68) or not (3 + 64 = 67 channels, region at 3..66) -- GDRN.py:171-173, :635-647
 template <bool W2D>
-__global__ void __launch_bounds__(kPixPerCta) head_glue_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ coord2d,
-                                                                   const float* __restrict__ extents, bf16* __restrict__ out_hi,
-                                                                   bf16* __restrict__ out_lo, int B, int HW) {
-    __shared__ __align__(16) float tile[kPixPerCta * kTilePitch];
+__global__ void __launch_bounds__(128) head_glue_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ coord2d,
+                                                            const float* __restrict__ extents, bf16* __restrict__ out_hi,
+                                                            bf16* __restrict__ out_lo, int B, int HW) {
     const long total = (long)B * HW;
-    for (long pix0 = (long)blockIdx.x * kPixPerCta; pix0 < total; pix0 += (long)gridDim.x * kPixPerCta) {
-        const int npix = (int)min((long)kPixPerCta, total - pix0);
-        __syncthreads();
-        stage_logit_rows(logits, pix0, npix, tile);
-        __syncthreads();
-        if ((int)threadIdx.x < npix) {
-            const long pix = pix0 + threadIdx.x;
-            const int b = (int)(pix / HW);
-            const int hw = (int)(pix - (long)b * HW);
-            float z[kLogitLd];
-            read_staged_row(tile, threadIdx.x, z);
-            float o[72];
+    for (long pix = blockIdx.x * (long)blockDim.x + threadIdx.x; pix < total; pix += (long)gridDim.x * blockDim.x) {
+        const int b = (int)(pix / HW);
+        const int hw = (int)(pix - (long)b * HW);
+        float z[kLogitLd];
+        load_logits(logits, pix, z);
+        float o[72];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) o[j] = (z[1 + j] - 0.5f) * __ldg(extents + b * 3 + j);
-            constexpr int RO = W2D ? 5 : 3;  // first region channel
-            if (W2D) {
-                o[3] = __ldg(coord2d + ((long)b * 2 + 0) * HW + hw);
-                o[4] = __ldg(coord2d + ((long)b * 2 + 1) * HW + hw);
-            }
-            float m = -INFINITY;
-#pragma unroll
-            for (int k = 0; k < kNumReg; ++k) m = fmaxf(m, z[5 + k]);
-            float s = 0.f;
-#pragma unroll
-            for (int k = 0; k < kNumReg; ++k) {
-                o[RO + k] = expf(z[5 + k] - m);
-                s += o[RO + k];
-            }
-            const float inv = 1.f / s;
-#pragma unroll
-            for (int k = 0; k < kNumReg; ++k) o[RO + k] *= inv;
-#pragma unroll
-            for (int k = RO + kNumReg; k < 72; ++k) o[k] = 0.f;
-            write_staged_row(tile, threadIdx.x, o);  // own row only: no hazard with the other threads' reads
+        for (int j = 0; j < 3; ++j) o[j] = (z[1 + j] - 0.5f) * __ldg(extents + b * 3 + j);
+        constexpr int RO = W2D ? 5 : 3;  // first region channel
+        if (W2D) {
+            o[3] = __ldg(coord2d + ((long)b * 2 + 0) * HW + hw);
+            o[4] = __ldg(coord2d + ((long)b * 2 + 1) * HW + hw);
         }
-        __syncthreads();
-        store_staged_rows_bf16(tile, out_hi, out_lo, pix0, npix);
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < kNumReg; ++k) m = fmaxf(m, z[5 + k]);
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < kNumReg; ++k) {
+            o[RO + k] = expf(z[5 + k] - m);
+            s += o[RO + k];
+        }
+        const float inv = 1.f / s;
+#pragma unroll
+        for (int k = 0; k < kNumReg; ++k) o[RO + k] *= inv;
+#pragma unroll
+        for (int k = RO + kNumReg; k < 72; ++k) o[k] = 0.f;
+        store_row_bf16(out_hi, out_lo, pix, kPnpLd, o, 72);
+        // zero the padding channels 72..127
+        const uint4 zz = make_uint4(0, 0, 0, 0);
+        for (int j = 72; j < kPnpLd; j += 8) {
+            *reinterpret_cast<uint4*>(out_hi + pix * kPnpLd + j) = zz;
+            if (out_lo != nullptr) *reinterpret_cast<uint4*>(out_lo + pix * kPnpLd + j) = zz;
+        }
     }
 }
 
@@ -186,20 +129,13 @@ __global__ void __launch_bounds__(128) pixel_loss_fwd_kernel(const float* __rest
                                                              const float* __restrict__ m_visib, const float* __restrict__ m_trunc,
                                                              const long long* __restrict__ labels, double* __restrict__ sums,
                                                              int B, int HW) {
-    __shared__ __align__(16) float tile[kPixPerCta * kTilePitch];
     const long total = (long)B * HW;
     float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (long pix0 = (long)blockIdx.x * kPixPerCta; pix0 < total; pix0 += (long)gridDim.x * kPixPerCta) {
-        const int npix = (int)min((long)kPixPerCta, total - pix0);
-        __syncthreads();
-        stage_logit_rows(logits, pix0, npix, tile);
-        __syncthreads();
-        if ((int)threadIdx.x >= npix) continue;
-        const long pix = pix0 + threadIdx.x;
+    for (long pix = blockIdx.x * (long)blockDim.x + threadIdx.x; pix < total; pix += (long)gridDim.x * blockDim.x) {
         const int b = (int)(pix / HW);
         const int hw = (int)(pix - (long)b * HW);
         float z[kLogitLd];
-        read_staged_row(tile, threadIdx.x, z);
+        load_logits(logits, pix, z);
         const float mv = __ldg(m_visib + pix), mt = __ldg(m_trunc + pix);
 #pragma unroll
         for (int j = 0; j < 3; ++j) acc[j] += fabsf(z[1 + j] * mv - __ldg(gt_xyz + ((long)b * 3 + j) * HW + hw) * mv);
@@ -241,22 +177,15 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ gw, const bf16* __restrict__ din_hi,
                                                        const bf16* __restrict__ din_lo, const float* __restrict__ extents,
                                                        bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int B, int HW) {
-    __shared__ __align__(16) float tile[kPixPerCta * kTilePitch];
     const long total = (long)B * HW;
     const float inv_fg = 1.f / fmaxf((float)sums[5], 1.f);
     const float inv_all = 1.f / (float)total;
     const float gwx = gw[0], gwy = gw[1], gwz = gw[2], gwm = gw[3], gwr = gw[4];
-    for (long pix0 = (long)blockIdx.x * kPixPerCta; pix0 < total; pix0 += (long)gridDim.x * kPixPerCta) {
-        const int npix = (int)min((long)kPixPerCta, total - pix0);
-        __syncthreads();
-        stage_logit_rows(logits, pix0, npix, tile);
-        __syncthreads();
-        const bool active = (int)threadIdx.x < npix;
-        const long pix = active ? pix0 + threadIdx.x : pix0;
+    for (long pix = blockIdx.x * (long)blockDim.x + threadIdx.x; pix < total; pix += (long)gridDim.x * blockDim.x) {
         const int b = (int)(pix / HW);
         const int hw = (int)(pix - (long)b * HW);
         float z[kLogitLd];
-        read_staged_row(tile, active ? threadIdx.x : 0, z);
+        load_logits(logits, pix, z);
         const float mv = __ldg(m_visib + pix), mt = __ldg(m_trunc + pix);
         float d[72];
         // mask channel: L1 mean
@@ -338,10 +267,12 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__
             for (int k = 0; k < kNumReg; ++k) d[5 + k] += pk[k] * (gin[RO + k] - dot);
         }
         d[69] = d[70] = d[71] = 0.f;
-        __syncthreads();  // every thread has consumed its staged logits row
-        if (active) write_staged_row(tile, threadIdx.x, d);
-        __syncthreads();
-        store_staged_rows_bf16(tile, out_hi, out_lo, pix0, npix);
+        store_row_bf16(out_hi, out_lo, pix, kPnpLd, d, 72);
+        const uint4 zz = make_uint4(0, 0, 0, 0);
+        for (int j = 72; j < kPnpLd; j += 8) {
+            *reinterpret_cast<uint4*>(out_hi + pix * kPnpLd + j) = zz;
+            if (out_lo != nullptr) *reinterpret_cast<uint4*>(out_lo + pix * kPnpLd + j) = zz;
+        }
     }
 }
 
