@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(kBnBwdThreads, 3) bn_bwd_reduce_kernel(
     const bf16* __restrict__ gb_lo, const bf16* __restrict__ y_hi, const bf16* __restrict__ u_hi,
     const bf16* __restrict__ u_lo, const float* __restrict__ mean, const float* __restrict__ invstd,
     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ sums, long rows, int C,
-    const uint8_t* __restrict__ mask_in) {
+    const uint8_t* __restrict__ mask_in, float* __restrict__ partial_out) {
     // block = (C/8) channel groups x rpb row lanes
     const int cg = C / 8;
     const int rpb = kBnBwdThreads / cg;  // cg in {8,16,32,64}: always divides 256
@@ -617,8 +617,60 @@ __global__ void __launch_bounds__(kBnBwdThreads, 3) bn_bwd_reduce_kernel(
         const int gg = c / 8, j = c % 8;
         float a = 0.f;
         for (int q = 0; q < rpb; ++q) a += red[which][q * cg + gg][j];
-        atomicAdd(sums + which * C + c, a);
+        // deterministic mode: per-block partials, summed in block order by sum_partials_kernel (no atomics anywhere)
+        if (partial_out != nullptr) partial_out[((long)blockIdx.x * 2 + which) * C + c] = a;
+        else atomicAdd(sums + which * C + c, a);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Deterministic reductions (Engine.deterministic / GDRN_DETERMINISTIC=1): two-stage, fixed work decomposition, fixed
+// summation order, no atomics -- bit-identical results run to run (the default path accumulates the BatchNorm batch
+// statistics with fp32 atomics from the GEMM epilogues and the backward sums with atomics across blocks).
+// ------------------------------------------------------------------------------------------------
+// stage 1 of the BatchNorm batch statistics: partials[blk][0][c] = sum x, [blk][1][c] = sum x^2 over the block's rows
+template <bool LO>
+__global__ void __launch_bounds__(kBnBwdThreads, 3) bn_stats_partial_kernel(const bf16* __restrict__ u_hi, const bf16* __restrict__ u_lo,
+                                                                            float* __restrict__ partials, long rows, int C) {
+    const int cg = C / 8;
+    const int rpb = kBnBwdThreads / cg;
+    const int g = threadIdx.x % cg, rl = threadIdx.x / cg;
+    __shared__ float red[2][kBnBwdThreads][8 + 1];
+    float s0[8], s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
+    const long rstride = (long)gridDim.x * rpb;
+    for (long r = (long)blockIdx.x * rpb + rl; r < rows; r += rstride) {
+        float v[8];
+        const long off = r * cg + g;
+        unpack8(ld16(u_hi, off), v);
+        if (LO) unpack8_lo(ld16(u_lo, off), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s0[j] += v[j];
+            s1[j] = fmaf(v[j], v[j], s1[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        red[0][threadIdx.x][j] = s0[j];
+        red[1][threadIdx.x][j] = s1[j];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * C; t += kBnBwdThreads) {
+        const int which = t / C, c = t % C;
+        float a = 0.f;
+        for (int q = 0; q < rpb; ++q) a += red[which][q * cg + c / 8][c % 8];
+        partials[((long)blockIdx.x * 2 + which) * C + c] = a;
+    }
+}
+// stage 2: out[i] = sum over parts (in order) of partials[part][i]
+__global__ void sum_partials_kernel(const float* __restrict__ partials, int nparts, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a = 0.0;
+    for (int p = 0; p < nparts; ++p) a += (double)partials[(long)p * n + i];
+    out[i] = (float)a;
 }
 
 // du = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) = k1*g + k2*u + k3 with per-channel constants (shared memory)
@@ -1023,15 +1075,17 @@ extern "C" int gdrn_zero_insert(const void* x_hi, const void* x_lo, void* y_hi, 
 extern "C" int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_hi, const void* gb_lo, const void* y_hi,
                            const void* u_hi, const void* u_lo, const float* mean, const float* invstd, const float* gamma,
                            const float* beta, float* sums, void* du_hi, void* du_lo, void* gout_hi, void* gout_lo,
-                           float* dgamma, float* dbeta, const void* relu_mask, long rows, int C, int train, int flags,
-                           void* stream_) {
+                           float* dgamma, float* dbeta, const void* relu_mask, float* det_ws, long rows, int C, int train,
+                           int flags, void* stream_) {
     STREAM;
     const uint8_t* mask_in = reinterpret_cast<const uint8_t*>(relu_mask);
+    const bool det = (flags & 4) != 0;
+    if (det && det_ws == nullptr) return set_error(GDRN_ERR_ARG, "bn_bwd: deterministic mode needs a workspace of 2*C*%d floats", 2 * num_sms());
     if (C % 64 || C > 512) return set_error(GDRN_ERR_ARG, "bn_bwd: unsupported C=%d", C);
     const int mask_u = flags & 1;
     if (mask_u && (y_hi != nullptr || beta == nullptr)) return set_error(GDRN_ERR_ARG, "bn_bwd: mask-from-u needs beta and no y");
     {  // the reductions also provide dgamma / dbeta when BN runs on frozen (eval) statistics
-        if (!(flags & 2)) GDRN_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream));
+        if (!(flags & 2) && !det) GDRN_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream));
         const int rpb = kBnBwdThreads / (C / 8);
         long blocks = (rows + (long)rpb * 16 - 1) / ((long)rpb * 16);  // >= 16 rows per thread: few atomics, amortised prologue
         const long cap = (long)num_sms() * 2;
@@ -1040,7 +1094,7 @@ extern "C" int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_
 #define GDRN_BN_RED(LO, MU)                                                                                                   \
     bn_bwd_reduce_kernel<LO, MU><<<(int)blocks, kBnBwdThreads, 0, stream>>>(CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo),       \
                                                                             CBF(y_hi), CBF(u_hi), CBF(u_lo), mean, invstd, gamma, \
-                                                                            beta, sums, rows, C, mask_in)
+                                                                            beta, sums, rows, C, mask_in, det ? det_ws : nullptr)
         if (u_lo != nullptr) {
             if (mask_u) GDRN_BN_RED(true, true); else GDRN_BN_RED(true, false);
         } else {
@@ -1049,6 +1103,11 @@ extern "C" int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_
 #undef GDRN_BN_RED
         GDRN_CUDA_OK(cudaGetLastError());
         count_launch();
+        if (det) {
+            sum_partials_kernel<<<(2 * C + 255) / 256, 256, 0, stream>>>(det_ws, (int)blocks, 2 * C, sums);
+            GDRN_CUDA_OK(cudaGetLastError());
+            count_launch();
+        }
     }
     const int agrid = ew_grid_amortised(rows * (C / 8), 256, 4);
 #define GDRN_BN_APP(LO, MU)                                                                                                      \
@@ -1061,6 +1120,25 @@ extern "C" int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_
         if (mask_u) GDRN_BN_APP(false, true); else GDRN_BN_APP(false, false);
     }
 #undef GDRN_BN_APP
+    LAUNCH_DONE();
+}
+
+// deterministic BatchNorm batch statistics straight from the tensor (two-stage, ordered): stats[0][c] = sum, stats[1][c] = sum of
+// squares.  ws: >= 2 * C * gdrn_det_parts() floats.
+extern "C" int gdrn_det_parts() { return 2 * num_sms(); }
+extern "C" int gdrn_bn_stats(const void* u_hi, const void* u_lo, float* ws, float* stats, long rows, int C, void* stream_) {
+    STREAM;
+    if (C % 64 || C > 512) return set_error(GDRN_ERR_ARG, "bn_stats: unsupported C=%d", C);
+    const int rpb = kBnBwdThreads / (C / 8);
+    long blocks = (rows + (long)rpb * 16 - 1) / ((long)rpb * 16);
+    const long cap = (long)num_sms() * 2;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (u_lo != nullptr) bn_stats_partial_kernel<true><<<(int)blocks, kBnBwdThreads, 0, stream>>>(CBF(u_hi), CBF(u_lo), ws, rows, C);
+    else bn_stats_partial_kernel<false><<<(int)blocks, kBnBwdThreads, 0, stream>>>(CBF(u_hi), CBF(u_lo), ws, rows, C);
+    GDRN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    sum_partials_kernel<<<(2 * C + 255) / 256, 256, 0, stream>>>(ws, (int)blocks, 2 * C, stats);
     LAUNCH_DONE();
 }
 

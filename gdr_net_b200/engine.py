@@ -113,6 +113,10 @@ class Engine:
             raise RuntimeError("gdr_net_b200 engine needs CUDA parameters (model.to('cuda')); no CPU fallback exists")
         self.ws = ops.Workspace(self.dev)
         self.sym_table = SymTable(self.dev)
+        # deterministic reductions (bit-identical run to run): BatchNorm batch statistics and backward sums in two ordered
+        # stages instead of fp32 atomics.  Costs one extra read of every pre-BN tensor in forward; a debugging / testing mode.
+        self.deterministic = os.environ.get("GDRN_DETERMINISTIC") == "1"
+        self._det_ws = None
         self.fold_eval = os.environ.get("GDRN_NO_FOLD_EVAL") != "1"  # A/B switch: eval forward through the unfused train-path kernels
         self.with_2d = int(model.pnp_net.features[0].in_channels == 69)  # 69 = xyz + coord2d + regions, 67 without coords
         assert model.pnp_net.features[0].in_channels in (67, 69), model.pnp_net.features[0].in_channels
@@ -391,6 +395,8 @@ class Engine:
         mom = mod.momentum if mod.momentum is not None else 0.1
         if train_bn and mod.num_batches_tracked is not None:
             self._nbt.append(mod.num_batches_tracked)
+        if train_bn and self.deterministic:
+            C.gdrn_bn_stats(u.hi_ptr, u.lo_ptr, self._det_workspace().data_ptr(), st.stats.data_ptr(), count, Cc, _stream())
         y = ops.like(u)
         mask = None
         if relu and getattr(self, "_want_masks", False) and _BN_BITMASK:
@@ -402,10 +408,15 @@ class Engine:
                       ops.ptr(mask), count, Cc, float(mod.eps), float(mom), int(train_bn), int(relu), _stream())
         return y
 
+    def _det_workspace(self):
+        if self._det_ws is None:
+            self._det_ws = torch.empty(2 * 512 * int(C.load().gdrn_det_parts()), device=self.dev)
+        return self._det_ws
+
     def _conv_bn(self, x: PT, ckey: str, conv, bkey: str, relu: bool, train_bn: bool, res: Optional[PT] = None,
                  wkey: Optional[str] = None, kind: str = "conv"):
         st = self.bn[bkey]
-        stats = st.stats if train_bn else None
+        stats = st.stats if (train_bn and not self.deterministic) else None  # deterministic: statistics from gdrn_bn_stats
         k, stride, pad = conv.kernel_size[0], conv.stride[0], conv.padding[0]
         if kind == "deconv":
             u = ops.conv_fwd(x, self.wf["deconv"], conv.out_channels, 3, 3, 1, 1, stats=stats, algo_scale=0.25)
@@ -473,7 +484,7 @@ class Engine:
         a_col = PT((B * 128 * 128, 192), pl, device=dev)
         C.gdrn_stem_im2col(x.data_ptr(), a_col.hi_ptr, a_col.lo_ptr, B, 256, 256, _stream())
         st0 = self.bn["backbone.bn1"]
-        u0 = ops.gemm_fwd(a_col, self.wf["stem"], 64, stats=st0.stats if train_bn else None).view(B, 128, 128, 64)
+        u0 = ops.gemm_fwd(a_col, self.wf["stem"], 64, stats=st0.stats if (train_bn and not self.deterministic) else None).view(B, 128, 128, 64)
         a0 = self._bn_fwd("backbone.bn1", u0, True, train_bn)
         if S is not None:
             cur, pool_arg = ops.maxpool_fwd(a0, want_arg=True)
@@ -615,7 +626,8 @@ class Engine:
         relu_from_u = relu_from_u and _BN_MASK_FROM_U and mask is None
         return ops.bn_bwd(ga, gb, None if (relu_from_u or mask is not None) else y, u, st.mean, st.invstd, mod.weight, st.sums,
                           self.grads[bkey + ".weight"], self.grads[bkey + ".bias"], self.saved["train_bn"], want_gout=want_gout,
-                          beta=mod.bias, relu_from_u=relu_from_u, sums_zeroed=True, relu_mask=mask)
+                          beta=mod.bias, relu_from_u=relu_from_u, sums_zeroed=True, relu_mask=mask,
+                          det_ws=self._det_workspace() if self.deterministic else None)
 
     def backward(self, grad_losses: torch.Tensor):
         """grad_losses: [8] upstream gradients of LOSS_NAMES.  Fills self.grads (views of self.flat_grad)."""

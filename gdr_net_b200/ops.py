@@ -309,7 +309,7 @@ def bn_act(x: PT, scale, shift, relu: bool, res: PT | None = None, out: PT | Non
 
 
 def bn_bwd(ga: PT, gb: PT | None, y: PT | None, u: PT, mean, invstd, gamma, sums, dgamma, dbeta, train: bool,
-           want_gout: bool = False, beta=None, relu_from_u: bool = False, sums_zeroed: bool = False, relu_mask=None):
+           want_gout: bool = False, beta=None, relu_from_u: bool = False, sums_zeroed: bool = False, relu_mask=None, det_ws=None):
     """y: activation whose sign gives the ReLU mask (needed when a residual was added before the ReLU); relu_from_u: plain
     conv-BN-ReLU, the mask is recomputed from u and beta and y is not read."""
     du = like(u)
@@ -320,7 +320,8 @@ def bn_bwd(ga: PT, gb: PT | None, y: PT | None, u: PT, mean, invstd, gamma, sums
     C.gdrn_bn_bwd(ga.hi_ptr, ga.lo_ptr, gb.hi_ptr if gb else None, gb.lo_ptr if gb else None, y.hi_ptr if y else None,
                   u.hi_ptr, u.lo_ptr, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), ptr(beta), sums.data_ptr(), du.hi_ptr,
                   du.lo_ptr, gout.hi_ptr if gout else None, gout.lo_ptr if gout else None, ptr(dgamma), ptr(dbeta), ptr(relu_mask),
-                  rows, Cc, int(train), (1 if relu_from_u else 0) | (2 if sums_zeroed else 0), _stream())
+                  ptr(det_ws), rows, Cc, int(train),
+                  (1 if relu_from_u else 0) | (2 if sums_zeroed else 0) | (4 if det_ws is not None else 0), _stream())
     return du, gout
 
 

@@ -100,11 +100,16 @@ int gdrn_bn_fwd(const void* x_hi, const void* x_lo, const void* r_hi, const void
 int gdrn_bn_act(const void* x_hi, const void* x_lo, const void* r_hi, const void* r_lo, void* y_hi, void* y_lo,
                 const float* scale, const float* shift, long rows, int C, int relu, void* stream);
 /* flags: bit 0 = the ReLU mask is recomputed from u (plain conv-BN-ReLU: pass y_hi = NULL and beta); bit 1 = `sums` is
- * already zero (the caller cleared all layers' accumulators in one memset) */
+ * already zero (the caller cleared all layers' accumulators in one memset); bit 2 = deterministic two-stage reductions */
 int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_hi, const void* gb_lo, const void* y_hi,
                 const void* u_hi, const void* u_lo, const float* mean, const float* invstd, const float* gamma,
                 const float* beta, float* sums, void* du_hi, void* du_lo, void* gout_hi, void* gout_lo, float* dgamma,
-                float* dbeta, const void* relu_mask, long rows, int C, int train, int flags, void* stream);
+                float* dbeta, const void* relu_mask, float* det_ws, long rows, int C, int train, int flags, void* stream);
+/* deterministic mode (no atomics, fixed summation order; Engine.deterministic): gdrn_bn_stats computes the BatchNorm batch
+ * statistics [2][C] (sum, sum of squares) from the tensor in two ordered stages instead of the GEMM epilogue's atomics;
+ * gdrn_bn_bwd with flags bit 2 does the same for its reductions.  ws / det_ws: >= 2 * C * gdrn_det_parts() floats. */
+int gdrn_det_parts(void);
+int gdrn_bn_stats(const void* u_hi, const void* u_lo, float* ws, float* stats, long rows, int C, void* stream);
 
 /* ---- MaxPool2d(3,2,1) resnet_backbone.py:72; UpsamplingBilinear2d(x2) cdpn_rot_head_region.py:102;
  * zero insertion (stride-2 transposed convs); GroupNorm(32)+ReLU conv_pnp_net.py:76-80 */
