@@ -115,6 +115,8 @@ class Engine:
         self.sym_table = SymTable(self.dev)
         # deterministic reductions (bit-identical run to run): BatchNorm batch statistics and backward sums in two ordered
         # stages instead of fp32 atomics.  Costs one extra read of every pre-BN tensor in forward; a debugging / testing mode.
+        self.wgrad_side_stream = os.environ.get("GDRN_WGRAD_STREAM", "1") == "1"
+        self._side_stream, self._side_keep = None, []
         self.deterministic = os.environ.get("GDRN_DETERMINISTIC") == "1"
         self._det_ws = None
         self.fold_eval = os.environ.get("GDRN_NO_FOLD_EVAL") != "1"  # A/B switch: eval forward through the unfused train-path kernels
@@ -606,10 +608,36 @@ class Engine:
                          S["dy9"].hi_ptr, S["dy9"].lo_ptr, B, n_pts, 1, 1e-4, _stream())
 
     # ------------------------------------------------------------------------------------------ backward
+    # ---- weight gradients on a SIDE STREAM.  In backward the chain  BN-bwd(L) -> dgrad(L) -> BN-bwd(L-1) -> ...  alternates
+    # tensor-bound GEMMs with HBM-bound BatchNorm passes, while wgrad(L) (+ its split-K unpack) only needs du(L) and feeds
+    # nothing but the flat gradient buffer.  Issued on a second stream it runs concurrently with dgrad(L) and -- the point --
+    # with the HBM-bound BN-bwd(L-1): tensor-bound and bandwidth-bound work overlap instead of serialising.  The streams join
+    # at every gradient-bucket boundary (before the loss-scale removal / all-reduce of that bucket) and at the end of backward;
+    # inside a CUDA graph the fork / join become graph edges.  GDRN_WGRAD_STREAM=0 keeps everything on one stream (A/B).
+    def _on_side(self, fn, keep=()):
+        if not self.wgrad_side_stream:
+            return fn()
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream()
+        side = self._side_stream
+        side.wait_stream(torch.cuda.current_stream())  # du(L) is ready
+        with torch.cuda.stream(side):
+            fn()
+        self._side_keep.extend(keep)  # operands allocated on the main stream stay referenced until the join
+
+    def _join_side(self):
+        if self._side_stream is not None and self._side_keep:
+            torch.cuda.current_stream().wait_stream(self._side_stream)
+        self._side_keep.clear()
+
     def _wgrad_conv(self, du: PT, x_in: PT, conv, wname: str, ipad: Optional[int] = None):
         O, I, k = conv.out_channels, conv.in_channels, conv.kernel_size[0]
-        buf, ks, kss = ops.conv_wgrad(du, x_in, self.ws, O, k, k, conv.stride[0], conv.padding[0])
-        ops.unpack_wgrad(buf, self.grads[wname], O, I, k, k, ipad or x_in.shape[-1], ks, kss, I * k * k, k * k, k, 1)
+
+        def work():
+            buf, ks, kss = ops.conv_wgrad(du, x_in, self.ws, O, k, k, conv.stride[0], conv.padding[0])
+            ops.unpack_wgrad(buf, self.grads[wname], O, I, k, k, ipad or x_in.shape[-1], ks, kss, I * k * k, k * k, k, 1)
+
+        self._on_side(work, keep=(du, x_in))
 
     def _dgrad_conv(self, du: PT, conv, wkey: str) -> PT:
         k, stride, pad = conv.kernel_size[0], conv.stride[0], conv.padding[0]
@@ -686,8 +714,11 @@ class Engine:
                         self.with_2d, _stream())
         hf = m.rot_head_net.features
         head_in = h(S["head_in"])
-        buf, ks, kss = ops.gemm_wgrad(dlog, head_in.view(B * 4096, 256), self.ws)
-        ops.unpack_wgrad(buf, self.grads["rot_head_net.features.23.weight"], 69, 256, 1, 1, 256, ks, kss, 256, 1, 0, 0)
+        def head_out_wgrad():
+            buf, ks, kss = ops.gemm_wgrad(dlog, head_in.view(B * 4096, 256), self.ws)
+            ops.unpack_wgrad(buf, self.grads["rot_head_net.features.23.weight"], 69, 256, 1, 1, 256, ks, kss, 256, 1, 0, 0)
+
+        self._on_side(head_out_wgrad, keep=(dlog,))
         tmp128 = torch.empty(128, device=dev)
         C.gdrn_colsum(dlog.hi_ptr, dlog.lo_ptr, tmp128.data_ptr(), B * 4096, 128, _stream())
         self.grads["rot_head_net.features.23.bias"].copy_(tmp128[:69])
@@ -703,9 +734,12 @@ class Engine:
                 g = ops.upsample2x_bwd(g)
         D = S["deconv"]
         du, _ = self._bn_bwd("rot_head_net.features.1", g, None, h(D["y"]), h(D["u"]), relu_from_u=True, mask=D["m"])
-        buf, ks, kss = ops.conv_wgrad(du, h(D["z"]), self.ws, 256, 3, 3, 1, 1)
-        # ConvTranspose2d weight is IOHW [512][256][3][3] with flipped taps relative to the equivalent conv
-        ops.unpack_wgrad(buf, self.grads["rot_head_net.features.0.weight"], 256, 512, 3, 3, 512, ks, kss, 9, 256 * 9, 3, 1, flip=1)
+        def deconv_wgrad(du=du):
+            buf, ks, kss = ops.conv_wgrad(du, h(D["z"]), self.ws, 256, 3, 3, 1, 1)
+            # ConvTranspose2d weight is IOHW [512][256][3][3] with flipped taps relative to the equivalent conv
+            ops.unpack_wgrad(buf, self.grads["rot_head_net.features.0.weight"], 256, 512, 3, 3, 512, ks, kss, 9, 256 * 9, 3, 1, flip=1)
+
+        self._on_side(deconv_wgrad, keep=(du,))
         g = ops.conv_fwd(du, self.wd["deconv"], 512, 3, 3, 2, 1)  # [B,8,8,512]
         self._segment_done("rot_head_net")
 
@@ -732,10 +766,13 @@ class Engine:
         St = S["stem"]
         g_a0 = ops.maxpool_bwd(St["pool_arg"], g_pool)
         du0, _ = self._bn_bwd("backbone.bn1", g_a0, None, h(St["a0"]), h(St["u0"]), relu_from_u=True, mask=St["m0"])
-        buf, ks, kss = ops.gemm_wgrad(du0.view(B * 128 * 128, 64), h(St["a_col"]), self.ws)
-        # ws rows [64][192] with k = (r*7+s)*3 + c  ->  OIHW [64][3][7][7]
-        ops.unpack_wgrad(buf, self.grads["backbone.conv1.weight"], 64, 3, 7, 7, 3, ks, kss, 147, 49, 7, 1, krow=192)
-        self._segment_done("backbone.stem")  # layer1 + bn1 + conv1
+        def stem_wgrad():  # on the side stream like every conv wgrad: the split-K workspace is owned by that stream by now
+            buf, ks, kss = ops.gemm_wgrad(du0.view(B * 128 * 128, 64), h(St["a_col"]), self.ws)
+            # ws rows [64][192] with k = (r*7+s)*3 + c  ->  OIHW [64][3][7][7]
+            ops.unpack_wgrad(buf, self.grads["backbone.conv1.weight"], 64, 3, 7, 7, 3, ks, kss, 147, 49, 7, 1, krow=192)
+
+        self._on_side(stem_wgrad, keep=(du0,))
+        self._segment_done("backbone.stem")  # layer1 + bn1 + conv1 (joins the wgrad side stream)
         self.saved = None
         return self.grads
 
@@ -750,6 +787,10 @@ class Engine:
                 p.grad = g.clone()
 
     def _segment_done(self, stage: str):
+        self._join_side()
+        self._segment_done_joined(stage)
+
+    def _segment_done_joined(self, stage: str):
         """All gradients of a sub-network are final: remove the loss scale from its slice of the flat buffer, then hand
         it to the data-parallel hook (bucketed all-reduce on a side stream)."""
         if self.grad_scale != 1.0:

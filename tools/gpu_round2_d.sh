@@ -4,6 +4,13 @@ set -x
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2d_pytest.log 2>&1; echo "pytest rc=$?"
 tail -3 gpurun_out/r2d_pytest.log
+for v in 0 1; do
+  echo "== quick bench mixed, wgrad side stream=$v"
+  GDRN_WGRAD_STREAM=$v timeout 300 python bench.py --quick --steps 20 --warmup 5 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'])"
+done
+echo "== quick bench half, wgrad side stream=1 / 0"
+GDRN_BENCH_MODE=half timeout 300 python bench.py --quick --steps 20 --warmup 5 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'])"
+GDRN_WGRAD_STREAM=0 GDRN_BENCH_MODE=half timeout 300 python bench.py --quick --steps 20 --warmup 5 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'])"
 NCU="ncu --set full --clock-control none --import-source on --profile-from-start off -f"
 RUN="python bench.py --quick --no-graph --steps 1 --warmup 3"
 export GDRN_PROFILE=1
