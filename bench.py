@@ -470,7 +470,8 @@ def roofline_live(main, peaks):
             fwd_gemm_ms += ms_
             fwd_mma += fl * passes
         if variant:
-            key = f"gdrn::gemm_fwd_kernel<{variant // 10}, {variant % 10}>"
+            kname = "gemm_fwd2_kernel" if variant >= 10000 else "gemm_fwd_kernel"  # fwd2 = cta_group::2 pair tiles
+            key = f"gdrn::{kname}<{(variant % 10000) // 10}, {variant % 10}>"
             d = inst.setdefault(key, [0.0, 0.0, 0, 0.0])
             d[0] += fl
             d[1] += ms_
@@ -490,7 +491,7 @@ def roofline_live(main, peaks):
         prof = json.load(open(ppath)).get(dom[0], {})
     tf = lambda fl, ms_: round(fl / (ms_ * 1e-3) / 1e12, 1) if ms_ > 0 else None  # noqa: E731
     return {
-        "bound": "tensor", "kernel": dom[0] + " (tcgen05 implicit-GEMM conv forward / dgrad)",
+        "bound": "tensor", "kernel": dom[0] + " (tcgen05 implicit-GEMM conv forward / dgrad" + (", cta_group::2 pair tiles)" if "fwd2" in dom[0] else ")"),
         "achieved": round(dom_tflops, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(dom_tflops / peak, 4),
         "peak_source": "bf16_tflops (burst; fp16 and bf16 tcgen05 rates are equal) of " + peaks["source"]
                        + ": the timed region is < 1 s at full boost clocks",
@@ -664,6 +665,7 @@ def inference_bench(B, dev, peaks, steps=20, warm=5):
     for precision, passes in (("mixed", 3), ("half", 1)):
         model, _ = build(precision)
         model.eval()
+        model.use_cuda_graphs = True  # the inference forward is replayed as one CUDA graph
         with torch.no_grad():
             for _ in range(warm):
                 out = model(batch["roi_img"], **kw)
@@ -682,7 +684,7 @@ def inference_bench(B, dev, peaks, steps=20, warm=5):
                           "mma_frac_of_burst_peak": round(tf * passes / peaks["bf16_burst"], 4)}
         del model
         torch.cuda.empty_cache()
-    res["what"] = ("GDRN.forward(do_loss=False) in eval mode, batch 64, eager launches (one ctypes call per kernel), inputs resident; "
+    res["what"] = ("GDRN.forward(do_loss=False) in eval mode, batch 64, use_cuda_graphs=True (one graph replay per forward), inputs resident; "
                    "folded conv+BN(+identity)+ReLU epilogues; 'mixed' = fp32-faithful 3-pass operands (1e-3 parity), 'half' = 1 pass; "
                    "mma_tflops = executed tensor-core rate of the WHOLE forward incl. all HBM-bound kernels and launch gaps")
     return res

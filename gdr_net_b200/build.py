@@ -73,10 +73,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(compile_one, jobs))
     if jobs or force or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-cudart", "shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
+        # link to a temporary name and rename atomically: a concurrent reader (a gpurun snapshot, another process importing
+        # the package) must never see a half-written library
+        tmp = LIB + f".tmp{os.getpid()}"
+        cmd = [NVCC, "-shared", "-o", tmp] + objs + ["-cudart", "shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        os.replace(tmp, LIB)
     return LIB
 
 

@@ -322,6 +322,34 @@ class Engine:
             cur = cbr(cur, f"rot_head_net.features.{ci}", f"rot_head_net.features.{bi}", hf[ci])
         return self._tail_inference(cur, aux, want_maps)
 
+    def _eval_graphed(self, x: torch.Tensor, aux: dict, want_maps: bool) -> dict:
+        """Inference forward replayed as ONE CUDA graph per input signature (`use_cuda_graphs`): ~230 launches incl. the
+        BatchNorm folding and the weight pack (so updated weights / running statistics are picked up at every replay)."""
+        tens = {k: v for k, v in aux.items() if isinstance(v, torch.Tensor)}
+        key = (tuple(x.shape), want_maps, tuple(sorted((k, tuple(v.shape)) for k, v in tens.items())),
+               tuple(p.data_ptr() for _, p in self.named_params))
+        cache = self.__dict__.setdefault("_eval_graphs", {})
+        g = cache.get(key)
+        if g is None:
+            st = dict(x=x.clone(), aux={k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in aux.items()})
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.forward_eval_folded(st["x"], st["aux"], want_maps=want_maps)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            st["graph"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(st["graph"], capture_error_mode=_capture_mode()):
+                st["res"] = self.forward_eval_folded(st["x"], st["aux"], want_maps=want_maps)
+            if len(cache) > 8:
+                cache.clear()
+            g = cache[key] = st
+        g["x"].copy_(x, non_blocking=True)
+        for k, v in tens.items():
+            g["aux"][k].copy_(v, non_blocking=True)
+        g["graph"].replay()
+        return {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in g["res"].items()}
+
     def _tail_inference(self, head_in: PT, aux: dict, want_maps: bool) -> dict:
         """1x1 output conv -> glue -> Patch-PnP -> test-time pose decode (shared by the folded and the plain eval forward)."""
         m, pl, dev = self.model, self.planes, self.dev
@@ -465,6 +493,8 @@ class Engine:
         if not do_loss:
             with torch.no_grad():
                 if not train_bn and self.fold_eval:  # inference: conv + BN (+ identity) + ReLU fused per layer
+                    if self.use_cuda_graphs:
+                        return self._eval_graphed(x, aux, want_maps)
                     return self.forward_eval_folded(x, aux, want_maps=want_maps)
                 return self.forward(x, aux, train_bn=train_bn, do_loss=False, want_maps=want_maps)
         params = [p for _, p in self.named_params]

@@ -32,7 +32,7 @@ int gdrn_storage_format(void); /* 0: bf16 (hi, lo) planes; 1: fp16 planes, lo = 
 float gdrn_lo_scale(void);
 int gdrn_set_2cta(int on); /* A/B: cta_group::2 pair tiles (256x256 1-pass / 256x128 3-pass) for eligible conv layers; default on */
 long gdrn_2cta_launch_count(void); /* launches of the 2-CTA kernel since load */
-int gdrn_last_gemm_variant(void); /* BLOCK_N*10 + nsplit of this thread's last conv/gemm forward launch */
+int gdrn_last_gemm_variant(void); /* BLOCK_N*10 + nsplit (+10000: 2-CTA kernel) of this thread's last conv/gemm forward launch */
 
 /* ---- tcgen05 implicit-GEMM convolution, forward (and dgrad with flipped/transposed weights) ------------
  * replaces nn.Conv2d / nn.ConvTranspose2d forward: resnet_backbone.py:21-49,69-76 (torchvision BasicBlock),
@@ -162,6 +162,12 @@ int gdrn_pose_loss(const float* pred, int ld_pred, const float* cams, const floa
                    int do_loss, float eps, void* stream);
 int gdrn_loss_finalize(const double* pix_sums, const double* pose_sums, const float* vis, float* losses, float* vis_out,
                        int B, int HW, int n_pts, void* stream);
+
+/* ---- evaluator metrics on the device (lib/pysixd/pose_error.py:297-337 add / adi, :400-436 re / te; the reference computes
+ * them per instance in numpy with a scipy KD-tree, gdrn_evaluator.py:316-436).  R_* [B][3][3], t_* [B][3], points [B][n_pts][3]
+ * (model points per instance, metres) -> out [B][4] = (ADD, ADD-S = ADI or 0 when !want_adi, re in degrees, te). */
+int gdrn_pose_errors(const float* R_est, const float* t_est, const float* R_gt, const float* t_gt, const float* points, int B,
+                     int n_pts, int want_adi, float* out, void* stream);
 
 /* ---- fused Ranger step (gradient centralisation + RAdam + Lookahead), lib/torch_utils/solver/ranger.py:100-200, for all
  * tensors of a param group in ONE launch.  jobs: device array of 64-byte records {float* p; const float* g; float* m; float* v;

@@ -472,3 +472,31 @@ def test_bn_relu_bitmask_roundtrip(planes, with_res):
         outs.append((DU.float(), GOUT.float(), dgamma.clone(), dbeta.clone()))
     assert int(((outs[0][0] - outs[1][0]).abs() > 1e-4).sum()) <= 4
     assert _rel(outs[1][1], outs[0][1]) < 1e-3 and _rel(outs[1][2], outs[0][2]) < 5e-2 and _rel(outs[1][3], outs[0][3]) < 5e-2
+
+
+def test_pose_errors_match_pysixd_restatement():
+    """gdrn_pose_errors (ADD / ADD-S / re / te on the device, one launch per batch) against the oracle's restatement of
+    lib/pysixd/pose_error.py:297-337, 400-436 (numpy + scipy cKDTree per instance)."""
+    import numpy as np
+
+    from gdr_net_b200 import synth
+    from gdr_net_b200.evaluator import pose_errors
+    from oracle import gdrn_oracle as O
+
+    g = synth._gen(9, "pose_errors")
+    B, n = 6, 3000
+    pts = (torch.rand(B, n, 3, generator=g) - 0.5) * 0.2
+    R_gt = synth.random_rotations(B, g)
+    R_est = torch.linalg.qr(R_gt + 0.05 * torch.randn(B, 3, 3, generator=g))[0]
+    R_est = R_est * torch.sign(torch.linalg.det(R_est))[:, None, None]
+    t_gt = torch.stack([torch.rand(B, generator=g) * 0.4 - 0.2, torch.rand(B, generator=g) * 0.4 - 0.2, 0.4 + torch.rand(B, generator=g)], 1)
+    t_est = t_gt + 0.01 * torch.randn(B, 3, generator=g)
+    out = pose_errors(R_est.cuda(), t_est.cuda(), R_gt.cuda(), t_gt.cuda(), pts.cuda())
+    torch.cuda.synchronize()
+    for i in range(B):
+        args = (R_est[i].numpy(), t_est[i].numpy(), R_gt[i].numpy(), t_gt[i].numpy(), pts[i].numpy())
+        add, adi = O.add_metric(*args), O.adi_metric(*args)
+        assert abs(float(out["add"][i]) - add) <= 1e-5 * add + 1e-8, (i, float(out["add"][i]), add)
+        assert abs(float(out["adi"][i]) - adi) <= 1e-5 * adi + 1e-8, (i, float(out["adi"][i]), adi)
+        assert abs(float(out["re"][i]) - O._re_deg(R_est[i].numpy(), R_gt[i].numpy())) < 1e-3
+        assert abs(float(out["te"][i]) - float(np.linalg.norm(t_gt[i].numpy() - t_est[i].numpy()))) < 1e-6

@@ -306,6 +306,18 @@ def test_eval_folded_bn_matches_unfused_and_oracle():
         print(f"[fold={fold}] eval B=3 head rel-L2 vs oracle {_rel(head, o['head']):.2e} rot {_rel(out['rot'], o['rot']):.2e} trans {_rel(out['trans'], o['trans']):.2e}")
         assert _rel(head, o["head"]) < REL and _rel(out["rot"], o["rot"]) < 2e-3 and _rel(out["trans"], o["trans"]) < 2e-3
     assert _rel(outs[True][0], outs[False][0]) < 3e-4
+    # the same forward replayed as a CUDA graph (twice: capture + replay), incl. a changed running statistic picked up on replay
+    model = _build("mixed", sd, use_pnp_test=True)
+    model.eval()
+    model.use_cuda_graphs = True
+    with torch.no_grad():
+        for it in range(2):
+            out = model(batch["roi_img"], **synth.forward_kwargs(batch, train=False))
+        head = torch.cat([out["mask"], out["coor_x"], out["coor_y"], out["coor_z"], out["region"]], dim=1).cpu()
+        assert torch.equal(head, outs[True][0]) and torch.equal(out["rot"].cpu(), outs[True][1])
+        model.backbone.bn1.running_mean.add_(0.05)
+        out2 = model(batch["roi_img"], **synth.forward_kwargs(batch, train=False))
+        assert not torch.equal(out2["rot"].cpu(), outs[True][1])  # the replay re-folds the BatchNorms from the live buffers
 
 
 def test_deterministic_mode_is_bit_reproducible_and_graph_equals_eager():
