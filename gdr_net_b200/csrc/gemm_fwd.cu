@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], p.cluster);  // every CTA of the cluster must have consumed the stage (multicast writes all)
+            mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
@@ -126,19 +126,15 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // cluster geometry: clusters stride over "tile groups" = (n_tile, group of `cl` consecutive m_tiles)
-    const int cl = p.cluster;
-    const uint32_t crank = cl > 1 ? cluster_ctarank() : 0u;
-    const uint16_t cmask = (uint16_t)((1u << cl) - 1u);
-    const int my_cluster = blockIdx.x / cl, num_clusters = gridDim.x / cl;
-    const int num_groups = (p.nphase ? p.nphase : 1) * num_tiles / cl;  // phase-major tile list for the stride-2 dgrad
-    if (cl > 1) cluster_sync_all();  // peers' barriers are initialised before any remote arrive / multicast write
+    // persistent CTAs stride over the tile list (phase-major for the stride-2 dgrad)
+    const int my_cluster = blockIdx.x, num_clusters = gridDim.x;
+    const int num_groups = (p.nphase ? p.nphase : 1) * num_tiles;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (cl == 1) {
-            // Fast path (no cluster), executed by the whole warp with warp-uniform control flow; one elected lane issues.  This single thread used to spend ~1100 cycles per k-block on index arithmetic (two
-            // integer divisions, generic->shared conversions, parameter reloads) -- more than the 128..512 cycles of MMA
+        {
+            // Executed by the whole warp with warp-uniform control flow; one elected lane issues.  A single thread used to
+            // spend ~1100 cycles per k-block here on index arithmetic (two integer divisions, generic->shared conversions, parameter reloads) -- more than the 128..512 cycles of MMA
             // work a k-block carries, so EVERY layer ran at the producer's pace (ncu: this warp ~100 % busy, tensor pipe
             // 11 % / 50 %).  Taps and channel chunks are now nested loops with incremental state; per k-block only the
             // barrier wait, the expect_tx and the TMA issues remain.
@@ -230,87 +226,11 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
                     }
                 }
             }
-        } else if (lane == 0) {  // cluster (multicast) experiment: the original generic loop
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int grp = my_cluster; grp < num_groups; grp += num_clusters) {
-                int rem = grp, nkb = p.num_kb, tap_base = 0;
-                if (p.nphase) {
-                    const int ph = grp / num_tiles;
-                    rem = grp - ph * num_tiles;
-                    tap_base = p.ph_tap0[ph];
-                    nkb = (p.ph_tap0[ph + 1] - tap_base) * p.cchunks;
-                }
-                const int n_tile = rem % p.num_n_tiles;
-                const int m_tile = (rem / p.num_n_tiles) * cl + (int)crank;
-                int n0 = 0, h0 = 0;
-                if (p.mode == 1) {
-                    if (p.TN == 1) {
-                        n0 = m_tile / p.tiles_per_img;
-                        h0 = (m_tile % p.tiles_per_img) * p.TH;
-                    } else {
-                        n0 = m_tile * p.TN;
-                    }
-                }
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
-                    int kb_w = kb;  // k-block of the packed weight matrix
-                    if (p.mode == 1) {
-                        const int tap = kb / p.cchunks;
-                        const int cc = kb - tap * p.cchunks;
-                        int dh, dw, map = 0;
-                        if (p.nphase) {
-                            dh = p.tap_dh[tap_base + tap];
-                            dw = p.tap_dw[tap_base + tap];
-                            kb_w = p.tap_w[tap_base + tap] * p.cchunks + cc;
-                        } else {
-                            const int r = tap / p.KW;
-                            const int s = tap - r * p.KW;
-                            dh = r - p.pad;
-                            dw = s - p.pad;
-                            if (p.stride == 2) {
-                                map = ((dh & 1) << 1) | (dw & 1);
-                                dh >>= 1;  // arithmetic shift == floor division
-                                dw >>= 1;
-                            }
-                        }
-#pragma unroll
-                        for (int pl = 0; pl < NPL; ++pl)
-                            tma_load_4d(st + pl * Cfg::A_BYTES, &p.tmA[pl][map], &full_bar[stage], cc * kBlockK, dw,
-                                        h0 + dh, n0);
-                    } else {
-#pragma unroll
-                        for (int pl = 0; pl < NPL; ++pl)
-                            tma_load_2d(st + pl * Cfg::A_BYTES, &p.tmA[pl][0], &full_bar[stage], kb * kBlockK,
-                                        m_tile * kBlockM);
-                    }
-                    if (cl == 1) {
-#pragma unroll
-                        for (int pl = 0; pl < NPL; ++pl)
-                            tma_load_2d(st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES, &p.tmB[pl], &full_bar[stage],
-                                        kb_w * kBlockK, n_tile * BLOCK_N);
-                    } else {
-                        // this CTA fetches rows [crank * BLOCK_N/cl, +BLOCK_N/cl) of the weight tile and multicasts them to
-                        // the same smem offset of every CTA in the cluster: L2 -> SM weight traffic drops by cl
-                        const int rows = BLOCK_N / cl;
-#pragma unroll
-                        for (int pl = 0; pl < NPL; ++pl)
-                            tma_load_2d_mcast(st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES + crank * rows * 128, &p.tmB[pl],
-                                              &full_bar[stage], kb_w * kBlockK, n_tile * BLOCK_N + crank * rows, cmask);
-                    }
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-            }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer (single thread)
-        if (cl == 1) {
-            // Fast path, executed by the WHOLE warp with warp-uniform control flow; only the tcgen05 instructions are issued by
+        // ------------------------------------------------------------------ MMA issuer
+        {
+            // Executed by the WHOLE warp with warp-uniform control flow; only the tcgen05 instructions are issued by
             // one elected lane.  (Inside an `if (lane == 0)` region the compiler wraps every UTCHMMA in an ELECT + 5x R2UR
             // "waterfall" loop, ~20 instructions per MMA.)
             // The shared-memory descriptors of a stage differ only in their 14-bit address field, so they are
@@ -371,52 +291,6 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
                 if (elect_one()) umma_commit_u32(tfull0 + acc * 8);
                 __syncwarp();
             }
-        } else if (lane == 0) {  // cluster (multicast) experiment: the original generic loop
-            constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N, 0, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int grp = my_cluster; grp < num_groups; grp += num_clusters, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_set = tmem_base + acc * Cfg::NACC * BLOCK_N;
-                int nkb = p.num_kb;
-                if (p.nphase) {
-                    const int ph = grp / num_tiles;
-                    nkb = (p.ph_tap0[ph + 1] - p.ph_tap0[ph]) * p.cchunks;
-                }
-                for (int kb = 0; kb < nkb; ++kb) {
-                    const uint32_t d_tmem = d_set + (NSPLIT == 3 ? (kb % Cfg::NMAIN) * BLOCK_N : 0);
-                    const uint32_t d_cross = d_set + Cfg::NMAIN * BLOCK_N;
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint32_t b_hi = a_hi + NPL * Cfg::A_BYTES;
-#pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        const uint64_t da = make_smem_desc(a_hi + k * 32, 16, 1024);
-                        const uint64_t db = make_smem_desc(b_hi + k * 32, 16, 1024);
-                        if (NSPLIT == 3) {
-                            const uint64_t da_lo = make_smem_desc(a_hi + Cfg::A_BYTES + k * 32, 16, 1024);
-                            const uint64_t db_lo = make_smem_desc(b_hi + Cfg::B_BYTES + k * 32, 16, 1024);
-                            umma_bf16(d_tmem, da, db, idesc, (kb >= Cfg::NMAIN || k != 0) ? 1u : 0u);
-                            umma_bf16(d_cross, da, db_lo, idesc, (kb | k) != 0 ? 1u : 0u);
-                            umma_bf16(d_cross, da_lo, db, idesc, 1u);
-                        } else {
-                            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-                        }
-                    }
-                    // frees this smem stage (in every CTA of the cluster: their multicasts write our smem) when the MMAs retire
-                    if (cl == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], cmask);
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-                umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-            }
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue: 2 warpgroups x 128 threads.
@@ -440,7 +314,7 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
                 rem = tg - ph * num_tiles;
             }
             const int n_tile = rem % p.num_n_tiles;
-            const int m_tile = (rem / p.num_n_tiles) * cl + (int)crank;
+            const int m_tile = rem / p.num_n_tiles;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tfull_bar[acc], acc_phase);
@@ -466,7 +340,6 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
 
     tc_fence_before();
     __syncthreads();
-    if (cl > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into its smem / arrive on its barriers
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -485,20 +358,19 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
         GDRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    const int cl = p.cluster;
-    const int groups = (p.nphase ? p.nphase : 1) * p.num_m_tiles * p.num_n_tiles / cl;
-    int clusters = groups < num_sms() / cl ? groups : num_sms() / cl;
+    const int groups = (p.nphase ? p.nphase : 1) * p.num_m_tiles * p.num_n_tiles;
+    int clusters = groups < num_sms() ? groups : num_sms();
     clusters -= clusters % p.num_n_tiles;  // every CTA keeps one n_tile => per-CTA BatchNorm partial sums
     if (clusters <= 0) clusters = p.num_n_tiles;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(clusters * cl);
+    cfg.gridDim = dim3(clusters);
     cfg.blockDim = dim3(128 + 32 * kEpiWarps);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -558,16 +430,6 @@ static bool want_2cta(int nsplit, int block_n, int num_m_tiles, int num_n_tiles)
     return (num_m_tiles / 2) * num_n_tiles * 4 >= num_sms();
 }
 
-static int pick_cluster(int num_m_tiles) {
-    static int forced = -1;
-    if (forced < 0) {
-        const char* e = getenv("GDRN_CLUSTER");
-        forced = e ? atoi(e) : 1;
-    }
-    if (forced != 2) return 1;
-    return (num_m_tiles % 2 == 0 && num_m_tiles >= 2) ? 2 : 1;
-}
-
 }  // namespace gdrn
 
 using namespace gdrn;
@@ -605,7 +467,7 @@ extern "C" int gdrn_conv_fwd(const void* x_hi, const void* x_lo, const void* w_h
     GemmParams p;
     memset(&p, 0, sizeof(p));
     const bool two_cta = want_2cta(nsplit, block_n, (N * Ho * Wo + 127) / 128, Cout_pad / block_n);
-    const int cluster = two_cta ? 2 : pick_cluster((N * Ho * Wo + 127) / 128);  // weight box = block_n / cluster rows
+    const int cluster = two_cta ? 2 : 1;  // 2-CTA pairs: each CTA loads half of the weight tile
     const int npl = nsplit == 1 ? 1 : 2;
     const void* xs[2] = {x_hi, x_lo};
     const void* ws[2] = {w_hi, w_lo};
@@ -752,7 +614,7 @@ extern "C" int gdrn_gemm_fwd(const void* a_hi, const void* a_lo, const void* w_h
     if (block_n < 0) return set_error(GDRN_ERR_ARG, "gemm_fwd: N_pad=%d must be a multiple of 64", N_pad);
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    const int cluster = pick_cluster((M + 127) / 128);
+    const int cluster = 1;
     const int npl = nsplit == 1 ? 1 : 2;
     const void* as[2] = {a_hi, a_lo};
     const void* ws[2] = {w_hi, w_lo};

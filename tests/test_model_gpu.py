@@ -93,7 +93,7 @@ def test_eval_forward_b2_vs_golden(sd, golden_dir, precision, tol):
 # forward values.  The reference's OWN fp32 gradients differ from its fp64 evaluation by 1.5e-2 relative L2 at the
 # stem (tools/noise_floor.py; forward difference only 4e-5).  We require <= 0.06 per tensor and cosine > 0.995 overall
 # in fp32x3 mode; per-op backward kernels are tested to ~1e-4 in tests/test_ops_gpu.py.
-@pytest.mark.parametrize("precision,tol,gtol", [("fp32x3", REL_FP32, 0.06), ("half", REL_HALF, 1.0)])
+@pytest.mark.parametrize("precision,tol,gtol", [("fp32x3", REL_FP32, 0.06), ("mixed", REL_FP32, 0.06), ("half", REL_HALF, 1.0)])
 @pytest.mark.parametrize("case,seed,sym", [("train_b4", 1, False), ("train_sym_b4", 2, True)])
 def test_train_fwd_bwd_b4(sd, golden_dir, precision, tol, gtol, case, seed, sym):
     from oracle import gdrn_oracle as O
@@ -115,7 +115,7 @@ def test_train_fwd_bwd_b4(sd, golden_dir, precision, tol, gtol, case, seed, sym)
         assert abs(float(v) - ref) <= tol * abs(ref), (k, float(v), ref)
     # logging side effect values (vis/*) against the reference's EventStorage scalars
     if "vis/error_R" in g.files:
-        assert abs(model.last_vis_dict["vis/error_R"] - float(g["vis/error_R"])) < (0.05 if precision == "fp32x3" else 30.0)
+        assert abs(model.last_vis_dict["vis/error_R"] - float(g["vis/error_R"])) < (0.05 if precision != "half" else 30.0)
         assert abs(model.last_vis_dict["vis/tz_gt"] - float(g["vis/tz_gt"])) < 1e-6
     # gradients: against the oracle's autograd (full tensors) and the reference's stored norms
     leaf = O.leaf_state_dict(sd)
@@ -137,13 +137,15 @@ def test_train_fwd_bwd_b4(sd, golden_dir, precision, tol, gtol, case, seed, sym)
     tail = {n: _rel(dict(model.named_parameters())[n].grad, leaf[n].grad) for n in ("pnp_net.fc_t.weight", "pnp_net.fc2.weight")}
     print(f"[{precision}] {case}: worst grad rel-L2 {worst}, cosine {cos:.6f}, tail {tail}")
     assert worst[1] < gtol, worst
-    if precision == "fp32x3":
-        assert cos > 0.995, cos
+    if precision in ("fp32x3", "mixed"):  # mixed = the fp32x3 forward + a single-pass backward: same bounds (measured 0.9996 / 0.9997)
+        assert cos > 0.999, cos
         assert tail["pnp_net.fc_t.weight"] < 5e-3 and tail["pnp_net.fc2.weight"] < 5e-2, tail
+    else:  # half: the 5e-2 forward deviation flips ReLU / L1 decisions; measured global cosine 0.82 (bound it)
+        assert cos > 0.7, cos
     # BatchNorm running statistics were updated like nn.BatchNorm2d(momentum=0.1)
     msd = model.state_dict()
     for k in ("backbone.bn1.running_mean", "backbone.layer4.2.bn2.running_var", "rot_head_net.features.21.running_mean"):
-        assert _relmax(msd[k], leaf[k]) < (2e-3 if precision == "fp32x3" else 0.2), k
+        assert _relmax(msd[k], leaf[k]) < (2e-3 if precision != "half" else 0.2), k
     assert int(msd["backbone.bn1.num_batches_tracked"]) == 1
 
 
@@ -260,3 +262,34 @@ def test_module_api_grad_accumulation_and_aliasing(sd):
         # run-to-run noise (atomics order -> ReLU / max-pool flips) reaches 4e-3 (head) .. 2e-2 (stem) on this non-smooth net;
         # a lost or doubled gradient would be an error of 0.5-1.0
         assert _rel(params[n].grad, want) < (0.25 if n.startswith("backbone") else 5e-2), n
+
+
+def test_train_harness_steps_and_async_losses(sd):
+    """f-1: batch_data + TrainStep (graphs + fused Ranger, no per-iteration .item()): losses of a step match a plain eager step on
+    the same batch, parameters move, and the asynchronous loss read-back returns the previous step's values."""
+    from gdr_net_b200.train_harness import TrainStep, batch_data
+
+    b = synth.make_batch(4, seed=71)
+    data = [dict(roi_img=b["roi_img"][i], roi_cls=0, roi_coord_2d=b["roi_coord_2d"][i], cam=b["roi_cam"][i], bbox_center=b["roi_center"][i],
+                 roi_wh=b["roi_wh"][i], resize_ratio=float(b["resize_ratio"][i]), roi_extent=b["roi_extent"][i],
+                 trans_ratio=b["roi_trans_ratio"][i], roi_xyz=b["roi_xyz"][i], roi_mask_trunc=b["roi_mask_trunc"][i],
+                 roi_mask_visib=b["roi_mask_visib"][i], roi_mask_obj=b["roi_mask_obj"][i], roi_region=b["roi_region"][i].int(),
+                 ego_rot=b["ego_rot"][i], trans=b["trans"][i], roi_points=b["roi_points"][i]) for i in range(4)]
+    batch = batch_data(None, data, device="cuda")
+    model, opt = _model(sd, "mixed")
+    model.train()
+    ref_model, _ = _model(sd, "mixed")
+    ref_model.train()
+    _, ref_ld = ref_model(batch["roi_img"], **synth.forward_kwargs(_cuda_batch(b), train=True))
+    step = TrainStep(model, opt, use_cuda_graphs=True)
+    before = model.rot_head_net.features[23].weight.detach().clone()
+    ld0 = step(batch)
+    assert step.losses_async() is None
+    for k, v in ld0.items():
+        assert abs(float(v) - float(ref_ld[k])) <= 1e-4 * abs(float(ref_ld[k])) + 1e-7, k
+    step(batch)
+    prev = step.losses_async()
+    assert abs(prev["total_loss"] - float(sum(ld0.values()))) <= 1e-5 * abs(prev["total_loss"])
+    cur = step.losses_async(wait_current=True)
+    assert cur["total_loss"] == cur["total_loss"] and cur["total_loss"] != prev["total_loss"]  # the weights moved
+    assert not torch.equal(before, model.rot_head_net.features[23].weight)

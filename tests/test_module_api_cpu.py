@@ -109,3 +109,32 @@ def test_ranger_matches_reference_algorithm():
                 p.copy_(s["slow"])
     for x, y in zip(a, b):
         assert torch.allclose(x.detach(), y, rtol=1e-5, atol=1e-6)
+
+
+def test_batch_data_matches_reference_collate_keys():
+    """train_harness.batch_data = the reference's collate (engine_utils.py:6-60): same keys, dtypes and shapes."""
+    from gdr_net_b200 import synth
+    from gdr_net_b200.train_harness import batch_data, forward_kwargs
+
+    b = synth.make_batch(3, seed=4, with_sym=True)
+    data = []
+    for i in range(3):  # per-sample dicts as the reference's dataset emits them (data_loader.py:617-632)
+        d = dict(roi_img=b["roi_img"][i], roi_cls=int(b["roi_cls"][i]), roi_coord_2d=b["roi_coord_2d"][i], cam=b["roi_cam"][i],
+                 bbox_center=b["roi_center"][i].double(), roi_wh=b["roi_wh"][i], resize_ratio=float(b["resize_ratio"][i]),
+                 roi_extent=b["roi_extent"][i], trans_ratio=b["roi_trans_ratio"][i], roi_xyz=b["roi_xyz"][i],
+                 roi_mask_trunc=b["roi_mask_trunc"][i], roi_mask_visib=b["roi_mask_visib"][i], roi_mask_obj=b["roi_mask_obj"][i],
+                 roi_region=b["roi_region"][i].int(), ego_rot=b["ego_rot"][i], trans=b["trans"][i], roi_points=b["roi_points"][i],
+                 sym_info=b["sym_info"][i])
+        data.append(d)
+    out = batch_data(None, data, device="cpu")
+    for k in ("roi_img", "roi_coord_2d", "roi_cam", "roi_center", "roi_wh", "resize_ratio", "roi_extent", "roi_trans_ratio", "roi_xyz",
+              "roi_mask_trunc", "roi_mask_visib", "roi_mask_obj", "ego_rot", "trans", "roi_points"):
+        assert out[k].dtype == torch.float32 and torch.allclose(out[k], b[k].float()), k
+    assert out["roi_region"].dtype == torch.long and torch.equal(out["roi_region"], b["roi_region"])
+    assert out["roi_cls"].dtype == torch.long and len(out["sym_info"]) == 3
+    kw = forward_kwargs(out, train=True)
+    import inspect
+
+    assert set(kw) <= set(inspect.signature(G.GDRN.forward).parameters)
+    test = batch_data(None, data, device="cpu", phase="test")
+    assert "roi_xyz" not in test and "roi_cam" in test
