@@ -259,9 +259,22 @@ __global__ void __launch_bounds__(256, 4) bn_fwd_kernel(const bf16* __restrict__
 struct Pix {
     int g, x, y, b;
 };
+// every tensor of this network has power-of-two channel groups / widths / heights: shifts and masks instead of three
+// 32-bit divisions (the gather kernels are instruction-bound, not bandwidth-bound)
+__device__ __forceinline__ bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 __device__ __forceinline__ Pix decode_pix(long idx, int cg, int W, int H) {
     unsigned t = (unsigned)idx;
     Pix p;
+    if (is_pow2(cg) && is_pow2(W) && is_pow2(H)) {  // block-uniform branch
+        const int lc = 31 - __clz(cg), lw = 31 - __clz(W), lh = 31 - __clz(H);
+        p.g = (int)(t & (unsigned)(cg - 1));
+        t >>= lc;
+        p.x = (int)(t & (unsigned)(W - 1));
+        t >>= lw;
+        p.y = (int)(t & (unsigned)(H - 1));
+        p.b = (int)(t >> lh);
+        return p;
+    }
     unsigned q = t / (unsigned)cg;
     p.g = (int)(t - q * (unsigned)cg);
     t = q;
@@ -759,23 +772,46 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(
 // GroupNorm(32 groups) + ReLU, one CTA per sample, tensor [HW][C] (C = 128 => 4 channels per group)
 // ------------------------------------------------------------------------------------------------
 // stats layout: [B][G][2] (mean, rstd).  Each thread owns one 8-channel column group (= 2 GN groups when C/G = 4)
+// A sample is split over a CLUSTER of kGnCluster CTAs (one CTA per sample used 64 of the 148 SMs at B = 64): each CTA owns a
+// contiguous quarter of the rows, the per-group partial sums are exchanged through distributed shared memory.
+constexpr int kGnCluster = 4;
+__device__ __forceinline__ unsigned gn_cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void gn_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double gn_remote_f64(const double* local_smem_ptr, unsigned rank) {  // the same smem offset in CTA `rank`
+    const unsigned a = (unsigned)__cvta_generic_to_shared(local_smem_ptr);
+    unsigned ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+    return v;
+}
+
 __global__ void __launch_bounds__(256) gn_relu_fwd_kernel(const bf16* __restrict__ u_hi, const bf16* __restrict__ u_lo,
                                                           bf16* __restrict__ y_hi, bf16* __restrict__ y_lo,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                          float* __restrict__ stats, int HW, int C, int G, float eps) {
-    const int b = blockIdx.x;
+                                                          float* __restrict__ stats, int HW, int C, int G, float eps, int ncl) {
+    const int b = blockIdx.x / ncl;
+    const unsigned crank = ncl > 1 ? gn_cluster_rank() : 0u;
     const int cg = C / 8;             // 16
     const int g = threadIdx.x % cg;   // column group
     const int rl = threadIdx.x / cg;  // row lane
     const int rpb = 256 / cg;
     const int cpg = C / G;  // channels per group (4)
+    const int rows = HW / ncl, r_begin = (int)crank * rows;  // this CTA's rows of the sample
     __shared__ float sm[2][256][8 + 1];
     __shared__ float gstat[64][2];
+    __shared__ double part[64][2];  // this CTA's per-group partial sums (read remotely by the cluster peers)
     float s0[8], s1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
     const long base = (long)b * HW * cg;
-    for (int r = rl; r < HW; r += rpb) {
+    for (int r = r_begin + rl; r < r_begin + rows; r += rpb) {
         float v[8];
         load8(u_hi, u_lo, base + (long)r * cg + g, v);
 #pragma unroll
@@ -800,6 +836,17 @@ __global__ void __launch_bounds__(256) gn_relu_fwd_kernel(const bf16* __restrict
                 a1 += sm[1][q * cg + gg][j];
             }
         }
+        part[grp][0] = a0;
+        part[grp][1] = a1;
+    }
+    if (ncl > 1) gn_cluster_sync(); else __syncthreads();
+    if (threadIdx.x < G) {
+        const int grp = threadIdx.x;
+        double a0 = 0, a1 = 0;
+        for (int r = 0; r < ncl; ++r) {  // fixed rank order: deterministic
+            a0 += ncl > 1 ? gn_remote_f64(&part[grp][0], r) : part[grp][0];
+            a1 += ncl > 1 ? gn_remote_f64(&part[grp][1], r) : part[grp][1];
+        }
         const double n = (double)HW * cpg;
         const double m = a0 / n;
         double var = a1 / n - m * m;
@@ -807,8 +854,10 @@ __global__ void __launch_bounds__(256) gn_relu_fwd_kernel(const bf16* __restrict
         const float rstd = rsqrtf((float)var + eps);
         gstat[grp][0] = (float)m;
         gstat[grp][1] = rstd;
-        stats[((long)b * G + grp) * 2 + 0] = (float)m;
-        stats[((long)b * G + grp) * 2 + 1] = rstd;
+        if (crank == 0) {
+            stats[((long)b * G + grp) * 2 + 0] = (float)m;
+            stats[((long)b * G + grp) * 2 + 1] = rstd;
+        }
     }
     __syncthreads();
     float sc[8], sh[8];
@@ -819,7 +868,7 @@ __global__ void __launch_bounds__(256) gn_relu_fwd_kernel(const bf16* __restrict
         sc[j] = gamma[c] * gstat[grp][1];
         sh[j] = beta[c] - gstat[grp][0] * sc[j];
     }
-    for (int r = rl; r < HW; r += rpb) {
+    for (int r = r_begin + rl; r < r_begin + rows; r += rpb) {
         float v[8];
         const long off = base + (long)r * cg + g;
         load8(u_hi, u_lo, off, v);
@@ -827,6 +876,7 @@ __global__ void __launch_bounds__(256) gn_relu_fwd_kernel(const bf16* __restrict
         for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
         store8(y_hi, y_lo, off, v);
     }
+    if (ncl > 1) gn_cluster_sync();  // no CTA may exit while a peer can still read its shared memory
 }
 
 // du = rstd * (dxh - mean_grp(dxh) - xh * mean_grp(dxh * xh)),  dxh = g*[y>0]*gamma;  dgamma += sum g*xh, dbeta += sum g
@@ -835,15 +885,18 @@ __global__ void __launch_bounds__(256) gn_relu_bwd_kernel(const bf16* __restrict
                                                           const bf16* __restrict__ u_lo, const float* __restrict__ gamma,
                                                           const float* __restrict__ stats, bf16* __restrict__ du_hi,
                                                           bf16* __restrict__ du_lo, float* __restrict__ dgamma,
-                                                          float* __restrict__ dbeta, int HW, int C, int G) {
-    const int b = blockIdx.x;
+                                                          float* __restrict__ dbeta, int HW, int C, int G, int ncl) {
+    const int b = blockIdx.x / ncl;
+    const unsigned crank = ncl > 1 ? gn_cluster_rank() : 0u;
     const int cg = C / 8;
     const int g = threadIdx.x % cg;
     const int rl = threadIdx.x / cg;
     const int rpb = 256 / cg;
     const int cpg = C / G;
+    const int rows = HW / ncl, r_begin = (int)crank * rows;
     __shared__ float sm[2][256][8 + 1];
     __shared__ float gred[64][2];
+    __shared__ double part[64][2];
     float mu[8], rs[8], ga[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -856,7 +909,7 @@ __global__ void __launch_bounds__(256) gn_relu_bwd_kernel(const bf16* __restrict
 #pragma unroll
     for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
     const long base = (long)b * HW * cg;
-    for (int r = rl; r < HW; r += rpb) {
+    for (int r = r_begin + rl; r < r_begin + rows; r += rpb) {
         const long off = base + (long)r * cg + g;
         float gv[8], y[8], u[8];
         load8(g_hi, g_lo, off, gv);
@@ -876,7 +929,7 @@ __global__ void __launch_bounds__(256) gn_relu_bwd_kernel(const bf16* __restrict
         sm[1][threadIdx.x][j] = s1[j];
     }
     __syncthreads();
-    // per-channel sums -> dgamma/dbeta (atomics over samples) and per-group means of dxh, dxh*xh
+    // per-channel sums -> dgamma/dbeta (atomics over samples / cluster ranks) and per-group sums of dxh, dxh*xh
     __shared__ float chs[2][128];
     for (int c = threadIdx.x; c < C; c += 256) {
         const int gg = c / 8, j = c % 8;
@@ -893,17 +946,28 @@ __global__ void __launch_bounds__(256) gn_relu_bwd_kernel(const bf16* __restrict
     __syncthreads();
     if (threadIdx.x < G) {
         const int grp = threadIdx.x;
-        float a0 = 0.f, a1 = 0.f;
+        double a0 = 0, a1 = 0;
         for (int c = grp * cpg; c < (grp + 1) * cpg; ++c) {
-            a0 += chs[0][c] * gamma[c];
-            a1 += chs[1][c] * gamma[c];
+            a0 += (double)chs[0][c] * gamma[c];
+            a1 += (double)chs[1][c] * gamma[c];
         }
-        const float n = (float)HW * cpg;
-        gred[grp][0] = a0 / n;
-        gred[grp][1] = a1 / n;
+        part[grp][0] = a0;
+        part[grp][1] = a1;
+    }
+    if (ncl > 1) gn_cluster_sync(); else __syncthreads();
+    if (threadIdx.x < G) {
+        const int grp = threadIdx.x;
+        double a0 = 0, a1 = 0;
+        for (int r = 0; r < ncl; ++r) {
+            a0 += ncl > 1 ? gn_remote_f64(&part[grp][0], r) : part[grp][0];
+            a1 += ncl > 1 ? gn_remote_f64(&part[grp][1], r) : part[grp][1];
+        }
+        const double n = (double)HW * cpg;
+        gred[grp][0] = (float)(a0 / n);
+        gred[grp][1] = (float)(a1 / n);
     }
     __syncthreads();
-    for (int r = rl; r < HW; r += rpb) {
+    for (int r = r_begin + rl; r < r_begin + rows; r += rpb) {
         const long off = base + (long)r * cg + g;
         float gv[8], y[8], u[8], o[8];
         load8(g_hi, g_lo, off, gv);
@@ -918,6 +982,7 @@ __global__ void __launch_bounds__(256) gn_relu_bwd_kernel(const bf16* __restrict
         }
         store8(du_hi, du_lo, off, o);
     }
+    if (ncl > 1) gn_cluster_sync();
 }
 
 // out (bf16 hi/lo) = a + b   (gradient merge of two branches)
@@ -1147,17 +1212,45 @@ extern "C" int gdrn_gn_relu_fwd(const void* u_hi, const void* u_lo, void* y_hi, 
                                 const float* beta, float* stats, int B, int HW, int C, int G, float eps, void* stream_) {
     STREAM;
     if (C != 128 || G > 64 || C % G) return set_error(GDRN_ERR_ARG, "gn_relu_fwd: only C=128 supported");
-    gn_relu_fwd_kernel<<<B, 256, 0, stream>>>(CBF(u_hi), CBF(u_lo), BF(y_hi), BF(y_lo), gamma, beta, stats, HW, C, G, eps);
-    LAUNCH_DONE();
+    const int ncl = (HW % (kGnCluster * 16) == 0) ? kGnCluster : 1;  // a sample's rows split over a cluster of CTAs (DSMEM exchange)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(B * ncl);
+    cfg.blockDim = dim3(256);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ncl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GDRN_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_relu_fwd_kernel, CBF(u_hi), CBF(u_lo), BF(y_hi), BF(y_lo), gamma, beta, stats, HW, C, G, eps, ncl));
+    count_launch();
+    return 0;
 }
 extern "C" int gdrn_gn_relu_bwd(const void* g_hi, const void* g_lo, const void* y_hi, const void* u_hi, const void* u_lo,
                                 const float* gamma, const float* stats, void* du_hi, void* du_lo, float* dgamma,
                                 float* dbeta, int B, int HW, int C, int G, void* stream_) {
     STREAM;
     if (C != 128 || G > 64 || C % G) return set_error(GDRN_ERR_ARG, "gn_relu_bwd: only C=128 supported");
-    gn_relu_bwd_kernel<<<B, 256, 0, stream>>>(CBF(g_hi), CBF(g_lo), CBF(y_hi), CBF(u_hi), CBF(u_lo), gamma, stats, BF(du_hi),
-                                              BF(du_lo), dgamma, dbeta, HW, C, G);
-    LAUNCH_DONE();
+    const int ncl = (HW % (kGnCluster * 16) == 0) ? kGnCluster : 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(B * ncl);
+    cfg.blockDim = dim3(256);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ncl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GDRN_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_relu_bwd_kernel, CBF(g_hi), CBF(g_lo), CBF(y_hi), CBF(u_hi), CBF(u_lo), gamma, stats,
+                                    BF(du_hi), BF(du_lo), dgamma, dbeta, HW, C, G, ncl));
+    count_launch();
+    return 0;
 }
 extern "C" int gdrn_add2(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* o_hi, void* o_lo,
                          long n, void* stream_) {

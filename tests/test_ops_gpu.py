@@ -363,10 +363,11 @@ def test_maxpool_upsample_zero_insert(planes):
 
 
 @pytest.mark.parametrize("planes", [1, 2])
-def test_groupnorm_relu(planes):
+@pytest.mark.parametrize("H", [6, 8, 16, 32])  # 8 / 16 / 32: a sample split over a 4-CTA cluster (DSMEM), 6: single-CTA fallback
+def test_groupnorm_relu(planes, H):
     ops = _ops()
-    g = torch.Generator(device="cuda").manual_seed(11)
-    B, H = 3, 16
+    g = torch.Generator(device="cuda").manual_seed(11 + H)
+    B = 3
     u = torch.randn(B, 128, H, H, device="cuda", generator=g) * 1.5 + 0.3
     gamma = (torch.rand(128, device="cuda", generator=g) + 0.5).requires_grad_(True)
     beta = (torch.randn(128, device="cuda", generator=g) * 0.1).requires_grad_(True)
