@@ -41,11 +41,13 @@ def main():
             continue
         header, units = rows[0], rows[1]
         name = os.path.splitext(os.path.basename(rep))[0]
+        short = re.sub(r"^r2[a-z]_", "r2_", name)
         lines = [f"== {name}  (ncu --set full --clock-control none --import-source on; one launch per row; `python tools/ncu_facts.py`)"]
         for r in rows[2:]:
             d = dict(zip(header, r))
             u = dict(zip(header, units))
-            kname = re.sub(r"\(.*", "", d.get("Kernel Name", "")).replace("void ", "")
+            kname = d.get("Kernel Name", "").replace("(int)", "").replace("(bool)", "")
+            kname = re.sub(r"\(.*", "", kname).replace("void ", "")
             lines.append(f"   Kernel Name                                                   {kname}   grid {d.get('Grid Size')} block {d.get('Block Size')}")
             for k in KEEP:
                 if k in d:
@@ -60,10 +62,10 @@ def main():
                 tp = d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")
                 facts[key] = {"dram_bytes_per_launch": rd + wr, "duration_us": round(dur_s * 1e6, 1),
                               "tensor_pipe_pct": float(tp) if tp not in (None, "", "n/a") else None,
-                              "note": f"ncu --set full of one launch ({name}.ncu-rep, profiles/{name}.txt): DRAM {rd / 1e6:.1f} MB read + {wr / 1e6:.1f} MB written"}
+                              "note": f"ncu --set full of one launch (profiles/{short}.txt): DRAM {rd / 1e6:.1f} MB read + {wr / 1e6:.1f} MB written"}
             lines.append("")
         txt = "\n".join(lines)
-        open(os.path.join(ROOT, "profiles", name.replace("r2d_", "r2_") + ".txt"), "w").write(txt)
+        open(os.path.join(ROOT, "profiles", short + ".txt"), "w").write(txt)
         print(txt)
     json.dump(facts, open(facts_path, "w"), indent=1)
 
