@@ -501,3 +501,44 @@ def test_pose_errors_match_pysixd_restatement():
         assert abs(float(out["adi"][i]) - adi) <= 1e-5 * adi + 1e-8, (i, float(out["adi"][i]), adi)
         assert abs(float(out["re"][i]) - O._re_deg(R_est[i].numpy(), R_gt[i].numpy())) < 1e-3
         assert abs(float(out["te"][i]) - float(np.linalg.norm(t_gt[i].numpy() - t_est[i].numpy()))) < 1e-6
+
+
+def test_roi_crop_and_targets_match_cv2_restatement():
+    """f-3: gdr_net_b200.roi_targets (cv2.warpAffine's fixed-point sampling restated in two kernels) against the reference's own
+    procedure run with cv2 / scipy (oracle/roi_oracle.py): nearest-sampled targets, region labels and the float crops exact (up to
+    fp32 rounding), the uint8 image within one grey level on < 2 % of the values."""
+    import numpy as np
+
+    from gdr_net_b200.roi_targets import make_roi_batch
+    from oracle import roi_oracle as RO
+
+    rng = np.random.default_rng(3)
+    B, H, W, F_ = 5, 480, 640, 64
+    img = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    xyz = np.zeros((B, H, W, 3), np.float32)
+    seg = np.zeros((B, H, W), np.float32)
+    trunc = (rng.random((B, H, W)) > 0.2).astype(np.float32)
+    centers = np.stack([rng.uniform(200, 440, B), rng.uniform(150, 330, B)], 1).astype(np.float32)
+    centers[4] = [30.0, 20.0]  # crop hanging over the image border
+    scales = rng.uniform(90, 300, B).astype(np.float32)
+    ext = rng.uniform(0.05, 0.3, (B, 3)).astype(np.float32)
+    fps = ((rng.random((B, F_, 3)) - 0.5) * ext[:, None, :]).astype(np.float32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for b in range(B):
+        blob = ((xx - centers[b, 0]) ** 2 + (yy - centers[b, 1]) ** 2) < (0.35 * scales[b]) ** 2
+        xyz[b][blob] = ((rng.random((int(blob.sum()), 3)) - 0.5) * ext[b]).astype(np.float32)
+        seg[b] = (blob & (rng.random((H, W)) > 0.1)).astype(np.float32)
+    out = make_roi_batch(torch.from_numpy(img).cuda(), torch.from_numpy(xyz).cuda(), torch.from_numpy(seg).cuda(), torch.from_numpy(trunc).cuda(),
+                         torch.from_numpy(centers).cuda(), torch.from_numpy(scales).cuda(), torch.from_numpy(ext).cuda(), torch.from_numpy(fps).cuda())
+    torch.cuda.synchronize()
+    for b in range(B):
+        ref = RO.roi_instance(img[b], xyz[b], seg[b], trunc[b], centers[b], float(scales[b]), ext[b], fps[b])
+        for k in ("roi_mask_trunc", "roi_mask_visib", "roi_mask_obj"):
+            assert np.array_equal(out[k][b].cpu().numpy(), ref[k]), (b, k)
+        assert np.array_equal(out["roi_region"][b].cpu().numpy(), ref["roi_region"]), b
+        assert np.abs(out["roi_xyz"][b].cpu().numpy() - ref["roi_xyz"]).max() < 1e-6, b
+        assert np.abs(out["roi_coord_2d"][b].cpu().numpy() - ref["roi_coord_2d"]).max() < 1e-6, b
+        d = np.abs(out["roi_img"][b].cpu().numpy() - ref["roi_img"]) * 255.0
+        assert d.max() <= 1.0 + 1e-3 and (d > 0.5).mean() < 0.02, (b, d.max(), (d > 0.5).mean())
+        assert abs(float(out["resize_ratio"][b]) - ref["resize_ratio"]) < 1e-6
+    assert int(out["roi_region"].max()) > 1 and float(out["roi_mask_visib"].sum()) > 100
