@@ -58,7 +58,7 @@ def main():
                 dur = float(d["gpu__time_duration.sum"].replace(",", ""))
                 dur_s = dur * {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3}.get(u["gpu__time_duration.sum"], 1e-9)
                 lines.append(f"   => DRAM read+write {(rd + wr) / 1e6:.1f} MB in {dur_s * 1e6:.1f} us = {(rd + wr) / dur_s / 1e9:.0f} GB/s")
-                key = "gdrn::" + kname.split("gdrn::")[-1].replace("<unnamed>::", "")
+                key = "gdrn::" + kname.split("gdrn::")[-1].replace("<unnamed>::", "").replace("unnamed>::", "")
                 tp = d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")
                 facts[key] = {"dram_bytes_per_launch": rd + wr, "duration_us": round(dur_s * 1e6, 1),
                               "tensor_pipe_pct": float(tp) if tp not in (None, "", "n/a") else None,
