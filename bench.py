@@ -391,6 +391,7 @@ def roofline_live(main, peaks):
 
     eng = main["eng"]
     hook, eng.grad_hook = eng.grad_hook, None  # rank-0-only instrumentation pass: no collectives
+    side, eng.wgrad_side_stream = eng.wgrad_side_stream, False  # the per-launch CUDA events bracket kernels on ONE stream
     batch = main["batch"]
     x = batch["roi_img"].float().contiguous()
     aux = {k: (v.float().contiguous() if isinstance(v, torch.Tensor) and v.dtype != torch.long else v)
@@ -453,6 +454,7 @@ def roofline_live(main, peaks):
         for n, f in orig.items():
             setattr(ops, n, f)
         eng.grad_hook = hook
+        eng.wgrad_side_stream = side
     step_ms, fwd_ms = e0.elapsed_time(e1), e0.elapsed_time(em)
     fam, inst = {}, {}
     fwd_fl = fwd_gemm_ms = fwd_mma = 0.0

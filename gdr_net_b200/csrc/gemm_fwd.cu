@@ -525,8 +525,8 @@ extern "C" int gdrn_conv_fwd(const void* x_hi, const void* x_lo, const void* w_h
 //   du [N][Ho][Wo][Cy] (Cy % 64 == 0), w = the dgrad-packed weights [Cx_pad][K*K*Cy] with flipped taps (pack_conv_dgrad),
 //   dx [N][2Ho][2Wo][ldc].  k = 1: only phase (0, 0) is computed, the caller passes a zero-filled dx.
 extern "C" int gdrn_conv_dgrad_s2(const void* du_hi, const void* du_lo, const void* w_hi, const void* w_lo, void* dx_hi,
-                                  void* dx_lo, int N, int Ho, int Wo, int Cy, int Cx, int Cx_pad, int K, int pad, int ldc,
-                                  int nsplit, void* stream_) {
+                                  void* dx_lo, const float* bias, float* stats, int N, int Ho, int Wo, int Cy, int Cx, int Cx_pad,
+                                  int K, int pad, int ldc, int act, int nsplit, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (nsplit != 1 && nsplit != 3) return set_error(GDRN_ERR_ARG, "conv_dgrad_s2: nsplit must be 1 or 3");
     if (nsplit == 3 && (du_lo == nullptr || w_lo == nullptr)) return set_error(GDRN_ERR_ARG, "conv_dgrad_s2: lo planes missing");
@@ -575,6 +575,9 @@ extern "C" int gdrn_conv_dgrad_s2(const void* du_hi, const void* du_lo, const vo
     p.out_hi = dx_hi;
     p.out_lo = dx_lo;
     p.ldc = ldc;
+    p.bias = bias;    // the same kernel is the FORWARD of ConvTranspose2d(k3, s2, p1, op1) (cdpn_rot_head_region.py:82-91): then
+    p.act = act;      // bias / activation (folded eval BatchNorm) and the BatchNorm batch statistics apply to its output
+    p.stats = stats;
     // phases in order of decreasing tap count (longest tiles first on the persistent CTAs)
     p.nphase = nphase;
     int nt = 0;

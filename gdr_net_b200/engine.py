@@ -30,6 +30,9 @@ _DGRAD_ZERO_INSERT = os.environ.get("GDRN_DGRAD_ZERO_INSERT") == "1"  # A/B swit
 # MEASURED (same box, graphed step): 11.39-11.47 ms with the recompute vs 11.11-11.33 ms reading y -- 2 B/element less HBM
 # traffic does not pay for the extra per-element FMA + compare + shared-memory constants, so it is off.
 _BN_MASK_FROM_U = os.environ.get("GDRN_BN_MASK_FROM_U") == "1"
+# A/B switch: ConvTranspose2d forward / wgrad by output-parity phases over the un-dilated input (default) instead of a
+# stride-1 conv over the zero-inserted input (4x the MACs + a zero_insert pass)
+_DECONV_PHASES = os.environ.get("GDRN_DECONV_PHASES", "1") == "1"
 # A/B switch: BatchNorm forward emits the ReLU mask as a bitmap that backward reads instead of the activation (default on)
 _BN_BITMASK = os.environ.get("GDRN_BN_BITMASK", "1") == "1"
 
@@ -261,7 +264,8 @@ class Engine:
                         wfe[ck] = PT((64, 192), pl, device=self.dev, zero=True)
                         ops._pack(w, wfe[ck], 64, 3, 7, 7, 64, 3, 192, 147, 49, 7, 1, 0)
                     elif ck == "deconv":
-                        wfe[ck] = ops.pack_deconv_fwd(self.model.rot_head_net.features[0].weight, pl)
+                        pk = ops.pack_deconv_fwd_phases if _DECONV_PHASES else ops.pack_deconv_fwd
+                        wfe[ck] = pk(self.model.rot_head_net.features[0].weight, pl)
                     else:
                         wfe[ck] = ops.pack_conv_fwd(convs[ck].weight, pl)
                     scales.append(sc[bk])
@@ -301,8 +305,10 @@ class Engine:
 
         def cbr(xin, ck, bk, conv, relu=True, res=None, kind="conv"):
             if kind == "deconv":
-                return ops.conv_fwd(xin, wfe[ck], conv.out_channels, 3, 3, 1, 1, bias=shift[bk], act=2 if relu else 0, res=res,
-                                    algo_scale=0.25)
+                if _DECONV_PHASES:
+                    return ops.conv_dgrad_s2(xin, wfe[ck], conv.out_channels, 3, 1, bias=shift[bk], act=2 if relu else 0)
+                return ops.conv_fwd(ops.zero_insert(xin), wfe[ck], conv.out_channels, 3, 3, 1, 1, bias=shift[bk], act=2 if relu else 0,
+                                    res=res, algo_scale=0.25)
             k, stride, pad = conv.kernel_size[0], conv.stride[0], conv.padding[0]
             return ops.conv_fwd(xin, wfe[ck], conv.out_channels, k, k, stride, pad, bias=shift[bk], act=2 if relu else 0, res=res)
 
@@ -321,7 +327,7 @@ class Engine:
                     idn = cbr(cur, p + ".downsample.0", p + ".downsample.1", blk.downsample[0], relu=False)
                 cur = cbr(a1, p + ".conv2", p + ".bn2", blk.conv2, res=idn)
         hf = m.rot_head_net.features
-        cur = cbr(ops.zero_insert(cur), "deconv", "rot_head_net.features.1", hf[0], kind="deconv")
+        cur = cbr(cur, "deconv", "rot_head_net.features.1", hf[0], kind="deconv")
         for ci, bi, up in HEAD_CONVS:
             if up:
                 cur = ops.upsample2x_fwd(cur)
@@ -398,7 +404,7 @@ class Engine:
             if need_dgrad:
                 wd[key] = ops.pack_conv_dgrad(conv.weight, bpl, out=wd.get(key))
         dc = m.rot_head_net.features[0]
-        wf["deconv"] = ops.pack_deconv_fwd(dc.weight, pl, out=wf.get("deconv"))
+        wf["deconv"] = (ops.pack_deconv_fwd_phases if _DECONV_PHASES else ops.pack_deconv_fwd)(dc.weight, pl, out=wf.get("deconv"))
         if need_dgrad:
             wd["deconv"] = ops.pack_deconv_dgrad(dc.weight, bpl, out=wd.get("deconv"))
         pn = m.pnp_net
@@ -454,7 +460,9 @@ class Engine:
         st = self.bn[bkey]
         stats = st.stats if (train_bn and not self.deterministic) else None  # deterministic: statistics from gdrn_bn_stats
         k, stride, pad = conv.kernel_size[0], conv.stride[0], conv.padding[0]
-        if kind == "deconv":
+        if kind == "deconv" and _DECONV_PHASES:
+            u = ops.conv_dgrad_s2(x, self.wf["deconv"], conv.out_channels, 3, 1, stats=stats)
+        elif kind == "deconv":
             u = ops.conv_fwd(x, self.wf["deconv"], conv.out_channels, 3, 3, 1, 1, stats=stats, algo_scale=0.25)
         else:
             u = ops.conv_fwd(x, self.wf[wkey or ckey], conv.out_channels, k, k, stride, pad, stats=stats)
@@ -551,7 +559,7 @@ class Engine:
 
         # ---- a2: geometry head (cdpn_rot_head_region.py:80-135)
         hf = m.rot_head_net.features
-        z = ops.zero_insert(feat)
+        z = feat if _DECONV_PHASES else ops.zero_insert(feat)
         u, y = self._conv_bn(z, "deconv", hf[0], "rot_head_net.features.1", True, train_bn, kind="deconv")
         if S is not None:
             S["deconv"] = dict(z=z, u=u, y=y, m=self._last_mask)
@@ -774,6 +782,12 @@ class Engine:
         D = S["deconv"]
         du, _ = self._bn_bwd("rot_head_net.features.1", g, None, h(D["y"]), h(D["u"]), relu_from_u=True, mask=D["m"])
         def deconv_wgrad(du=du):
+            if _DECONV_PHASES:
+                # d wt[ci][co][r][s] = sum_q x[ci][q] * du[co][2q + (r, s) - 1]: the weight gradient of the stride-2 conv du -> x
+                # with x in the role of dY; its [O = 512][I = 256][3][3] layout IS the ConvTranspose2d IOHW layout (no flip)
+                buf, ks, kss = ops.conv_wgrad(h(D["z"]), du, self.ws, 512, 3, 3, 2, 1)
+                ops.unpack_wgrad(buf, self.grads["rot_head_net.features.0.weight"], 512, 256, 3, 3, 256, ks, kss, 256 * 9, 9, 3, 1)
+                return
             buf, ks, kss = ops.conv_wgrad(du, h(D["z"]), self.ws, 256, 3, 3, 1, 1)
             # ConvTranspose2d weight is IOHW [512][256][3][3] with flipped taps relative to the equivalent conv
             ops.unpack_wgrad(buf, self.grads["rot_head_net.features.0.weight"], 256, 512, 3, 3, 512, ks, kss, 9, 256 * 9, 3, 1, flip=1)

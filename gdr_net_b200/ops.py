@@ -143,9 +143,16 @@ def pack_conv_dgrad(w: torch.Tensor, planes: int, out: PT | None = None) -> PT:
     return out
 
 
+def pack_deconv_fwd_phases(wt: torch.Tensor, planes: int, out: PT | None = None) -> PT:
+    """ConvTranspose2d IOHW [Cin][Cout][k][k] -> the operand of gdrn_conv_dgrad_s2 (rows = Cout, cols = taps x Cin, flipped taps):
+    the transposed conv's forward IS the data gradient of the stride-2 conv whose OIHW weight this tensor is, evaluated by output
+    parity over the un-dilated input (no zero-inserted tensor, 1/4 of the MACs)."""
+    return pack_conv_dgrad(wt, planes, out=out)
+
+
 def pack_deconv_fwd(wt: torch.Tensor, planes: int, out: PT | None = None) -> PT:
     """ConvTranspose2d IOHW [Cin][Cout][k][k] -> equivalent stride-1 conv over the zero-inserted input
-    (taps flipped): rows = Cout, cols = Cin."""
+    (taps flipped): rows = Cout, cols = Cin.  (First formulation, kept for the op tests / A-B.)"""
     I, O, KH, KW = wt.shape
     opad, ipad = _round_up(O, 64), _round_up(I, 64)
     krow = KH * KW * ipad
@@ -216,15 +223,15 @@ def conv_fwd(x: PT, wp: PT, Cout: int, KH: int, KW: int, stride: int, pad: int, 
     return out
 
 
-def conv_dgrad_s2(du: PT, wd: PT, Cx: int, K: int, pad: int, *, out: PT | None = None) -> PT:
+def conv_dgrad_s2(du: PT, wd: PT, Cx: int, K: int, pad: int, *, out: PT | None = None, bias=None, stats=None, act: int = 0) -> PT:
     """dX of a stride-2 conv (k3 p1 / k1 p0) from the UN-dilated dY, decomposed by output parity (gdrn_conv_dgrad_s2);
     wd = pack_conv_dgrad(weight).  Replaces zero_insert + stride-1 conv (4x the MACs, plus the dilated tensor in HBM)."""
     N, Ho, Wo, Cy = du.shape
     ldc = _round_up(Cx, 64)
     if out is None:
         out = PT((N, 2 * Ho, 2 * Wo, ldc), du.planes, device=du.buf.device, zero=(K == 1 or ldc != Cx))
-    C.gdrn_conv_dgrad_s2(du.hi_ptr, du.lo_ptr, wd.hi_ptr, wd.lo_ptr, out.hi_ptr, out.lo_ptr, N, Ho, Wo, Cy, Cx, wd.shape[0], K,
-                         pad, ldc, du.nsplit, _stream())
+    C.gdrn_conv_dgrad_s2(du.hi_ptr, du.lo_ptr, wd.hi_ptr, wd.lo_ptr, out.hi_ptr, out.lo_ptr, ptr(bias), ptr(stats), N, Ho, Wo, Cy, Cx,
+                         wd.shape[0], K, pad, ldc, act, du.nsplit, _stream())
     return out
 
 

@@ -51,9 +51,12 @@ int gdrn_conv_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const vo
 
 /* Data gradient of a stride-2 conv (k3 p1 / k1 p0) by output-parity phases over the un-dilated dY: replaces the reference's
  * cuDNN conv-backward-data for the stride-2 layers (resnet_backbone.py layerN.0.conv1 / downsample, conv_pnp_net.py:76-80).
- * du [N][Ho][Wo][Cy], w = dgrad-packed weights (flipped taps), dx [N][2Ho][2Wo][ldc]; k1: dx must be pre-zeroed. */
+ * du [N][Ho][Wo][Cy], w = dgrad-packed weights (flipped taps), dx [N][2Ho][2Wo][ldc]; k1: dx must be pre-zeroed.
+ * The same arithmetic is the FORWARD of nn.ConvTranspose2d(k3, s2, p1, output_padding 1) (cdpn_rot_head_region.py:82-91; its IOHW
+ * weight is the OIHW weight of the transposed conv): bias / act / stats (optional) then apply to the output like gdrn_conv_fwd. */
 int gdrn_conv_dgrad_s2(const void* du_hi, const void* du_lo, const void* w_hi, const void* w_lo, void* dx_hi, void* dx_lo,
-                       int N, int Ho, int Wo, int Cy, int Cx, int Cx_pad, int K, int pad, int ldc, int nsplit, void* stream);
+                       const float* bias, float* stats, int N, int Ho, int Wo, int Cy, int Cx, int Cx_pad, int K, int pad, int ldc,
+                       int act, int nsplit, void* stream);
 
 /* ---- plain GEMM  y[M][N] = a[M][K] * w[N_pad][K]^T (+bias, act); replaces nn.Linear (conv_pnp_net.py:89-92,
  * 152-156), the 7x7 stem over its im2col matrix (resnet_backbone.py:69) and their dgrads. */
