@@ -29,7 +29,11 @@ def make_roi_batch(image_u8: torch.Tensor, xyz: torch.Tensor, mask_visib: torch.
     image_u8 = image_u8.contiguous()
     xyz, mask_visib = _f(xyz, dev), _f(mask_visib, dev)
     mask_trunc = None if mask_trunc is None else _f(mask_trunc, dev)
-    centers, scales, extents, fps = _f(bbox_center, dev).reshape(B, 2), _f(scale, dev).reshape(B), _f(extents, dev).reshape(B, 3), _f(fps_points, dev)
+    # bbox centre / scale stay float64 like the reference's aug_bbox output: get_affine_transform rounds them to float32 at specific
+    # points of its computation and the kernels reproduce exactly those roundings
+    centers = torch.as_tensor(bbox_center).to(dev).double().reshape(B, 2).contiguous()
+    scales = torch.as_tensor(scale).to(dev).double().reshape(B).contiguous()
+    extents, fps = _f(extents, dev).reshape(B, 3), _f(fps_points, dev)
     if xyz.shape != (B, H, W, 3) or mask_visib.shape != (B, H, W) or fps.dim() != 3 or fps.shape[0] != B or fps.shape[2] != 3:
         raise ValueError("make_roi_batch: inconsistent shapes")
     s = torch.cuda.current_stream().cuda_stream
@@ -45,5 +49,5 @@ def make_roi_batch(image_u8: torch.Tensor, xyz: torch.Tensor, mask_visib: torch.
                        scales.data_ptr(), extents.data_ptr(), fps.data_ptr(), fps.shape[1], out["roi_xyz"].data_ptr(),
                        out["roi_mask_trunc"].data_ptr(), out["roi_mask_visib"].data_ptr(), out["roi_mask_obj"].data_ptr(),
                        out["roi_region"].data_ptr(), out["roi_coord_2d"].data_ptr(), B, H, W, out_res, s)
-    out["resize_ratio"] = out_res / scales  # data_loader.py:621
+    out["resize_ratio"] = (out_res / scales).float()  # data_loader.py:621
     return out

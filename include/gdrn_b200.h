@@ -168,13 +168,13 @@ int gdrn_loss_finalize(const double* pix_sums, const double* pose_sums, const fl
 
 /* ---- per-instance crop / target generation of the data loader on the device (core/gdrn_modeling/data_loader.py:487-560,
  * core/utils/data_utils.py:80-137 crop_resize_by_warp_affine, :213-219 xyz_to_region), cv2.warpAffine's fixed-point sampling
- * restated.  image_u8 [B][H][W][3] (BGR uint8), centers [B][2], scales [B] -> roi_img [B][3][R][R] = bilinear crop / pixel_std.
+ * restated.  image_u8 [B][H][W][3] (BGR uint8), centers [B][2], scales [B] (float64 like the reference's aug_bbox output) -> roi_img [B][3][R][R] = bilinear crop / pixel_std.
  * xyz [B][H][W][3] (object coordinates, 0 = background), mask_visib / mask_trunc [B][H][W] (mask_trunc may be NULL),
  * extents [B][3], fps_points [B][n_fps][3] -> roi_xyz [B][3][R][R] (normalised), roi_mask_{trunc,visib,obj} [B][R][R],
  * roi_region [B][R][R] int64 (0 = background), roi_coord_2d [B][2][R][R]. */
-int gdrn_roi_crop_image(const void* image_u8, const float* centers, const float* scales, float* roi_img, int B, int H, int W,
+int gdrn_roi_crop_image(const void* image_u8, const double* centers, const double* scales, float* roi_img, int B, int H, int W,
                         int out_res, float pixel_std, void* stream);
-int gdrn_roi_targets(const float* xyz, const float* mask_visib, const float* mask_trunc, const float* centers, const float* scales,
+int gdrn_roi_targets(const float* xyz, const float* mask_visib, const float* mask_trunc, const double* centers, const double* scales,
                      const float* extents, const float* fps_points, int n_fps, float* roi_xyz, float* roi_mask_trunc,
                      float* roi_mask_visib, float* roi_mask_obj, long long* roi_region, float* roi_coord_2d, int B, int H, int W,
                      int out_res, void* stream);

@@ -8,25 +8,37 @@ import numpy as np
 from scipy.spatial.distance import cdist
 
 
+def _get_dir(src_point, rot_rad):
+    """core/utils/data_utils.py:151-158"""
+    sn, cs = np.sin(rot_rad), np.cos(rot_rad)
+    src_result = [0, 0]
+    src_result[0] = src_point[0] * cs - src_point[1] * sn
+    src_result[1] = src_point[0] * sn + src_point[1] * cs
+    return src_result
+
+
+def _get_3rd_point(a, b):
+    """core/utils/data_utils.py:146-148"""
+    direct = a - b
+    return b + np.array([-direct[1], direct[0]], dtype=np.float32)
+
+
 def get_affine_transform(center, scale, output_size):
-    """core/utils/data_utils.py:96-137 with rot = 0, shift = 0."""
-    center = np.asarray(center, dtype=np.float32)
-    src_w, dst_w, dst_h = float(scale), output_size, output_size
-    src_dir = np.array([0, src_w * -0.5], np.float32)
+    """core/utils/data_utils.py:96-137 with rot = 0, shift = 0, inv = False; `scale` = (s, s) as crop_resize_by_warp_affine passes it.
+    Operand types are kept as in the reference (float64 centre / scale, float32 point arrays): their roundings matter."""
+    scale_tmp = (scale, scale)
+    shift = np.array([0, 0], dtype=np.float32)
+    src_w, dst_w, dst_h = scale_tmp[0], output_size, output_size
+    src_dir = _get_dir([0, src_w * -0.5], np.pi * 0 / 180)
     dst_dir = np.array([0, dst_w * -0.5], np.float32)
     src = np.zeros((3, 2), dtype=np.float32)
     dst = np.zeros((3, 2), dtype=np.float32)
-    src[0, :] = center
-    src[1, :] = center + src_dir
+    src[0, :] = center + scale_tmp * shift
+    src[1, :] = center + src_dir + scale_tmp * shift
     dst[0, :] = [dst_w * 0.5, dst_h * 0.5]
     dst[1, :] = np.array([dst_w * 0.5, dst_h * 0.5], np.float32) + dst_dir
-
-    def third(a, b):  # get_3rd_point
-        d = a - b
-        return b + np.array([-d[1], d[0]], dtype=np.float32)
-
-    src[2:, :] = third(src[0, :], src[1, :])
-    dst[2:, :] = third(dst[0, :], dst[1, :])
+    src[2:, :] = _get_3rd_point(src[0, :], src[1, :])
+    dst[2:, :] = _get_3rd_point(dst[0, :], dst[1, :])
     return cv2.getAffineTransform(np.float32(src), np.float32(dst))
 
 

@@ -518,14 +518,14 @@ def test_roi_crop_and_targets_match_cv2_restatement():
     xyz = np.zeros((B, H, W, 3), np.float32)
     seg = np.zeros((B, H, W), np.float32)
     trunc = (rng.random((B, H, W)) > 0.2).astype(np.float32)
-    centers = np.stack([rng.uniform(200, 440, B), rng.uniform(150, 330, B)], 1).astype(np.float32)
-    centers[4] = [30.0, 20.0]  # crop hanging over the image border
-    scales = rng.uniform(90, 300, B).astype(np.float32)
+    centers = np.stack([rng.uniform(200, 440, B), rng.uniform(150, 330, B)], 1)  # float64, like the reference's aug_bbox output
+    centers[4] = [30.3, 20.7]  # crop hanging over the image border
+    scales = rng.uniform(90, 300, B)
     ext = rng.uniform(0.05, 0.3, (B, 3)).astype(np.float32)
     fps = ((rng.random((B, F_, 3)) - 0.5) * ext[:, None, :]).astype(np.float32)
     yy, xx = np.mgrid[0:H, 0:W]
     for b in range(B):
-        blob = ((xx - centers[b, 0]) ** 2 + (yy - centers[b, 1]) ** 2) < (0.35 * scales[b]) ** 2
+        blob = ((xx - centers[b, 0]) ** 2 + (yy - centers[b, 1]) ** 2) < (0.35 * scales[b]) ** 2  # noqa: E501
         xyz[b][blob] = ((rng.random((int(blob.sum()), 3)) - 0.5) * ext[b]).astype(np.float32)
         seg[b] = (blob & (rng.random((H, W)) > 0.1)).astype(np.float32)
     out = make_roi_batch(torch.from_numpy(img).cuda(), torch.from_numpy(xyz).cuda(), torch.from_numpy(seg).cuda(), torch.from_numpy(trunc).cuda(),
@@ -533,17 +533,19 @@ def test_roi_crop_and_targets_match_cv2_restatement():
     torch.cuda.synchronize()
     for b in range(B):
         ref = RO.roi_instance(img[b], xyz[b], seg[b], trunc[b], centers[b], float(scales[b]), ext[b], fps[b])
-        # The sampling positions are evaluated like cv2 (10-bit fixed point); the inverse affine map itself is formed analytically
-        # here and by cv2.getAffineTransform + inversion there, so a position that lands within ~1e-13 of a rounding boundary can
-        # fall on the other side: allow a handful of such pixels (one source pixel / one 1/32-pixel step), everything else exact.
+        # The sampling positions are evaluated like cv2 (10-bit fixed point) from an inverse affine map obtained with the reference's
+        # own operation sequence (float32 points, OpenCV's 6x6 LU, warpAffine's inversion -- bit-identical to cv2.getAffineTransform
+        # on the host), so the nearest-sampled targets and labels are expected to be EXACT; the thresholds only leave room for a
+        # stray pixel.
         for k in ("roi_mask_trunc", "roi_mask_visib", "roi_mask_obj"):
-            assert (out[k][b].cpu().numpy() != ref[k]).mean() < 2e-3, (b, k)
+            assert (out[k][b].cpu().numpy() != ref[k]).mean() < 5e-4, (b, k)
         region_bad = out["roi_region"][b].cpu().numpy() != ref["roi_region"]
-        assert region_bad.mean() < 2e-3, (b, region_bad.mean())
+        assert region_bad.mean() < 5e-4, (b, region_bad.mean())
         dx = np.abs(out["roi_xyz"][b].cpu().numpy() - ref["roi_xyz"])
-        assert (dx > 1e-6).mean() < 2e-3, (b, (dx > 1e-6).mean())
+        assert (dx > 1e-6).mean() < 5e-4, (b, (dx > 1e-6).mean())
         dc = np.abs(out["roi_coord_2d"][b].cpu().numpy() - ref["roi_coord_2d"])
-        assert dc.max() < 1.01 / (32.0 * (W - 1)) + 1e-6 and (dc > 1e-6).mean() < 2e-2, (b, dc.max(), (dc > 1e-6).mean())
+        assert dc.max() < 1.01 / (32.0 * (W - 1)) + 1e-6 and (dc > 1e-6).mean() < 5e-4, (b, dc.max(), (dc > 1e-6).mean())
+        print(f"roi {b}: mask/region mismatches {int(region_bad.sum())}, coord max diff {dc.max():.1e}")
         d = np.abs(out["roi_img"][b].cpu().numpy() - ref["roi_img"]) * 255.0
         assert d.max() <= 1.0 + 1e-3 and (d > 0.5).mean() < 0.02, (b, d.max(), (d > 0.5).mean())
         assert abs(float(out["resize_ratio"][b]) - ref["resize_ratio"]) < 1e-6
