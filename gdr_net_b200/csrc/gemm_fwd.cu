@@ -426,7 +426,7 @@ static bool want_2cta(int nsplit, int block_n, int num_m_tiles, int num_n_tiles)
         g_2cta_mode = e ? atoi(e) : 1;
     }
     if (g_2cta_mode != 1 || (num_m_tiles & 1)) return false;
-    if (!((nsplit == 1 && block_n == 256) || (nsplit == 3 && block_n == 128))) return false;
+    if (!((nsplit == 1 && (block_n == 256 || block_n == 128)) || (nsplit == 3 && block_n == 128))) return false;
     return (num_m_tiles / 2) * num_n_tiles * 4 >= num_sms();
 }
 

@@ -43,8 +43,8 @@ struct Cfg2 {
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kAux + 1024;
     static constexpr int NACC = (NSPLIT == 3) ? 2 : 1;  // main (+ cross-term) accumulator
-    static constexpr int TMEM_COLS = 2 * NACC * BLOCK_N;
-    static_assert(TMEM_COLS == 512, "two accumulator sets fill the 512 TMEM columns");
+    static constexpr int TMEM_COLS = 2 * NACC * BLOCK_N;  // two accumulator sets (the allocation is always the full 512 columns)
+    static_assert(TMEM_COLS <= 512, "TMEM overflow");
     static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
@@ -345,11 +345,12 @@ int launch2(const GemmParams& p, cudaStream_t stream) {
 
 }  // namespace
 
-// block_n is the PAIR tile width: 256 (1 pass) or 128 (3 pass); p.num_n_tiles = Cout_pad / block_n, p.num_m_tiles even,
+// block_n is the PAIR tile width: 256 / 128 (1 pass) or 128 (3 pass); p.num_n_tiles = Cout_pad / block_n, p.num_m_tiles even,
 // weight tensor maps with boxes of block_n / 2 rows (each CTA loads its half), p.nphase == 0.
 int launch_gemm_2cta(const GemmParams& p, int block_n, int nsplit, cudaStream_t stream) {
     if (p.nphase != 0 || (p.num_m_tiles & 1)) return set_error(GDRN_ERR_ARG, "2-CTA tiles: even tile count, no phase decomposition");
     if (nsplit == 1 && block_n == 256) return launch2<256, 1>(p, stream);
+    if (nsplit == 1 && block_n == 128) return launch2<128, 1>(p, stream);  // 128-channel layers: 48 instead of 64 KB of smem traffic per k-block
     if (nsplit == 3 && block_n == 128) return launch2<128, 3>(p, stream);
     return set_error(GDRN_ERR_ARG, "2-CTA tiles: unsupported block_n=%d nsplit=%d", block_n, nsplit);
 }

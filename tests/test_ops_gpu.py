@@ -105,7 +105,8 @@ def test_conv_fwd(planes, case):
 
 
 @pytest.mark.parametrize("planes,case", [(1, (8, 64, 256, 256, 1)), (2, (8, 64, 256, 256, 1)), (1, (16, 32, 128, 256, 1)),
-                                         (2, (16, 32, 128, 128, 1)), (2, (16, 64, 64, 128, 2)), (1, (64, 32, 256, 512, 2))])
+                                         (2, (16, 32, 128, 128, 1)), (2, (16, 64, 64, 128, 2)), (1, (64, 32, 256, 512, 2)),
+                                         (1, (16, 32, 128, 128, 1))])  # last: the 256 x 128 one-pass pair tile
 def test_conv_fwd_2cta_variant(planes, case):
     """The cta_group::2 kernel (one 256 x 256 [1 pass] / 256 x 128 [3 pass] tile per CTA pair) on layers that select it,
     against the 1-CTA kernel's reference AND bit-compared with the 1-CTA kernel itself (same MMAs, same accumulation order)."""
