@@ -16,3 +16,5 @@ print('value', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'parity',
 "
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 timeout 120 python bench.py --impl reference --steps 2 --warmup 1 | tail -c 200
+GDRN_PROFILE=1 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none --kernel-name-base demangled -k regex:"gemm" --csv --log-file gpurun_out/r2j_tensor_pipe.csv python bench.py --quick --no-graph --steps 1 --warmup 3 > gpurun_out/r2j_ncu_tp.log 2>&1; echo "ncu tensor-pipe rc=$?"
+python tools/tensor_pipe_summary.py gpurun_out/r2j_tensor_pipe.csv | head -30
