@@ -230,6 +230,42 @@ def test_conv_wgrad(planes, case):
     assert _rel(grad, gw) < 5e-5
 
 
+@pytest.mark.parametrize("case", [(4, 16, 16, 256, 256, 3, 1, 1), (8, 8, 8, 512, 512, 3, 1, 1), (2, 32, 32, 128, 256, 3, 2, 1),
+                                  (2, 32, 32, 128, 256, 1, 2, 0), (64, 8, 8, 512, 512, 3, 1, 1), (8, 32, 32, 256, 256, 3, 1, 1),
+                                  (3, 16, 16, 256, 512, 3, 2, 1)])
+def test_conv_wgrad_2cta_variant(case):
+    """Single-plane weight gradient on CTA pairs (256 co x 128/256 ci per pair) against autograd AND bit-compared with the
+    1-CTA kernel (same MMAs per accumulator, same k order, same split-K partition)."""
+    ops = _ops()
+    from gdr_net_b200.capi import C
+
+    dll = C.load()
+    N, H, W, Cin, Cout, k, stride, pad = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case) + 5)
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g)
+    w = torch.zeros(Cout, Cin, k, k, device="cuda", requires_grad=True)
+    y = F.conv2d(_operand(x, 1), w, None, stride=stride, padding=pad)
+    dy = torch.randn_like(y) / 8
+    (gw,) = torch.autograd.grad(y, w, _operand(dy, 1))
+    grads = []
+    try:
+        for mode in (1, 0):
+            C.gdrn_set_wgrad_2cta(mode)
+            ws = ops.Workspace()
+            n0 = dll.gdrn_wgrad_2cta_launch_count()
+            buf, ks, ks_stride = ops.conv_wgrad(_nhwc(dy, 1), _nhwc(x, 1), ws, Cout, k, k, stride, pad)
+            grad = torch.zeros_like(w)
+            ops.unpack_wgrad(buf, grad, Cout, Cin, k, k, Cin, ks, ks_stride, Cin * k * k, k * k, k, 1)
+            torch.cuda.synchronize()
+            if mode == 1:
+                assert dll.gdrn_wgrad_2cta_launch_count() == n0 + 1, "the shape did not select the pair kernel"
+            grads.append(grad)
+    finally:
+        C.gdrn_set_wgrad_2cta(1)
+    assert _rel(grads[0], gw) < 5e-5
+    assert torch.equal(grads[0], grads[1])
+
+
 @pytest.mark.parametrize("planes", [1, 2])
 @pytest.mark.parametrize("P,M,N", [(64, 1024, 8192), (2, 64, 256), (4096, 64, 192), (300, 256, 1024)])
 def test_gemm_wgrad(planes, P, M, N):
