@@ -289,7 +289,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) gemm_wgrad_kernel(const __grid_
 // Same reasoning as gemm_fwd2.cu: per 64-pixel k-block the 1-CTA kernel's shared memory serves 48 KB of TMA writes + 4 x 12 KB
 // of MMA operand reads = 96 KB for 512 MMA cycles (187 B/clk against 128 B/clk); in a pair each CTA stages its own 128 output
 // channels of dY but only HALF of the X columns: 32 KB + 4 x 8 KB = 64 KB (125 B/clk).  Eligible: Cout a multiple of 256 (head,
-// layer3, layer4, deconv), no tap packing.  Identical arithmetic / accumulation order to the 1-CTA kernel.
+// layer3, layer4, deconv), no tap packing.  Identical arithmetic / accumulation order to the 1-CTA kernel (bit-equal, tested).
+// MEASURED (profiles/r2_wgrad_2cta_ab.txt): alone under ncu the two long-K head layers go from 76 % to 84 % tensor pipe (210 ->
+// 197 us), every short-K layer (layer3 / layer4, 32 k-blocks per CTA) stays at 33 % -- those are bound by the fixed cost per
+// work item (prologue + 128 KB fp32 partial per CTA + its unpack), not by shared memory.  In the real step the pair kernel runs
+// on the weight-gradient side stream next to main-stream kernels, where a cluster needs BOTH SMs of a TPC free at once: A/B
+// 10.99 / 10.93 ms (off) vs 11.05 / 11.00 ms (on).  Hence default OFF; GDRN_WGRAD_2CTA=1 / gdrn_set_wgrad_2cta(1) enables it.
 template <int N_TILE>
 struct Wgrad2Cfg {
     static constexpr int NCH = N_TILE / 64;      // 64-column chunks of the pair tile
@@ -512,12 +517,12 @@ static int launch_wgrad2(const WgradParams& p, cudaStream_t stream) {
     return 0;
 }
 
-static int g_wgrad_2cta = -1;  // GDRN_WGRAD_2CTA=0 disables the pair kernel (A/B)
+static int g_wgrad_2cta = -1;  // GDRN_WGRAD_2CTA=1 enables the pair kernel (default off: neutral-to-slower in situ, see header comment)
 static std::atomic<long> g_wgrad_2cta_launches{0};
 static bool want_wgrad_2cta(const WgradParams& p, int n_tile, int nsplit) {
     if (g_wgrad_2cta < 0) {
         const char* e = getenv("GDRN_WGRAD_2CTA");
-        g_wgrad_2cta = e ? atoi(e) : 1;
+        g_wgrad_2cta = e ? atoi(e) : 0;
     }
     return g_wgrad_2cta == 1 && nsplit == 1 && !p.tap_pack && (p.num_m_tiles % 2) == 0 && (n_tile == 256 || n_tile == 128) &&
            (p.Mvalid % 256) == 0;
