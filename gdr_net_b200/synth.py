@@ -208,3 +208,54 @@ def seeded_state_dict(template: dict, seed: int = 0) -> dict:
             out[name] = torch.zeros(shape)
         out[name] = out[name].to(t.dtype) if t.dtype.is_floating_point else out[name]
     return out
+
+
+def make_pnp_maps(bs: int, seed: int = 0, res: int = 64, noise: float = 0.004, outlier_frac: float = 0.15, im_wh=(640, 480)) -> dict:
+    """Geometrically consistent test-time head outputs for the RANSAC-PnP path (gdrn_evaluator.py:316-436): an ellipsoid with the
+    object's extent is placed at a random pose, every pixel of the `res` x `res` ROI grid whose viewing ray hits it gets the
+    normalised object coordinate of the hit point (+ Gaussian noise; a fraction of the pixels gets a random coordinate = outlier),
+    the raw mask output is high on the object and low elsewhere (with a few wrong pixels).  Returns CPU tensors:
+    mask [B,1,res,res] (raw, L1-head style), xyz [B,3,res,res] in [0,1], coord_2d [B,2,res,res] in [0,1], extents [B,3], cams
+    [B,3,3], im_wh [B,2], R [B,3,3], t [B,3] (the true pose)."""
+    g = _gen(seed, "pnp_maps")
+    W, H = im_wh
+    K = torch.tensor(LM_K, dtype=torch.float64)
+    R = random_rotations(bs, g).double()
+    ext = (torch.rand(bs, 3, generator=g, dtype=torch.float64) * 0.2 + 0.06)
+    tz = torch.rand(bs, generator=g, dtype=torch.float64) * 0.8 + 0.5
+    cx = torch.rand(bs, generator=g, dtype=torch.float64) * 0.4 * W + 0.3 * W
+    cy = torch.rand(bs, generator=g, dtype=torch.float64) * 0.4 * H + 0.3 * H
+    t = torch.stack([(cx - K[0, 2]) * tz / K[0, 0], (cy - K[1, 2]) * tz / K[1, 1], tz], dim=1)
+    scale = 1.5 * ext.max(dim=1).values / tz * K[0, 0]  # ROI side in pixels
+    lin = (torch.arange(res, dtype=torch.float64) + 0.5) / res - 0.5
+    mask = torch.zeros(bs, 1, res, res)
+    xyz = torch.zeros(bs, 3, res, res)
+    c2d = torch.zeros(bs, 2, res, res)
+    for b in range(bs):
+        u = cx[b] + lin.view(1, res) * scale[b]
+        v = cy[b] + lin.view(res, 1) * scale[b]
+        u, v = u.expand(res, res), v.expand(res, res)
+        c2d[b, 0], c2d[b, 1] = (u / W).float(), (v / H).float()
+        # ray d through the pixel, in the object frame: o = -R^T t, dir = R^T d; unit sphere after scaling by 2 / extent
+        d = torch.stack([(u - K[0, 2]) / K[0, 0], (v - K[1, 2]) / K[1, 1], torch.ones_like(u)], dim=-1)
+        s = 2.0 / ext[b]
+        o = (-(R[b].T @ t[b])) * s
+        dd = (d @ R[b]) * s  # R^T d for row vectors
+        A = (dd * dd).sum(-1)
+        Bq = 2 * (dd * o).sum(-1)
+        Cq = (o * o).sum() - 1.0
+        disc = Bq * Bq - 4 * A * Cq
+        hit = disc > 0
+        lam = (-Bq - torch.sqrt(disc.clamp_min(0))) / (2 * A)
+        p = (o + lam.unsqueeze(-1) * dd) / s  # object-frame point, metres
+        xn = p / ext[b] + 0.5
+        xn = xn + torch.randn(res, res, 3, generator=g, dtype=torch.float64) * noise
+        outl = torch.rand(res, res, generator=g) < outlier_frac
+        xn = torch.where(outl.unsqueeze(-1), torch.rand(res, res, 3, generator=g, dtype=torch.float64), xn)
+        xyz[b] = torch.where(hit.unsqueeze(-1), xn, torch.zeros_like(xn)).permute(2, 0, 1).float()
+        m = torch.where(hit, torch.full_like(A, 0.9), torch.full_like(A, 0.05)) + torch.randn(res, res, generator=g, dtype=torch.float64) * 0.03
+        flip = torch.rand(res, res, generator=g) < 0.01
+        m = torch.where(flip, 0.95 - m, m)
+        mask[b, 0] = m.float()
+    return dict(mask=mask, xyz=xyz, coord_2d=c2d, extents=ext.float(), cams=K.float().expand(bs, 3, 3).contiguous(),
+                im_wh=torch.tensor([[W, H]] * bs, dtype=torch.float32), R=R.float(), t=t.float())

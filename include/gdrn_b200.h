@@ -187,6 +187,20 @@ int gdrn_roi_targets(const float* xyz, const float* mask_visib, const float* mas
 int gdrn_pose_errors(const float* R_est, const float* t_est, const float* R_gt, const float* t_gt, const float* points, int B,
                      int n_pts, int want_adi, float* out, void* stream);
 
+/* ---- test-time RANSAC-PnP of the evaluator on the device (core/gdrn_modeling/gdrn_evaluator.py:316-436 `process_pnp_ransac`:
+ * `get_img_model_points_with_coords2d` :89-126 + lib/pysixd/misc.py:145-194 `pnp_v2` = cv2.solvePnPRansac(EPNP, reprojErr 3, 100
+ * iterations) per instance on the host).  mask [B][H*W] (mask_mode 0: used as is, 1: per-ROI min-max normalised like
+ * engine_utils.py:113-118 for the L1 mask head, 2: sigmoid), xyz [B][3][H*W] in [0,1], coord2d [B][2][H*W] in [0,1],
+ * extents [B][3], im_wh [B][2] = (im_W, im_H), K [B][3][3].  out_pose [B][3][4] = [R | t]; out_info [B][4] = (selected points,
+ * inliers, RANSAC iterations run, ok); out_inliers (optional) [B][H*W] flags indexed like cv2's inlier list (position in the
+ * row-major list of selected points).  Follows OpenCV's algorithm (RNG-driven 5-point subsets, EPnP minimal + final solver,
+ * adaptive iteration count): same inlier sets / poses as cv2 up to round-off. */
+long gdrn_pnp_ransac_workspace_bytes(int B, int HW, int iters);
+int gdrn_pnp_ransac(const float* mask, const float* xyz, const float* coord2d, const float* extents, const float* im_wh,
+                    const float* K, int B, int H, int W, int mask_mode, float mask_thr, double reproj_err, int iters,
+                    double confidence, void* workspace, long workspace_bytes, float* out_pose, int* out_info,
+                    unsigned char* out_inliers, void* stream);
+
 /* ---- fused Ranger step (gradient centralisation + RAdam + Lookahead), lib/torch_utils/solver/ranger.py:100-200, for all
  * tensors of a param group in ONE launch.  jobs: device array of 64-byte records {float* p; const float* g; float* m; float* v;
  * float* slow; long numel; int row_len; int pad[3]} (row_len > 0: centralise rows of that length);
