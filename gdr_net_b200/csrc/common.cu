@@ -3,6 +3,8 @@
 
 #include <atomic>
 
+#include <stdlib.h>
+
 #include "gdrn_internal.h"
 #include "ptx.cuh"
 
@@ -35,6 +37,17 @@ int num_sms() {
 }
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// Programmatic dependent launch for the GEMM kernels (GDRN_PDL=0 disables; A/B).  See ptx.cuh pdl_wait().
+static int g_pdl = -1;
+bool pdl_enabled() {
+    if (g_pdl < 0) {
+        const char* e = getenv("GDRN_PDL");
+        g_pdl = e ? atoi(e) : 1;
+    }
+    return g_pdl == 1;
+}
+void set_pdl(int on) { g_pdl = on ? 1 : 0; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -82,6 +95,10 @@ int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims
 
 extern "C" const char* gdrn_last_error() { return gdrn::g_err; }
 extern "C" long gdrn_launch_count() { return gdrn::g_launches.load(); }
+extern "C" int gdrn_set_pdl(int on) {
+    gdrn::set_pdl(on);
+    return 0;
+}
 extern "C" int gdrn_abi_version() { return 1; }
 
 // 0 = bf16 planes, 1 = fp16 planes (compile-time GDRN_STORE_F16); the host side mirrors dtype and lo-plane scale

@@ -18,6 +18,8 @@ int set_error(int code, const char* fmt, ...);
 int cuda_error(cudaError_t e, const char* file, int line);
 int num_sms();
 void count_launch();
+bool pdl_enabled();  // programmatic dependent launch for the GEMM kernels (GDRN_PDL / gdrn_set_pdl)
+void set_pdl(int on);
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency).
 // bf16 elements, 128-byte swizzle, zero fill for out-of-bounds box elements.

@@ -126,6 +126,8 @@ __global__ void __launch_bounds__(128 + 32 * kEpiWarps, 1) gemm_fwd_kernel(const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();  // the next kernel of the stream may start its prologue under our tail
+    pdl_wait();               // nothing above touched global memory; from here on we read what the predecessor wrote
     // persistent CTAs stride over the tile list (phase-major for the stride-2 dgrad)
     const int my_cluster = blockIdx.x, num_clusters = gridDim.x;
     const int num_groups = (p.nphase ? p.nphase : 1) * num_tiles;
@@ -368,13 +370,19 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
     cfg.blockDim = dim3(128 + 32 * kEpiWarps);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    int na = 1;
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     GDRN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
     count_launch();
     return 0;

@@ -109,6 +109,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) gemm_wgrad_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();  // the next kernel of the stream may start its prologue under our tail
+    pdl_wait();               // nothing above touched global memory; from here on we read what the predecessor wrote
 
     // Producer and MMA issuer run their loops with the WHOLE warp (warp-uniform control flow, operands in uniform registers);
     // one elected lane issues the TMA / tcgen05 instructions.  Per k-block nothing but the barrier wait, the expect_tx and the
@@ -359,6 +361,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) gemm_wgrad2_kernel(const __grid
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();  // the next kernel of the stream may start its prologue under our tail
+    pdl_wait();               // nothing above touched global memory; from here on we read what the predecessor wrote
 
     if (warp == 0) {
         if (nkb > 0) {
@@ -505,13 +509,19 @@ static int launch_wgrad2(const WgradParams& p, cudaStream_t stream) {
     cfg.blockDim = dim3(kWgThreads);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    int na = 1;
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     GDRN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
     count_launch();
     return 0;
@@ -537,9 +547,22 @@ static int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
         GDRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    const int grid = p.num_m_tiles * p.num_n_tiles * p.items * p.ksplit;
-    kern<<<grid, kWgThreads, Cfg::SMEM_BYTES, stream>>>(p);
-    GDRN_CUDA_OK(cudaGetLastError());
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(p.num_m_tiles * p.num_n_tiles * p.items * p.ksplit);
+    cfg.blockDim = dim3(kWgThreads);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    int na = 0;
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    GDRN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
     count_launch();
     return 0;
 }

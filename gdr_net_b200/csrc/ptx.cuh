@@ -122,6 +122,15 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is
+// still running; `pdl_wait` blocks until that predecessor has COMPLETED and its memory is visible.  Everything before it
+// (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's tail.  `pdl_launch_dependents` lets the NEXT
+// kernel of the stream begin that early start; it is always safe because the next kernel protects itself with its own wait.
+// Both are no-ops when the launch carries no programmatic dependency.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- cta_group::2 (CTA pairs)
 // cp.async.bulk.tensor issued by EITHER CTA of the pair; the transaction bytes are counted on the LEADER's barrier
 // (`bar` = shared::cluster address of CTA 0's mbarrier)

@@ -32,6 +32,7 @@ int gdrn_storage_format(void); /* 0: bf16 (hi, lo) planes; 1: fp16 planes, lo = 
 float gdrn_lo_scale(void);
 int gdrn_set_2cta(int on); /* A/B: cta_group::2 pair tiles (256x256 1-pass / 256x128 3-pass) for eligible conv layers; default on */
 long gdrn_2cta_launch_count(void); /* launches of the 2-CTA kernel since load */
+int gdrn_set_pdl(int on); /* A/B: programmatic dependent launch of the GEMM kernels (prologue under the predecessor's tail); default on, GDRN_PDL=0 disables */
 int gdrn_set_wgrad_2cta(int on); /* A/B: cta_group::2 pair tiles (256 co x 128/256 ci) for single-plane weight gradients with Cout % 256 == 0; default OFF (bit-equal to the 1-CTA kernel, no in-situ gain) */
 long gdrn_wgrad_2cta_launch_count(void);
 int gdrn_last_gemm_variant(void); /* BLOCK_N*10 + nsplit (+10000: 2-CTA kernel) of this thread's last conv/gemm forward launch */

@@ -206,6 +206,38 @@ def test_deconv_fwd_and_dgrad(planes):
     assert _rel(dx32, gx.permute(0, 2, 3, 1)) < TOL[planes]
 
 
+def test_pdl_chain_bit_equal():
+    """Programmatic dependent launch: every GEMM kernel may start under the tail of its predecessor and waits (griddepcontrol.wait)
+    before its first global read.  A chain conv -> conv -> conv (each consuming the previous output, different shapes so the
+    tails differ) repeated many times must give bit-identical results with the attribute on and off."""
+    ops = _ops()
+    from gdr_net_b200.capi import C
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(16, 64, 32, 32, device="cuda", generator=g)
+    ws = [torch.randn(co, ci, 3, 3, device="cuda", generator=g) / math.sqrt(9 * ci) for ci, co in ((64, 128), (128, 256), (256, 64))]
+    X = _nhwc(x, 1)
+    Wp = [ops.pack_conv_fwd(w, 1) for w in ws]
+
+    def chain():
+        t = X
+        for w, wp in zip(ws, Wp):
+            t = ops.conv_fwd(t, wp, w.shape[0], 3, 3, 1, 1)
+        return t.float()
+
+    try:
+        C.gdrn_set_pdl(0)
+        ref = chain()
+        torch.cuda.synchronize()
+        C.gdrn_set_pdl(1)
+        for _ in range(30):
+            out = chain()
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
+    finally:
+        C.gdrn_set_pdl(1)
+
+
 WGRAD_CASES = [(2, 64, 64, 64, 64, 3, 1, 1), (2, 32, 32, 128, 128, 3, 1, 1), (4, 16, 16, 256, 256, 3, 1, 1),
                (8, 8, 8, 512, 512, 3, 1, 1), (2, 64, 64, 64, 128, 3, 2, 1), (2, 64, 64, 64, 128, 1, 2, 0),
                (2, 64, 64, 256, 128, 1, 1, 0)]
