@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(256, 4) bn_act_kernel(const bf16* __restrict__
                                                         bf16* __restrict__ y_hi, bf16* __restrict__ y_lo,
                                                         const float* __restrict__ scale, const float* __restrict__ shift,
                                                         long rows, int C, int relu) {
-    pdl_launch_dependents();  // a GEMM that follows in the stream may set up (barriers, TMEM) while this kernel drains
+    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
+    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
     __shared__ float s_sc[512], s_sh[512];
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         s_sc[c] = scale[c];
@@ -220,7 +221,8 @@ __global__ void __launch_bounds__(256, 4) bn_fwd_kernel(const bf16* __restrict__
                                                         float* __restrict__ mean_out, float* __restrict__ invstd_out, long rows,
                                                         int C, float eps, float momentum, int train, int relu,
                                                         uint8_t* __restrict__ mask_out) {
-    pdl_launch_dependents();  // a GEMM that follows in the stream may set up (barriers, TMEM) while this kernel drains
+    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
+    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
     __shared__ float s_sc[512], s_sh[512];
     const float count = (float)rows;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -294,7 +296,8 @@ __device__ __forceinline__ Pix decode_pix(long idx, int cg, int W, int H) {
 // ------------------------------------------------------------------------------------------------
 __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo, bf16* __restrict__ y_hi,
                                    bf16* __restrict__ y_lo, uint8_t* __restrict__ arg_out, int B, int H, int W, int C) {
-    pdl_launch_dependents();  // a GEMM that follows in the stream may set up (barriers, TMEM) while this kernel drains
+    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
+    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
     const int cg = C / 8, Ho = H / 2, Wo = W / 2;
     const long total = (long)B * Ho * Wo * cg;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -339,7 +342,8 @@ __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x_hi, const bf16* __
 __global__ void maxpool_bwd_kernel(const uint8_t* __restrict__ arg_in, const bf16* __restrict__ g_hi,
                                    const bf16* __restrict__ g_lo, bf16* __restrict__ dx_hi, bf16* __restrict__ dx_lo, int B, int H,
                                    int W, int C) {
-    pdl_launch_dependents();  // a GEMM that follows in the stream may set up (barriers, TMEM) while this kernel drains
+    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
+    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
     const int cg = C / 8, Ho = H / 2, Wo = W / 2;
     const long total = (long)B * H * W * cg;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -385,7 +389,8 @@ __global__ void maxpool_bwd_kernel(const uint8_t* __restrict__ arg_in, const bf1
 // ------------------------------------------------------------------------------------------------
 __global__ void upsample2x_fwd_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo, bf16* __restrict__ y_hi,
                                       bf16* __restrict__ y_lo, int B, int H, int W, int C) {
-    pdl_launch_dependents();  // a GEMM that follows in the stream may set up (barriers, TMEM) while this kernel drains
+    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
+    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
     const int cg = C / 8, Ho = 2 * H, Wo = 2 * W;
     const float sh = (float)(H - 1) / (float)(Ho - 1), sw = (float)(W - 1) / (float)(Wo - 1);
     const long total = (long)B * Ho * Wo * cg;
@@ -411,7 +416,8 @@ __global__ void upsample2x_fwd_kernel(const bf16* __restrict__ x_hi, const bf16*
 // gather form of the transpose: dx[iy,ix] = sum_{oy,ox} w(oy->iy) * w(ox->ix) * g[oy,ox]
 __global__ void upsample2x_bwd_kernel(const bf16* __restrict__ g_hi, const bf16* __restrict__ g_lo, bf16* __restrict__ dx_hi,
                                       bf16* __restrict__ dx_lo, int B, int H, int W, int C) {
-    pdl_launch_dependents();  // a GEMM that follows in the stream may set up (barriers, TMEM) while this kernel drains
+    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
+    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
     const int cg = C / 8, Ho = 2 * H, Wo = 2 * W;
     const float sh = (float)(H - 1) / (float)(Ho - 1), sw = (float)(W - 1) / (float)(Wo - 1);
     const long total = (long)B * H * W * cg;
@@ -482,7 +488,8 @@ __global__ void upsample2x_bwd_kernel(const bf16* __restrict__ g_hi, const bf16*
 // ------------------------------------------------------------------------------------------------
 __global__ void zero_insert_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo, bf16* __restrict__ y_hi,
                                    bf16* __restrict__ y_lo, int B, int H, int W, int C, int mode) {
-    pdl_launch_dependents();  // a GEMM that follows in the stream may set up (barriers, TMEM) while this kernel drains
+    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
+    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
     const int cg = C / 8;
     const int Hy = mode == 0 ? 2 * H : H, Wy = mode == 0 ? 2 * W : W;
     const long total = (long)B * Hy * Wy * cg;
@@ -564,6 +571,8 @@ __global__ void __launch_bounds__(kBnBwdThreads, 2) bn_bwd_reduce_kernel(
     const bf16* __restrict__ u_lo, const float* __restrict__ mean, const float* __restrict__ invstd,
     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ sums, long rows, int C,
     const uint8_t* __restrict__ mask_in, float* __restrict__ partial_out) {
+    pdl_launch_dependents();
+    pdl_wait();
     // block = (C/8) channel groups x rpb row lanes
     const int cg = C / 8;
     const int rpb = kBnBwdThreads / cg;  // cg in {8,16,32,64}: always divides 256
@@ -703,7 +712,8 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ sums, bf16* __restrict__ du_hi,
     bf16* __restrict__ du_lo, bf16* __restrict__ gout_hi, bf16* __restrict__ gout_lo, float* __restrict__ dgamma,
     float* __restrict__ dbeta, long rows, int C, int train, const uint8_t* __restrict__ mask_in) {
-    pdl_launch_dependents();  // a GEMM that follows in the stream may set up (barriers, TMEM) while this kernel drains
+    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
+    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
     __shared__ __align__(16) float s_k1[512], s_k2[512], s_k3[512], s_sc[512], s_sh[512];
     const int cg = C / 8;
     const long total = rows * cg;
@@ -804,7 +814,8 @@ __global__ void __launch_bounds__(256) gn_relu_fwd_kernel(const bf16* __restrict
                                                           bf16* __restrict__ y_hi, bf16* __restrict__ y_lo,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float* __restrict__ stats, int HW, int C, int G, float eps, int ncl) {
-    pdl_launch_dependents();  // a GEMM that follows in the stream may set up (barriers, TMEM) while this kernel drains
+    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
+    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
     const int b = blockIdx.x / ncl;
     const unsigned crank = ncl > 1 ? gn_cluster_rank() : 0u;
     const int cg = C / 8;             // 16
@@ -895,7 +906,8 @@ __global__ void __launch_bounds__(256) gn_relu_bwd_kernel(const bf16* __restrict
                                                           const float* __restrict__ stats, bf16* __restrict__ du_hi,
                                                           bf16* __restrict__ du_lo, float* __restrict__ dgamma,
                                                           float* __restrict__ dbeta, int HW, int C, int G, int ncl) {
-    pdl_launch_dependents();  // a GEMM that follows in the stream may set up (barriers, TMEM) while this kernel drains
+    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
+    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
     const int b = blockIdx.x / ncl;
     const unsigned crank = ncl > 1 ? gn_cluster_rank() : 0u;
     const int cg = C / 8;
@@ -998,7 +1010,8 @@ __global__ void __launch_bounds__(256) gn_relu_bwd_kernel(const bf16* __restrict
 // out (bf16 hi/lo) = a + b   (gradient merge of two branches)
 __global__ void add2_kernel(const bf16* __restrict__ a_hi, const bf16* __restrict__ a_lo, const bf16* __restrict__ b_hi,
                             const bf16* __restrict__ b_lo, bf16* __restrict__ o_hi, bf16* __restrict__ o_lo, long n8) {
-    pdl_launch_dependents();  // a GEMM that follows in the stream may set up (barriers, TMEM) while this kernel drains
+    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
+    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n8; idx += (long)gridDim.x * blockDim.x) {
         float a[8], b[8];
         load8(a_hi, a_lo, idx, a);
@@ -1030,6 +1043,8 @@ __global__ void planes_to_f32_kernel(const bf16* __restrict__ x_hi, const bf16* 
 // out[c] (+)= sum_rows x[r][c]   (bias gradients).  Block = 256 threads = (ld/8) column groups x row lanes.
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo,
                                                      float* __restrict__ out, long rows, int ld) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int cg = ld / 8;
     const int rpb = 256 / cg;
     const int g = threadIdx.x % cg, rl = threadIdx.x / cg;
@@ -1058,7 +1073,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x_
 // LeakyReLU(0.1) backward through the saved OUTPUT y (sign(y) == sign(pre-activation)): g *= y > 0 ? 1 : 0.1
 __global__ void leaky_bwd_kernel(const bf16* __restrict__ g_hi, const bf16* __restrict__ g_lo, const bf16* __restrict__ y_hi,
                                  bf16* __restrict__ o_hi, bf16* __restrict__ o_lo, long n8) {
-    pdl_launch_dependents();  // a GEMM that follows in the stream may set up (barriers, TMEM) while this kernel drains
+    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
+    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n8; idx += (long)gridDim.x * blockDim.x) {
         float g[8], y[8];
         load8(g_hi, g_lo, idx, g);
@@ -1104,7 +1120,7 @@ extern "C" int gdrn_bn_act(const void* x_hi, const void* x_lo, const void* r_hi,
     if (C > 512 || 256 % (C / 8)) return set_error(GDRN_ERR_ARG, "bn_act: unsupported C=%d", C);
     const int grid = ew_grid_amortised(rows * (C / 8), 256, 4);
 #define GDRN_BN_ACT(LO, RES) \
-    bn_act_kernel<LO, RES><<<grid, 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), CBF(r_hi), CBF(r_lo), BF(y_hi), BF(y_lo), scale, shift, rows, C, relu)
+    GDRN_LAUNCH_PDL((bn_act_kernel<LO, RES>), grid, 256, 0, stream, CBF(x_hi), CBF(x_lo), CBF(r_hi), CBF(r_lo), BF(y_hi), BF(y_lo), scale, shift, rows, C, relu)
     if (x_lo != nullptr) {
         if (r_hi != nullptr) GDRN_BN_ACT(true, true); else GDRN_BN_ACT(true, false);
     } else {
@@ -1117,28 +1133,28 @@ extern "C" int gdrn_bn_act(const void* x_hi, const void* x_lo, const void* r_hi,
 extern "C" int gdrn_maxpool_fwd(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, void* arg_out, int B, int H,
                                 int W, int C, void* stream_) {
     STREAM;
-    maxpool_fwd_kernel<<<ew_grid((long)B * (H / 2) * (W / 2) * (C / 8), 256), 256, 0, stream>>>(
+    GDRN_LAUNCH_PDL(maxpool_fwd_kernel, ew_grid((long)B * (H / 2) * (W / 2) * (C / 8), 256), 256, 0, stream, 
         CBF(x_hi), CBF(x_lo), BF(y_hi), BF(y_lo), reinterpret_cast<uint8_t*>(arg_out), B, H, W, C);
     LAUNCH_DONE();
 }
 extern "C" int gdrn_maxpool_bwd(const void* arg_in, const void* g_hi, const void* g_lo, void* dx_hi, void* dx_lo, int B,
                                 int H, int W, int C, void* stream_) {
     STREAM;
-    maxpool_bwd_kernel<<<ew_grid((long)B * H * W * (C / 8), 256), 256, 0, stream>>>(
+    GDRN_LAUNCH_PDL(maxpool_bwd_kernel, ew_grid((long)B * H * W * (C / 8), 256), 256, 0, stream, 
         reinterpret_cast<const uint8_t*>(arg_in), CBF(g_hi), CBF(g_lo), BF(dx_hi), BF(dx_lo), B, H, W, C);
     LAUNCH_DONE();
 }
 extern "C" int gdrn_upsample2x_fwd(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int B, int H, int W, int C,
                                    void* stream_) {
     STREAM;
-    upsample2x_fwd_kernel<<<ew_grid((long)B * 4 * H * W * (C / 8), 256), 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), BF(y_hi),
+    GDRN_LAUNCH_PDL(upsample2x_fwd_kernel, ew_grid((long)B * 4 * H * W * (C / 8), 256), 256, 0, stream, CBF(x_hi), CBF(x_lo), BF(y_hi),
                                                                                            BF(y_lo), B, H, W, C);
     LAUNCH_DONE();
 }
 extern "C" int gdrn_upsample2x_bwd(const void* g_hi, const void* g_lo, void* dx_hi, void* dx_lo, int B, int H, int W, int C,
                                    void* stream_) {
     STREAM;
-    upsample2x_bwd_kernel<<<ew_grid((long)B * H * W * (C / 8), 256), 256, 0, stream>>>(CBF(g_hi), CBF(g_lo), BF(dx_hi),
+    GDRN_LAUNCH_PDL(upsample2x_bwd_kernel, ew_grid((long)B * H * W * (C / 8), 256), 256, 0, stream, CBF(g_hi), CBF(g_lo), BF(dx_hi),
                                                                                        BF(dx_lo), B, H, W, C);
     LAUNCH_DONE();
 }
@@ -1146,7 +1162,7 @@ extern "C" int gdrn_zero_insert(const void* x_hi, const void* x_lo, void* y_hi, 
                                 int mode, void* stream_) {
     STREAM;
     const long total = (long)B * H * W * (C / 8) * (mode == 0 ? 4 : 1);
-    zero_insert_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), BF(y_hi), BF(y_lo), B, H, W, C, mode);
+    GDRN_LAUNCH_PDL(zero_insert_kernel, ew_grid(total, 256), 256, 0, stream, CBF(x_hi), CBF(x_lo), BF(y_hi), BF(y_lo), B, H, W, C, mode);
     LAUNCH_DONE();
 }
 
@@ -1170,7 +1186,7 @@ extern "C" int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
 #define GDRN_BN_RED(LO, MU)                                                                                                   \
-    bn_bwd_reduce_kernel<LO, MU><<<(int)blocks, kBnBwdThreads, 0, stream>>>(CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo),       \
+    GDRN_LAUNCH_PDL((bn_bwd_reduce_kernel<LO, MU>), (int)blocks, kBnBwdThreads, 0, stream, CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo),       \
                                                                             CBF(y_hi), CBF(u_hi), CBF(u_lo), mean, invstd, gamma, \
                                                                             beta, sums, rows, C, mask_in, det ? det_ws : nullptr)
         if (u_lo != nullptr) {
@@ -1189,7 +1205,7 @@ extern "C" int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_
     }
     const int agrid = ew_grid_amortised(rows * (C / 8), 256, 4);
 #define GDRN_BN_APP(LO, MU)                                                                                                      \
-    bn_bwd_apply_kernel<LO, MU><<<agrid, 256, 0, stream>>>(CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo), CBF(y_hi), CBF(u_hi),    \
+    GDRN_LAUNCH_PDL((bn_bwd_apply_kernel<LO, MU>), agrid, 256, 0, stream, CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo), CBF(y_hi), CBF(u_hi),    \
                                                            CBF(u_lo), mean, invstd, gamma, beta, sums, BF(du_hi), BF(du_lo),       \
                                                            BF(gout_hi), BF(gout_lo), dgamma, dbeta, rows, C, train, mask_in)
     if (u_lo != nullptr) {
@@ -1267,7 +1283,7 @@ extern "C" int gdrn_gn_relu_bwd(const void* g_hi, const void* g_lo, const void* 
 extern "C" int gdrn_add2(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* o_hi, void* o_lo,
                          long n, void* stream_) {
     STREAM;
-    add2_kernel<<<ew_grid(n / 8, 256), 256, 0, stream>>>(CBF(a_hi), CBF(a_lo), CBF(b_hi), CBF(b_lo), BF(o_hi), BF(o_lo), n / 8);
+    GDRN_LAUNCH_PDL(add2_kernel, ew_grid(n / 8, 256), 256, 0, stream, CBF(a_hi), CBF(a_lo), CBF(b_hi), CBF(b_lo), BF(o_hi), BF(o_lo), n / 8);
     LAUNCH_DONE();
 }
 extern "C" int gdrn_f32_to_planes(const float* x, void* y_hi, void* y_lo, long n, void* stream_) {
@@ -1290,13 +1306,13 @@ extern "C" int gdrn_colsum(const void* x_hi, const void* x_lo, float* out, long 
     const long cap = (long)num_sms() * 4;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    colsum_kernel<<<(int)blocks, 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), out, rows, ld);
+    GDRN_LAUNCH_PDL(colsum_kernel, (int)blocks, 256, 0, stream, CBF(x_hi), CBF(x_lo), out, rows, ld);
     LAUNCH_DONE();
 }
 extern "C" int gdrn_leaky_bwd(const void* g_hi, const void* g_lo, const void* y_hi, void* o_hi, void* o_lo, long n,
                               void* stream_) {
     STREAM;
-    leaky_bwd_kernel<<<ew_grid(n / 8, 256), 256, 0, stream>>>(CBF(g_hi), CBF(g_lo), CBF(y_hi), BF(o_hi), BF(o_lo), n / 8);
+    GDRN_LAUNCH_PDL(leaky_bwd_kernel, ew_grid(n / 8, 256), 256, 0, stream, CBF(g_hi), CBF(g_lo), CBF(y_hi), BF(o_hi), BF(o_lo), n / 8);
     LAUNCH_DONE();
 }
 
@@ -1309,7 +1325,7 @@ extern "C" int gdrn_bn_fwd(const void* x_hi, const void* x_lo, const void* r_hi,
     if (train && stats == nullptr) return set_error(GDRN_ERR_ARG, "bn_fwd: batch statistics missing");
     const int grid = ew_grid_amortised(rows * (C / 8), 256, 4);
 #define GDRN_BN_FWD(LO, RES)                                                                                                  \
-    bn_fwd_kernel<LO, RES><<<grid, 256, 0, stream>>>(CBF(x_hi), CBF(x_lo), CBF(r_hi), CBF(r_lo), BF(y_hi), BF(y_lo), stats, gamma, beta, \
+    GDRN_LAUNCH_PDL((bn_fwd_kernel<LO, RES>), grid, 256, 0, stream, CBF(x_hi), CBF(x_lo), CBF(r_hi), CBF(r_lo), BF(y_hi), BF(y_lo), stats, gamma, beta, \
                                                      running_mean, running_var, mean_out, invstd_out, rows, C, eps, momentum, train, relu,  \
                                                      reinterpret_cast<uint8_t*>(relu_mask_out))
     if (x_lo != nullptr) {

@@ -28,6 +28,34 @@ int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims
 
 }  // namespace gdrn
 
+#ifdef __CUDACC__
+namespace gdrn {
+// <<<>>> with the programmatic-dependent-launch attribute (when enabled).  ONLY for kernels whose first statements are
+// pdl_launch_dependents(); pdl_wait();  (ptx.cuh) -- a kernel launched this way may start before its predecessor has finished.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    int na = 0;
+    if (pdl_enabled()) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        na = 1;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+}  // namespace gdrn
+#define GDRN_LAUNCH_PDL(kernel, grid, block, smem, stream, ...) \
+    (void)gdrn::launch_pdl(kernel, dim3(grid), dim3(block), smem, stream, __VA_ARGS__)
+#endif
+
 #define GDRN_CUDA_OK(expr)                                                      \
     do {                                                                        \
         cudaError_t _e = (expr);                                                \

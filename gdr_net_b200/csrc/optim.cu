@@ -10,6 +10,7 @@
 // host (gdr_net_b200/solver.py).  Tensors with dim > 1 are centralised per output row (mean over dims 1..): rows of up to
 // 2048 elements are owned by one warp (8 rows in flight per block), longer rows by the whole block.
 #include "gdrn_internal.h"
+#include "ptx.cuh"
 
 namespace gdrn {
 
@@ -98,6 +99,8 @@ __global__ void __launch_bounds__(256) ranger_step_kernel(const RangerJob* __res
 // x[i] *= s (removal of the static fp16 loss scale from a slice of the flat fp32 gradient buffer); `head` unaligned leading
 // elements and the tail are handled by block 0, the 16-byte aligned body with float4 accesses
 __global__ void scale_f32_kernel(float* __restrict__ x, long head, long n4, long n, float s) {
+    pdl_launch_dependents();
+    pdl_wait();
     float4* body = reinterpret_cast<float4*>(x + head);
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         float4 q = body[i];
@@ -146,7 +149,7 @@ extern "C" int gdrn_scale_f32(float* x, long n, float s, void* stream_) {
     const long cap = (long)num_sms() * 8;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
-    scale_f32_kernel<<<(int)g, 256, 0, stream>>>(x, head, n4, n, s);
+    GDRN_LAUNCH_PDL(scale_f32_kernel, (int)g, 256, 0, stream, x, head, n4, n, s);
     GDRN_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;

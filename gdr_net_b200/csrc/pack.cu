@@ -59,7 +59,8 @@ constexpr int kPackTC = 9;   // taps per tile
 constexpr int kPackLD = kPackDC + 1;
 
 __global__ void __launch_bounds__(256) pack_weight_batched_kernel(const PackJob* __restrict__ jobs, int njobs, long total_blocks) {
-    pdl_launch_dependents();  // a GEMM that follows in the stream may set up (barriers, TMEM) while this kernel drains
+    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
+    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
     // One block = one tile of 16 dst rows x 64 dst channels x <= 9 taps, staged through shared memory:
     //   load : threads walk the tile in SOURCE order (taps innermost, then whichever of the row / channel strides is
     //          smaller), so a warp reads runs of >= 36..1152 contiguous bytes of the fp32 parameter;
@@ -161,7 +162,8 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
                                                            int KH, int KW, int IC, int n_ic, int KP, int ipad, int krow_,
                                                            int ksplit, long ks_stride, long so, long si, long sr, long ss,
                                                            int flip, int accumulate) {
-    pdl_launch_dependents();  // a GEMM that follows in the stream may set up (barriers, TMEM) while this kernel drains
+    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
+    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
     extern __shared__ __align__(16) float sm[];
     const int taps = KH * KW;
     const int nelem = taps * IC;
@@ -257,7 +259,8 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
 template <int W>
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a_hi,
                                                           __nv_bfloat16* __restrict__ a_lo, int B, int H) {
-    pdl_launch_dependents();  // a GEMM that follows in the stream may set up (barriers, TMEM) while this kernel drains
+    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
+    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
     constexpr int WP = W + 6;  // 3-pixel zero halo left and right
     __shared__ float tile[3][7][WP];
     const int Ho = H / 2, Wo = W / 2;
@@ -361,10 +364,10 @@ extern "C" int gdrn_unpack_wgrad(const float* ws, float* grad, int O, int I, int
     const bool vec_ok = (IC % 4 == 0) && (I % 4 == 0) && (ipad % 4 == 0) && (krow % 4 == 0) && (ks_stride % 4 == 0) &&
                         ((reinterpret_cast<uintptr_t>(ws) & 15) == 0);
     if (variant == 1 || !vec_ok)
-        unpack_wgrad_kernel<1><<<O * n_ic, 256, smem, stream>>>(ws, grad, O, I, KH, KW, IC, n_ic, KP, ipad, krow, ksplit, ks_stride,
+        GDRN_LAUNCH_PDL(unpack_wgrad_kernel<1>, O * n_ic, 256, smem, stream, ws, grad, O, I, KH, KW, IC, n_ic, KP, ipad, krow, ksplit, ks_stride,
                                                                so, si, sr, ss, flip, accumulate);
     else
-        unpack_wgrad_kernel<0><<<O * n_ic, 256, smem, stream>>>(ws, grad, O, I, KH, KW, IC, n_ic, KP, ipad, krow, ksplit, ks_stride,
+        GDRN_LAUNCH_PDL(unpack_wgrad_kernel<0>, O * n_ic, 256, smem, stream, ws, grad, O, I, KH, KW, IC, n_ic, KP, ipad, krow, ksplit, ks_stride,
                                                                so, si, sr, ss, flip, accumulate);
     GDRN_CUDA_OK(cudaGetLastError());
     count_launch();
@@ -374,7 +377,7 @@ extern "C" int gdrn_unpack_wgrad(const float* ws, float* grad, int O, int I, int
 extern "C" int gdrn_stem_im2col(const float* x, void* a_hi, void* a_lo, int B, int H, int W, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (H % 2 || W != 256) return set_error(GDRN_ERR_ARG, "stem_im2col: expects 256-wide crops (INPUT_RES=256), even height");
-    stem_im2col_kernel<256><<<B * (H / 2), 256, 0, stream>>>(x, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo, B, H);
+    GDRN_LAUNCH_PDL(stem_im2col_kernel<256>, B * (H / 2), 256, 0, stream, x, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo, B, H);
     GDRN_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;
@@ -387,7 +390,7 @@ extern "C" int gdrn_pack_weight_batched(const void* jobs_dev, int njobs, long to
     long grid = total_blocks;
     const long cap = (long)num_sms() * 16;
     if (grid > cap) grid = cap;
-    pack_weight_batched_kernel<<<(int)grid, 256, 0, stream>>>(reinterpret_cast<const PackJob*>(jobs_dev), njobs, total_blocks);
+    GDRN_LAUNCH_PDL(pack_weight_batched_kernel, (int)grid, 256, 0, stream, reinterpret_cast<const PackJob*>(jobs_dev), njobs, total_blocks);
     GDRN_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;
