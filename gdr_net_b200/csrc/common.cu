@@ -39,15 +39,18 @@ int num_sms() {
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // Programmatic dependent launch for the GEMM kernels (GDRN_PDL=0 disables; A/B).  See ptx.cuh pdl_wait().
+// mode 0: off; 1: GEMM kernels only; 2: GEMM + elementwise / pack kernels
 static int g_pdl = -1;
-bool pdl_enabled() {
+static int pdl_mode() {
     if (g_pdl < 0) {
         const char* e = getenv("GDRN_PDL");
         g_pdl = e ? atoi(e) : 1;
     }
-    return g_pdl == 1;
+    return g_pdl;
 }
-void set_pdl(int on) { g_pdl = on ? 1 : 0; }
+bool pdl_enabled() { return pdl_mode() >= 1; }
+bool pdl_ew_enabled() { return pdl_mode() >= 2; }
+void set_pdl(int mode) { g_pdl = mode < 0 ? 0 : mode; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -199,8 +199,7 @@ __global__ void __launch_bounds__(256, 4) bn_act_kernel(const bf16* __restrict__
                                                         bf16* __restrict__ y_hi, bf16* __restrict__ y_lo,
                                                         const float* __restrict__ scale, const float* __restrict__ shift,
                                                         long rows, int C, int relu) {
-    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
-    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
+    pdl_ew_entry();
     __shared__ float s_sc[512], s_sh[512];
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         s_sc[c] = scale[c];
@@ -221,8 +220,7 @@ __global__ void __launch_bounds__(256, 4) bn_fwd_kernel(const bf16* __restrict__
                                                         float* __restrict__ mean_out, float* __restrict__ invstd_out, long rows,
                                                         int C, float eps, float momentum, int train, int relu,
                                                         uint8_t* __restrict__ mask_out) {
-    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
-    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
+    pdl_ew_entry();
     __shared__ float s_sc[512], s_sh[512];
     const float count = (float)rows;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -296,8 +294,7 @@ __device__ __forceinline__ Pix decode_pix(long idx, int cg, int W, int H) {
 // ------------------------------------------------------------------------------------------------
 __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo, bf16* __restrict__ y_hi,
                                    bf16* __restrict__ y_lo, uint8_t* __restrict__ arg_out, int B, int H, int W, int C) {
-    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
-    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
+    pdl_ew_entry();
     const int cg = C / 8, Ho = H / 2, Wo = W / 2;
     const long total = (long)B * Ho * Wo * cg;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -342,8 +339,7 @@ __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x_hi, const bf16* __
 __global__ void maxpool_bwd_kernel(const uint8_t* __restrict__ arg_in, const bf16* __restrict__ g_hi,
                                    const bf16* __restrict__ g_lo, bf16* __restrict__ dx_hi, bf16* __restrict__ dx_lo, int B, int H,
                                    int W, int C) {
-    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
-    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
+    pdl_ew_entry();
     const int cg = C / 8, Ho = H / 2, Wo = W / 2;
     const long total = (long)B * H * W * cg;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -389,8 +385,7 @@ __global__ void maxpool_bwd_kernel(const uint8_t* __restrict__ arg_in, const bf1
 // ------------------------------------------------------------------------------------------------
 __global__ void upsample2x_fwd_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo, bf16* __restrict__ y_hi,
                                       bf16* __restrict__ y_lo, int B, int H, int W, int C) {
-    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
-    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
+    pdl_ew_entry();
     const int cg = C / 8, Ho = 2 * H, Wo = 2 * W;
     const float sh = (float)(H - 1) / (float)(Ho - 1), sw = (float)(W - 1) / (float)(Wo - 1);
     const long total = (long)B * Ho * Wo * cg;
@@ -416,8 +411,7 @@ __global__ void upsample2x_fwd_kernel(const bf16* __restrict__ x_hi, const bf16*
 // gather form of the transpose: dx[iy,ix] = sum_{oy,ox} w(oy->iy) * w(ox->ix) * g[oy,ox]
 __global__ void upsample2x_bwd_kernel(const bf16* __restrict__ g_hi, const bf16* __restrict__ g_lo, bf16* __restrict__ dx_hi,
                                       bf16* __restrict__ dx_lo, int B, int H, int W, int C) {
-    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
-    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
+    pdl_ew_entry();
     const int cg = C / 8, Ho = 2 * H, Wo = 2 * W;
     const float sh = (float)(H - 1) / (float)(Ho - 1), sw = (float)(W - 1) / (float)(Wo - 1);
     const long total = (long)B * H * W * cg;
@@ -488,8 +482,7 @@ __global__ void upsample2x_bwd_kernel(const bf16* __restrict__ g_hi, const bf16*
 // ------------------------------------------------------------------------------------------------
 __global__ void zero_insert_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo, bf16* __restrict__ y_hi,
                                    bf16* __restrict__ y_lo, int B, int H, int W, int C, int mode) {
-    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
-    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
+    pdl_ew_entry();
     const int cg = C / 8;
     const int Hy = mode == 0 ? 2 * H : H, Wy = mode == 0 ? 2 * W : W;
     const long total = (long)B * Hy * Wy * cg;
@@ -571,8 +564,7 @@ __global__ void __launch_bounds__(kBnBwdThreads, 2) bn_bwd_reduce_kernel(
     const bf16* __restrict__ u_lo, const float* __restrict__ mean, const float* __restrict__ invstd,
     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ sums, long rows, int C,
     const uint8_t* __restrict__ mask_in, float* __restrict__ partial_out) {
-    pdl_launch_dependents();
-    pdl_wait();
+    pdl_ew_entry();
     // block = (C/8) channel groups x rpb row lanes
     const int cg = C / 8;
     const int rpb = kBnBwdThreads / cg;  // cg in {8,16,32,64}: always divides 256
@@ -712,8 +704,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ sums, bf16* __restrict__ du_hi,
     bf16* __restrict__ du_lo, bf16* __restrict__ gout_hi, bf16* __restrict__ gout_lo, float* __restrict__ dgamma,
     float* __restrict__ dbeta, long rows, int C, int train, const uint8_t* __restrict__ mask_in) {
-    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
-    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
+    pdl_ew_entry();
     __shared__ __align__(16) float s_k1[512], s_k2[512], s_k3[512], s_sc[512], s_sh[512];
     const int cg = C / 8;
     const long total = rows * cg;
@@ -814,8 +805,7 @@ __global__ void __launch_bounds__(256) gn_relu_fwd_kernel(const bf16* __restrict
                                                           bf16* __restrict__ y_hi, bf16* __restrict__ y_lo,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float* __restrict__ stats, int HW, int C, int G, float eps, int ncl) {
-    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
-    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
+    pdl_ew_entry();
     const int b = blockIdx.x / ncl;
     const unsigned crank = ncl > 1 ? gn_cluster_rank() : 0u;
     const int cg = C / 8;             // 16
@@ -906,8 +896,7 @@ __global__ void __launch_bounds__(256) gn_relu_bwd_kernel(const bf16* __restrict
                                                           const float* __restrict__ stats, bf16* __restrict__ du_hi,
                                                           bf16* __restrict__ du_lo, float* __restrict__ dgamma,
                                                           float* __restrict__ dbeta, int HW, int C, int G, int ncl) {
-    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
-    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
+    pdl_ew_entry();
     const int b = blockIdx.x / ncl;
     const unsigned crank = ncl > 1 ? gn_cluster_rank() : 0u;
     const int cg = C / 8;
@@ -1010,8 +999,7 @@ __global__ void __launch_bounds__(256) gn_relu_bwd_kernel(const bf16* __restrict
 // out (bf16 hi/lo) = a + b   (gradient merge of two branches)
 __global__ void add2_kernel(const bf16* __restrict__ a_hi, const bf16* __restrict__ a_lo, const bf16* __restrict__ b_hi,
                             const bf16* __restrict__ b_lo, bf16* __restrict__ o_hi, bf16* __restrict__ o_lo, long n8) {
-    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
-    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
+    pdl_ew_entry();
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n8; idx += (long)gridDim.x * blockDim.x) {
         float a[8], b[8];
         load8(a_hi, a_lo, idx, a);
@@ -1043,8 +1031,7 @@ __global__ void planes_to_f32_kernel(const bf16* __restrict__ x_hi, const bf16* 
 // out[c] (+)= sum_rows x[r][c]   (bias gradients).  Block = 256 threads = (ld/8) column groups x row lanes.
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo,
                                                      float* __restrict__ out, long rows, int ld) {
-    pdl_launch_dependents();
-    pdl_wait();
+    pdl_ew_entry();
     const int cg = ld / 8;
     const int rpb = 256 / cg;
     const int g = threadIdx.x % cg, rl = threadIdx.x / cg;
@@ -1073,8 +1060,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x_
 // LeakyReLU(0.1) backward through the saved OUTPUT y (sign(y) == sign(pre-activation)): g *= y > 0 ? 1 : 0.1
 __global__ void leaky_bwd_kernel(const bf16* __restrict__ g_hi, const bf16* __restrict__ g_lo, const bf16* __restrict__ y_hi,
                                  bf16* __restrict__ o_hi, bf16* __restrict__ o_lo, long n8) {
-    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
-    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
+    pdl_ew_entry();
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n8; idx += (long)gridDim.x * blockDim.x) {
         float g[8], y[8];
         load8(g_hi, g_lo, idx, g);

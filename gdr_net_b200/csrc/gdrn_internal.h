@@ -18,7 +18,8 @@ int set_error(int code, const char* fmt, ...);
 int cuda_error(cudaError_t e, const char* file, int line);
 int num_sms();
 void count_launch();
-bool pdl_enabled();  // programmatic dependent launch for the GEMM kernels (GDRN_PDL / gdrn_set_pdl)
+bool pdl_enabled();     // programmatic dependent launch for the GEMM kernels (GDRN_PDL >= 1 / gdrn_set_pdl)
+bool pdl_ew_enabled();  // ... and for the elementwise / pack kernels (GDRN_PDL >= 2)
 void set_pdl(int on);
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency).
@@ -42,7 +43,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     int na = 0;
-    if (pdl_enabled()) {
+    if (pdl_ew_enabled()) {
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         na = 1;

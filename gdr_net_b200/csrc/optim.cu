@@ -99,8 +99,7 @@ __global__ void __launch_bounds__(256) ranger_step_kernel(const RangerJob* __res
 // x[i] *= s (removal of the static fp16 loss scale from a slice of the flat fp32 gradient buffer); `head` unaligned leading
 // elements and the tail are handled by block 0, the 16-byte aligned body with float4 accesses
 __global__ void scale_f32_kernel(float* __restrict__ x, long head, long n4, long n, float s) {
-    pdl_launch_dependents();
-    pdl_wait();
+    pdl_ew_entry();
     float4* body = reinterpret_cast<float4*>(x + head);
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         float4 q = body[i];

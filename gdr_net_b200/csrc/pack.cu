@@ -59,8 +59,7 @@ constexpr int kPackTC = 9;   // taps per tile
 constexpr int kPackLD = kPackDC + 1;
 
 __global__ void __launch_bounds__(256) pack_weight_batched_kernel(const PackJob* __restrict__ jobs, int njobs, long total_blocks) {
-    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
-    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
+    pdl_ew_entry();
     // One block = one tile of 16 dst rows x 64 dst channels x <= 9 taps, staged through shared memory:
     //   load : threads walk the tile in SOURCE order (taps innermost, then whichever of the row / channel strides is
     //          smaller), so a warp reads runs of >= 36..1152 contiguous bytes of the fp32 parameter;
@@ -162,8 +161,7 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
                                                            int KH, int KW, int IC, int n_ic, int KP, int ipad, int krow_,
                                                            int ksplit, long ks_stride, long so, long si, long sr, long ss,
                                                            int flip, int accumulate) {
-    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
-    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
+    pdl_ew_entry();
     extern __shared__ __align__(16) float sm[];
     const int taps = KH * KW;
     const int nelem = taps * IC;
@@ -259,8 +257,7 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
 template <int W>
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a_hi,
                                                           __nv_bfloat16* __restrict__ a_lo, int B, int H) {
-    pdl_launch_dependents();  // the next kernel of the stream may be scheduled while this one drains ...
-    pdl_wait();               // ... and this one was: wait for the predecessor before the first global access
+    pdl_ew_entry();
     constexpr int WP = W + 6;  // 3-pixel zero halo left and right
     __shared__ float tile[3][7][WP];
     const int Ho = H / 2, Wo = W / 2;

@@ -130,6 +130,13 @@ __device__ __forceinline__ void cluster_sync_all() {
 // Both are no-ops when the launch carries no programmatic dependency.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// First statement of every elementwise / pack kernel that launch_pdl() (gdrn_internal.h) may start early.
+__device__ __forceinline__ void pdl_ew_entry() {
+#if !defined(GDRN_PDL_EW_NO_TRIGGER)
+    pdl_launch_dependents();
+#endif
+    pdl_wait();
+}
 
 // ---------------------------------------------------------------- cta_group::2 (CTA pairs)
 // cp.async.bulk.tensor issued by EITHER CTA of the pair; the transaction bytes are counted on the LEADER's barrier
