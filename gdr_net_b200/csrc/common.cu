@@ -39,7 +39,7 @@ int num_sms() {
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // Programmatic dependent launch for the GEMM kernels (GDRN_PDL=0 disables; A/B).  See ptx.cuh pdl_wait().
-// mode 0: off; 1: GEMM kernels only; 2: GEMM + elementwise / pack kernels
+// mode 0: off; 1: GEMM kernels only; 2: GEMM + elementwise / pack kernels; 3: GEMM + the forward pass's elementwise kernels
 static int g_pdl = -1;
 static int pdl_mode() {
     if (g_pdl < 0) {
@@ -49,7 +49,7 @@ static int pdl_mode() {
     return g_pdl;
 }
 bool pdl_enabled() { return pdl_mode() >= 1; }
-bool pdl_ew_enabled() { return pdl_mode() >= 2; }
+bool pdl_ew_enabled(bool forward_kernel) { return pdl_mode() == 2 || (pdl_mode() == 3 && forward_kernel); }
 void set_pdl(int mode) { g_pdl = mode < 0 ? 0 : mode; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

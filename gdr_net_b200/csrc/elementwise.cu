@@ -1106,7 +1106,7 @@ extern "C" int gdrn_bn_act(const void* x_hi, const void* x_lo, const void* r_hi,
     if (C > 512 || 256 % (C / 8)) return set_error(GDRN_ERR_ARG, "bn_act: unsupported C=%d", C);
     const int grid = ew_grid_amortised(rows * (C / 8), 256, 4);
 #define GDRN_BN_ACT(LO, RES) \
-    GDRN_LAUNCH_PDL((bn_act_kernel<LO, RES>), grid, 256, 0, stream, CBF(x_hi), CBF(x_lo), CBF(r_hi), CBF(r_lo), BF(y_hi), BF(y_lo), scale, shift, rows, C, relu)
+    GDRN_LAUNCH_PDL_FWD((bn_act_kernel<LO, RES>), grid, 256, 0, stream, CBF(x_hi), CBF(x_lo), CBF(r_hi), CBF(r_lo), BF(y_hi), BF(y_lo), scale, shift, rows, C, relu)
     if (x_lo != nullptr) {
         if (r_hi != nullptr) GDRN_BN_ACT(true, true); else GDRN_BN_ACT(true, false);
     } else {
@@ -1119,7 +1119,7 @@ extern "C" int gdrn_bn_act(const void* x_hi, const void* x_lo, const void* r_hi,
 extern "C" int gdrn_maxpool_fwd(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, void* arg_out, int B, int H,
                                 int W, int C, void* stream_) {
     STREAM;
-    GDRN_LAUNCH_PDL(maxpool_fwd_kernel, ew_grid((long)B * (H / 2) * (W / 2) * (C / 8), 256), 256, 0, stream, 
+    GDRN_LAUNCH_PDL_FWD(maxpool_fwd_kernel, ew_grid((long)B * (H / 2) * (W / 2) * (C / 8), 256), 256, 0, stream, 
         CBF(x_hi), CBF(x_lo), BF(y_hi), BF(y_lo), reinterpret_cast<uint8_t*>(arg_out), B, H, W, C);
     LAUNCH_DONE();
 }
@@ -1133,7 +1133,7 @@ extern "C" int gdrn_maxpool_bwd(const void* arg_in, const void* g_hi, const void
 extern "C" int gdrn_upsample2x_fwd(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int B, int H, int W, int C,
                                    void* stream_) {
     STREAM;
-    GDRN_LAUNCH_PDL(upsample2x_fwd_kernel, ew_grid((long)B * 4 * H * W * (C / 8), 256), 256, 0, stream, CBF(x_hi), CBF(x_lo), BF(y_hi),
+    GDRN_LAUNCH_PDL_FWD(upsample2x_fwd_kernel, ew_grid((long)B * 4 * H * W * (C / 8), 256), 256, 0, stream, CBF(x_hi), CBF(x_lo), BF(y_hi),
                                                                                            BF(y_lo), B, H, W, C);
     LAUNCH_DONE();
 }
@@ -1148,7 +1148,7 @@ extern "C" int gdrn_zero_insert(const void* x_hi, const void* x_lo, void* y_hi, 
                                 int mode, void* stream_) {
     STREAM;
     const long total = (long)B * H * W * (C / 8) * (mode == 0 ? 4 : 1);
-    GDRN_LAUNCH_PDL(zero_insert_kernel, ew_grid(total, 256), 256, 0, stream, CBF(x_hi), CBF(x_lo), BF(y_hi), BF(y_lo), B, H, W, C, mode);
+    GDRN_LAUNCH_PDL_FWD(zero_insert_kernel, ew_grid(total, 256), 256, 0, stream, CBF(x_hi), CBF(x_lo), BF(y_hi), BF(y_lo), B, H, W, C, mode);
     LAUNCH_DONE();
 }
 
@@ -1311,7 +1311,7 @@ extern "C" int gdrn_bn_fwd(const void* x_hi, const void* x_lo, const void* r_hi,
     if (train && stats == nullptr) return set_error(GDRN_ERR_ARG, "bn_fwd: batch statistics missing");
     const int grid = ew_grid_amortised(rows * (C / 8), 256, 4);
 #define GDRN_BN_FWD(LO, RES)                                                                                                  \
-    GDRN_LAUNCH_PDL((bn_fwd_kernel<LO, RES>), grid, 256, 0, stream, CBF(x_hi), CBF(x_lo), CBF(r_hi), CBF(r_lo), BF(y_hi), BF(y_lo), stats, gamma, beta, \
+    GDRN_LAUNCH_PDL_FWD((bn_fwd_kernel<LO, RES>), grid, 256, 0, stream, CBF(x_hi), CBF(x_lo), CBF(r_hi), CBF(r_lo), BF(y_hi), BF(y_lo), stats, gamma, beta, \
                                                      running_mean, running_var, mean_out, invstd_out, rows, C, eps, momentum, train, relu,  \
                                                      reinterpret_cast<uint8_t*>(relu_mask_out))
     if (x_lo != nullptr) {

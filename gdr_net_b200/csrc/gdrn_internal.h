@@ -19,7 +19,7 @@ int cuda_error(cudaError_t e, const char* file, int line);
 int num_sms();
 void count_launch();
 bool pdl_enabled();     // programmatic dependent launch for the GEMM kernels (GDRN_PDL >= 1 / gdrn_set_pdl)
-bool pdl_ew_enabled();  // ... and for the elementwise / pack kernels (GDRN_PDL >= 2)
+bool pdl_ew_enabled(bool forward_kernel);  // ... and for the elementwise / pack kernels (GDRN_PDL = 2: all, 3: forward-pass kernels only)
 void set_pdl(int on);
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency).
@@ -34,7 +34,8 @@ namespace gdrn {
 // <<<>>> with the programmatic-dependent-launch attribute (when enabled).  ONLY for kernels whose first statements are
 // pdl_launch_dependents(); pdl_wait();  (ptx.cuh) -- a kernel launched this way may start before its predecessor has finished.
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+inline cudaError_t launch_pdl(bool forward_kernel, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid;
@@ -43,7 +44,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     int na = 0;
-    if (pdl_ew_enabled()) {
+    if (pdl_ew_enabled(forward_kernel)) {
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         na = 1;
@@ -54,7 +55,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 }  // namespace gdrn
 #define GDRN_LAUNCH_PDL(kernel, grid, block, smem, stream, ...) \
-    (void)gdrn::launch_pdl(kernel, dim3(grid), dim3(block), smem, stream, __VA_ARGS__)
+    (void)gdrn::launch_pdl(false, kernel, dim3(grid), dim3(block), smem, stream, __VA_ARGS__)
+#define GDRN_LAUNCH_PDL_FWD(kernel, grid, block, smem, stream, ...) \
+    (void)gdrn::launch_pdl(true, kernel, dim3(grid), dim3(block), smem, stream, __VA_ARGS__)
 #endif
 
 #define GDRN_CUDA_OK(expr)                                                      \

@@ -374,7 +374,7 @@ extern "C" int gdrn_unpack_wgrad(const float* ws, float* grad, int O, int I, int
 extern "C" int gdrn_stem_im2col(const float* x, void* a_hi, void* a_lo, int B, int H, int W, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (H % 2 || W != 256) return set_error(GDRN_ERR_ARG, "stem_im2col: expects 256-wide crops (INPUT_RES=256), even height");
-    GDRN_LAUNCH_PDL(stem_im2col_kernel<256>, B * (H / 2), 256, 0, stream, x, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo, B, H);
+    GDRN_LAUNCH_PDL_FWD(stem_im2col_kernel<256>, B * (H / 2), 256, 0, stream, x, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo, B, H);
     GDRN_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;
