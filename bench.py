@@ -320,31 +320,38 @@ def run_ours(args):
 
         n_e2e = max(3, args.steps)
         cur = upload()
-        n_w = max(3, args.warmup // 2)  # >= 3 untimed steps (the first one also captures the forward / backward graphs)
+        # >= 8 untimed steps: the first one captures the forward / backward graphs, the next few let the caching allocator reach
+        # its steady state (the prefetched input tensors are held by record_stream for a step, so early steps still cudaMalloc)
+        n_w = max(8, args.warmup)
         for i in range(n_w):
             cur = e2e_step(cur, i)
         drain(n_w - 1)
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        read_back.clear()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_host0 = time.perf_counter()
-        e0.record()
-        for i in range(n_e2e):
-            cur = e2e_step(cur, i)
-        drain(n_e2e - 1)
-        e1.record()
-        torch.cuda.synchronize()
-        t_host = (time.perf_counter() - t_host0) * 1e3 / n_e2e
-        assert len(read_back) == n_e2e and all(v == v and abs(v) < 1e6 for v in read_back), read_back
-        ms_e2e = max(e0.elapsed_time(e1) / n_e2e, t_host)  # device events and the host clock must agree
+        # three timed regions of exactly K steps each, the MEDIAN is reported (all three are in `regions_ms`): a region is
+        # 0.2 s long, so one host-side hiccup (GC pause, a page fault in the pinned staging) would otherwise move it by 10-20 %
+        regions = []
+        for rep in range(3):
+            if world > 1:
+                dist.barrier()
+            read_back.clear()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_host0 = time.perf_counter()
+            e0.record()
+            for i in range(n_e2e):
+                cur = e2e_step(cur, i)
+            drain(n_e2e - 1)
+            e1.record()
+            torch.cuda.synchronize()
+            t_host = (time.perf_counter() - t_host0) * 1e3 / n_e2e
+            assert len(read_back) == n_e2e and all(v == v and abs(v) < 1e6 for v in read_back), read_back
+            regions.append(max(e0.elapsed_time(e1) / n_e2e, t_host))  # device events and the host clock must agree
+        ms_e2e = sorted(regions)[1]
         if world > 1:
             t = torch.tensor([ms_e2e], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e2e = float(t)
         out["e2e"] = {"value": round(world * B / (ms_e2e / 1e3), 1), "unit": "crops/s", "ms_per_step": round(ms_e2e, 3),
-                      "steps": n_e2e, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                      "steps": n_e2e, "regions_ms": [round(r, 3) for r in regions], "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                       "api": "gdr_net_b200.GDRN.GDRN.forward(...do_loss=True) + sum(loss_dict.values()).backward() (precision "
                              f"'{HEADLINE_MODE}'); every step's inputs are copied from pinned host memory (prefetched one step ahead "
                              "on a copy stream) and every step's loss is read back to the host (4-byte async D2H, consumed one step later)"}
