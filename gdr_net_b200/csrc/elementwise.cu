@@ -7,6 +7,8 @@
 //   nn.UpsamplingBilinear2d(scale_factor=2) (align_corners)  cdpn_rot_head_region.py:102
 //   nn.GroupNorm(32, 128) + ReLU                             conv_pnp_net.py:76-80
 // and their autograd backward.
+#include <stdlib.h>
+
 #include "gdrn_internal.h"
 #include "ptx.cuh"
 
@@ -143,16 +145,21 @@ template <bool LO, bool RES>
 __device__ __forceinline__ void bn_apply_loop(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo,
                                               const bf16* __restrict__ r_hi, const bf16* __restrict__ r_lo,
                                               bf16* __restrict__ y_hi, bf16* __restrict__ y_lo, const float* s_sc,
-                                              const float* s_sh, long total, int cg, int relu, uint8_t* __restrict__ mask_out) {
+                                              const float* s_sh, long total, int cg, int relu, uint8_t* __restrict__ mask_out,
+                                              bool rev = false) {
+    // rev: walk the tensor from its END to its start.  The producing GEMM wrote it front to back, so for tensors larger than
+    // the 126 MB L2 the freshest ~100 MB are the tail; this kernel's own output then leaves its HEAD in L2, which is where the
+    // consuming GEMM starts (total is a multiple of cg, so a thread's channel group stays fixed in both directions).
     const long stride = (long)gridDim.x * blockDim.x;
     const long first = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    const int c0 = (int)(first % cg) * 8;
+    const int c0 = (rev ? cg - 1 - (int)(first % cg) : (int)(first % cg)) * 8;
     for (long idx = first; idx < total; idx += 4 * stride) {
         uint4 xr[4], xl[4], rr[4], rl[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            const long it = idx + t * stride;
-            if (it < total) {
+            const long it0 = idx + t * stride;
+            const long it = rev ? total - 1 - it0 : it0;
+            if (it0 < total) {
                 xr[t] = ld16(x_hi, it);
                 if (LO) xl[t] = ld16(x_lo, it);
                 if (RES) {
@@ -163,8 +170,9 @@ __device__ __forceinline__ void bn_apply_loop(const bf16* __restrict__ x_hi, con
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            const long it = idx + t * stride;
-            if (it < total) {
+            const long it0 = idx + t * stride;
+            const long it = rev ? total - 1 - it0 : it0;
+            if (it0 < total) {
                 float v[8];
                 unpack8(xr[t], v);
                 if (LO) unpack8_lo(xl[t], v);
@@ -219,7 +227,7 @@ __global__ void __launch_bounds__(256, 4) bn_fwd_kernel(const bf16* __restrict__
                                                         const float* __restrict__ beta, float* running_mean, float* running_var,
                                                         float* __restrict__ mean_out, float* __restrict__ invstd_out, long rows,
                                                         int C, float eps, float momentum, int train, int relu,
-                                                        uint8_t* __restrict__ mask_out) {
+                                                        uint8_t* __restrict__ mask_out, int rev) {
     pdl_ew_entry();
     __shared__ float s_sc[512], s_sh[512];
     const float count = (float)rows;
@@ -252,7 +260,7 @@ __global__ void __launch_bounds__(256, 4) bn_fwd_kernel(const bf16* __restrict__
         }
     }
     __syncthreads();
-    bn_apply_loop<LO, RES>(x_hi, x_lo, r_hi, r_lo, y_hi, y_lo, s_sc, s_sh, rows * (C / 8), C / 8, relu, mask_out);
+    bn_apply_loop<LO, RES>(x_hi, x_lo, r_hi, r_lo, y_hi, y_lo, s_sc, s_sh, rows * (C / 8), C / 8, relu, mask_out, rev != 0);
 }
 
 
@@ -703,7 +711,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(
     const bf16* __restrict__ u_lo, const float* __restrict__ mean, const float* __restrict__ invstd,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ sums, bf16* __restrict__ du_hi,
     bf16* __restrict__ du_lo, bf16* __restrict__ gout_hi, bf16* __restrict__ gout_lo, float* __restrict__ dgamma,
-    float* __restrict__ dbeta, long rows, int C, int train, const uint8_t* __restrict__ mask_in) {
+    float* __restrict__ dbeta, long rows, int C, int train, const uint8_t* __restrict__ mask_in, int rev) {
     pdl_ew_entry();
     __shared__ __align__(16) float s_k1[512], s_k2[512], s_k3[512], s_sc[512], s_sh[512];
     const int cg = C / 8;
@@ -733,16 +741,18 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(
     __syncthreads();
     const bool has_bits = !MASKU && mask_in != nullptr;
     const bool has_gb = gb_hi != nullptr, has_y = !MASKU && !has_bits && y_hi != nullptr, has_gout = gout_hi != nullptr;
+    // rev: back to front (see bn_apply_loop): the reduction pass that ran just before left the TAIL of g / u in L2
     const long stride = (long)gridDim.x * blockDim.x;
     const long first = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    const int c0 = (int)(first % cg) * 8;
+    const int c0 = (rev ? cg - 1 - (int)(first % cg) : (int)(first % cg)) * 8;
     for (long idx = first; idx < total; idx += 2 * stride) {
         uint4 gah[2], gal[2], gbh[2], gbl[2], yh[2], uh[2], ul[2];
         uint32_t mb[2] = {0, 0};
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-            const long it = idx + t * stride;
-            if (it < total) {
+            const long it0 = idx + t * stride;
+            const long it = rev ? total - 1 - it0 : it0;
+            if (it0 < total) {
                 gah[t] = ld16(ga_hi, it);
                 uh[t] = ld16(u_hi, it);
                 if (has_bits) mb[t] = __ldg(mask_in + it);
@@ -757,8 +767,9 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(
         }
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-            const long it = idx + t * stride;
-            if (it < total) {
+            const long it0 = idx + t * stride;
+            const long it = rev ? total - 1 - it0 : it0;
+            if (it0 < total) {
                 float gv[8], u[8], o[8];
                 masked_grad<LO>(gah[t], gal[t], gbh[t], gbl[t], yh[t], has_gb, has_y, gv, has_bits, mb[t]);
                 unpack8(uh[t], u);
@@ -1082,6 +1093,17 @@ using namespace gdrn;
     count_launch();                    \
     return 0
 
+// GDRN_BN_REVERSE=0: BN forward / BN backward apply walk their tensors front to back like every other kernel (A/B; default: back
+// to front, so that consecutive kernels of the chain meet in the part of a > L2 tensor that is still cached)
+static int bn_reverse() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GDRN_BN_REVERSE");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
 extern "C" int gdrn_bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean,
                                 float* running_var, float* scale, float* shift, float* mean_out, float* invstd_out, int C,
                                 float count, float eps, float momentum, int train, void* stream_) {
@@ -1193,7 +1215,7 @@ extern "C" int gdrn_bn_bwd(const void* ga_hi, const void* ga_lo, const void* gb_
 #define GDRN_BN_APP(LO, MU)                                                                                                      \
     GDRN_LAUNCH_PDL((bn_bwd_apply_kernel<LO, MU>), agrid, 256, 0, stream, CBF(ga_hi), CBF(ga_lo), CBF(gb_hi), CBF(gb_lo), CBF(y_hi), CBF(u_hi),    \
                                                            CBF(u_lo), mean, invstd, gamma, beta, sums, BF(du_hi), BF(du_lo),       \
-                                                           BF(gout_hi), BF(gout_lo), dgamma, dbeta, rows, C, train, mask_in)
+                                                           BF(gout_hi), BF(gout_lo), dgamma, dbeta, rows, C, train, mask_in, bn_reverse())
     if (u_lo != nullptr) {
         if (mask_u) GDRN_BN_APP(true, true); else GDRN_BN_APP(true, false);
     } else {
@@ -1313,7 +1335,7 @@ extern "C" int gdrn_bn_fwd(const void* x_hi, const void* x_lo, const void* r_hi,
 #define GDRN_BN_FWD(LO, RES)                                                                                                  \
     GDRN_LAUNCH_PDL_FWD((bn_fwd_kernel<LO, RES>), grid, 256, 0, stream, CBF(x_hi), CBF(x_lo), CBF(r_hi), CBF(r_lo), BF(y_hi), BF(y_lo), stats, gamma, beta, \
                                                      running_mean, running_var, mean_out, invstd_out, rows, C, eps, momentum, train, relu,  \
-                                                     reinterpret_cast<uint8_t*>(relu_mask_out))
+                                                     reinterpret_cast<uint8_t*>(relu_mask_out), bn_reverse())
     if (x_lo != nullptr) {
         if (r_hi != nullptr) GDRN_BN_FWD(true, true); else GDRN_BN_FWD(true, false);
     } else {
