@@ -35,7 +35,12 @@ def make_roi_batch(image_u8: torch.Tensor, xyz: torch.Tensor, mask_visib: torch.
     scales = torch.as_tensor(scale).to(dev).double().reshape(B).contiguous()
     extents, fps = _f(extents, dev).reshape(B, 3), _f(fps_points, dev)
     if xyz.shape != (B, H, W, 3) or mask_visib.shape != (B, H, W) or fps.dim() != 3 or fps.shape[0] != B or fps.shape[2] != 3:
-        raise ValueError("make_roi_batch: inconsistent shapes")
+        raise ValueError(f"make_roi_batch: inconsistent shapes: image {tuple(image_u8.shape)}, xyz {tuple(xyz.shape)}, mask_visib "
+                         f"{tuple(mask_visib.shape)}, fps_points {tuple(fps.shape)}")
+    if mask_trunc is not None and mask_trunc.shape != (B, H, W):
+        raise ValueError(f"make_roi_batch: mask_trunc {tuple(mask_trunc.shape)} does not match the images [{B},{H},{W}]")
+    if fps.shape[1] < 1 or fps.shape[1] > 1024:
+        raise ValueError(f"make_roi_batch: {fps.shape[1]} region anchors (1..1024 supported)")
     s = torch.cuda.current_stream().cuda_stream
     out = dict(roi_img=torch.empty(B, 3, input_res, input_res, device=dev),
                roi_xyz=torch.empty(B, 3, out_res, out_res, device=dev),
