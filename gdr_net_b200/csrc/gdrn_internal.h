@@ -60,6 +60,12 @@ inline cudaError_t launch_pdl(bool forward_kernel, void (*kernel)(KArgs...), dim
     (void)gdrn::launch_pdl(true, kernel, dim3(grid), dim3(block), smem, stream, __VA_ARGS__)
 #endif
 
+// Plain launch, spelled as a macro so that tests/emu can rebuild a translation unit for the host (one thread per CTA) and
+// single-step its kernels in the CPU test suite; in the library this IS kernel<<<grid, block, smem, stream>>>(args...).
+#ifndef GDRN_LAUNCH_SMEM
+#define GDRN_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
 #define GDRN_CUDA_OK(expr)                                                      \
     do {                                                                        \
         cudaError_t _e = (expr);                                                \

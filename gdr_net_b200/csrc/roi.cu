@@ -246,8 +246,8 @@ extern "C" int gdrn_roi_crop_image(const void* image_u8, const double* centers, 
     if (B <= 0 || H <= 0 || W <= 0 || out_res <= 0 || pixel_std == 0.f) return set_error(GDRN_ERR_ARG, "roi_crop_image: bad shape");
     int chunks = (out_res * out_res + 255) / 256;
     if (chunks > 64) chunks = 64;
-    roi_crop_image_kernel<<<dim3(chunks, B), 256, 0, stream>>>(reinterpret_cast<const uint8_t*>(image_u8), centers, scales, roi_img, B,
-                                                              H, W, out_res, 1.f / pixel_std);
+    GDRN_LAUNCH_SMEM(roi_crop_image_kernel, dim3(chunks, B), dim3(256), 0, stream, reinterpret_cast<const uint8_t*>(image_u8), centers, scales,
+                     roi_img, B, H, W, out_res, 1.f / pixel_std);
     GDRN_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;
@@ -260,9 +260,9 @@ extern "C" int gdrn_roi_targets(const float* xyz, const float* mask_visib, const
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (B <= 0 || n_fps <= 0 || n_fps > 1024) return set_error(GDRN_ERR_ARG, "roi_targets: bad B=%d / n_fps=%d", B, n_fps);
     dim3 grid((out_res * out_res + 127) / 128, B);
-    roi_targets_kernel<<<grid, 128, n_fps * 3 * sizeof(float), stream>>>(xyz, mask_visib, mask_trunc, centers, scales, extents, fps_points,
-                                                                        n_fps, roi_xyz, roi_mask_trunc, roi_mask_visib, roi_mask_obj,
-                                                                        roi_region, roi_coord_2d, B, H, W, out_res);
+    GDRN_LAUNCH_SMEM(roi_targets_kernel, grid, dim3(128), n_fps * 3 * sizeof(float), stream, xyz, mask_visib, mask_trunc, centers, scales,
+                     extents, fps_points, n_fps, roi_xyz, roi_mask_trunc, roi_mask_visib, roi_mask_obj, roi_region, roi_coord_2d, B, H, W,
+                     out_res);
     GDRN_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;
