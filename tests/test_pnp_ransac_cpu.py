@@ -88,7 +88,7 @@ def emu(tmp_path_factory):
     if shutil.which("g++") is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
         pytest.skip("g++ / CUDA headers needed for the host emulation build")
     out = tmp_path_factory.mktemp("emu") / "libpnp_emu.so"
-    subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-I/usr/local/cuda/include",
+    subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-Wl,-Bsymbolic", "-I/usr/local/cuda/include",
                            os.path.join(ROOT, "tests", "emu", "pnp_ransac_emu.cpp"), "-o", str(out)])
     lib = ctypes.CDLL(str(out))
     lib.gdrn_pnp_ransac_workspace_bytes.restype = ctypes.c_long

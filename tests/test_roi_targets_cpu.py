@@ -20,8 +20,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def emu(tmp_path_factory):
     if shutil.which("g++") is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
         pytest.skip("g++ / CUDA headers needed for the host emulation build")
+    # -Bsymbolic: other CPU tests load the real libgdrn_b200.so with RTLD_GLOBAL; without it this library's calls to its own
+    # (host-compiled) kernels would bind to the real library's CUDA launch stubs of the same name
     out = tmp_path_factory.mktemp("emu") / "libroi_emu.so"
-    subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-I/usr/local/cuda/include",
+    subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-Wl,-Bsymbolic", "-I/usr/local/cuda/include",
                            os.path.join(ROOT, "tests", "emu", "roi_emu.cpp"), "-o", str(out)])
     return ctypes.CDLL(str(out))
 
