@@ -17,6 +17,11 @@ unpinned; 4.13.0 in this image).  Two oracles are kept here:
     RNG-driven 5-point subsets, EPnP [Lepetit, Moreno-Noguer, Fua, IJCV 2009] as the minimal and as the final solver, squared
     reprojection error threshold, adaptive iteration count), PINNED against cv2 by tests/test_pnp_ransac_cpu.py (same inlier
     sets, poses equal to ~1e-8) -- the CUDA kernel follows this restatement line by line.
+
+Pinning against the reference itself: oracle/make_golden_pnp.py imports the UNMODIFIED `get_out_mask`,
+`GDRN_Evaluator.get_img_model_points_with_coords2d` and `misc.pnp_v2` from /root/reference and stores their outputs for a
+seeded batch in tests/golden/pnp_ransac_b4.npz; `select_points` reproduces those point lists bit for bit and `pnp_ransac_cv2`
+the poses (tests/test_pnp_ransac_cpu.py::test_oracle_matches_reference_golden).
 """
 from __future__ import annotations
 

@@ -141,3 +141,33 @@ def test_kernel_logic_emulated_edge_cases(emu):
     uv = pc @ np.array(synth.LM_K).T
     assert np.abs(uv[:, :2] / uv[:, 2:] - ip).max() < 10.0  # noisy 5-point fit: a few pixels (cv2 is no better)
     pnp_common.check_against_reference({k: v[3:] for k, v in d.items()}, ref[3:], pose[3:], info[3:], inl[3:], min_identical_frac=0.0)
+
+
+# ------------------------------------------------------------------------------------------------ the reference's own outputs
+def _golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "pnp_ransac_b4.npz"))
+    d = {k: torch.from_numpy(g[k]) for k in ("mask", "xyz", "coord_2d", "extents", "cams", "im_wh", "R", "t")}
+    return g, d
+
+
+def test_oracle_matches_reference_golden(golden_dir):
+    """tests/golden/pnp_ransac_b4.npz holds what the UNMODIFIED reference functions produced (oracle/make_golden_pnp.py:
+    get_out_mask, get_img_model_points_with_coords2d, misc.pnp_v2): the oracle's selection must reproduce the point lists bit for
+    bit, and its cv2 call the poses (same cv2 build: exactly; another build: to solver tolerance)."""
+    g, d = _golden(golden_dir)
+    ref = pnp_common.reference_results(d)
+    same_cv2 = str(g["cv2_version"]) == cv2.__version__
+    for b in range(4):
+        ip, mp, pose, _ = ref[b]
+        assert np.array_equal(ip, g[f"img_points_{b}"]) and np.array_equal(mp, g[f"model_points_{b}"]), b
+        assert np.abs(pose - g[f"pose_{b}"]).max() < (1e-9 if same_cv2 else 5e-3), b
+
+
+def test_kernel_logic_emulated_matches_reference_golden(emu, golden_dir):
+    g, d = _golden(golden_dir)
+    pose, info, inl = _run_emu(emu, d)
+    for b in range(4):
+        assert int(info[b, 0]) == len(g[f"img_points_{b}"]) and int(info[b, 3]) == 1
+        ang = pnp_common.geodesic_deg(pose[b, :, :3].astype(np.float64), g[f"pose_{b}"][:, :3])
+        dt = np.abs(pose[b, :, 3] - g[f"pose_{b}"][:, 3]).max()
+        assert ang < 1.0 and dt < 5e-3 * g[f"pose_{b}"][2, 3], (b, ang, dt)
