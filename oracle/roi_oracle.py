@@ -1,6 +1,10 @@
 """TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference's per-instance crop / target generation
 (core/gdrn_modeling/data_loader.py:487-560) with the SAME libraries the reference uses (cv2.warpAffine, scipy cdist), for the
-parity test of gdr_net_b200.roi_targets.  Citations are relative to /root/reference/."""
+parity test of gdr_net_b200.roi_targets.  Citations are relative to /root/reference/.
+
+Pinned: oracle/make_golden_roi.py imports the UNMODIFIED helpers (`crop_resize_by_warp_affine`, `get_2d_coord_np`, `xyz_to_region`)
+from /root/reference and stores their outputs in tests/golden/roi_targets_b3.npz; the restatements below reproduce them bit for bit
+(tests/test_roi_targets_cpu.py::test_roi_oracle_matches_reference_golden)."""
 from __future__ import annotations
 
 import cv2

@@ -66,3 +66,57 @@ def test_roi_kernels_emulated_match_cv2_procedure(emu):
         assert dc.max() < 1.01 / (32.0 * (W - 1)) + 1e-6 and (dc > 1e-6).mean() < 5e-4, (b, dc.max())
         d = np.abs(out["roi_img"][b] - ref["roi_img"]) * 255.0
         assert d.max() <= 1.0 + 1e-3 and (d > 0.5).mean() < 0.02, (b, d.max(), (d > 0.5).mean())
+
+
+def test_roi_oracle_matches_reference_golden(golden_dir):
+    """tests/golden/roi_targets_b3.npz: outputs of the UNMODIFIED reference helpers (oracle/make_golden_roi.py imports
+    crop_resize_by_warp_affine / get_2d_coord_np / xyz_to_region from /root/reference).  The oracle's restatement of those helpers
+    must reproduce them bit for bit (same cv2 build; a different build may differ in warpAffine's last bits)."""
+    g = np.load(os.path.join(golden_dir, "roi_targets_b3.npz"))
+    if str(g["cv2_version"]) != cv2.__version__:
+        pytest.skip(f"golden made with cv2 {g['cv2_version']}, running {cv2.__version__}")
+    B, H, W = g["image"].shape[:3]
+    in_res, out_res = int(g["in_res"]), int(g["out_res"])
+    x = np.linspace(0, 1, W, dtype=np.float32)
+    y = np.linspace(0, 1, H, dtype=np.float32)
+    coord_2d = np.asarray(np.meshgrid(x, y)).transpose(1, 2, 0)
+    for b in range(B):
+        c, s = g["centers"][b], float(g["scales"][b])
+        xyz = g["xyz"][b]
+        mask_obj = ((xyz[:, :, 0] != 0) | (xyz[:, :, 1] != 0) | (xyz[:, :, 2] != 0)).astype(np.float32)
+        assert np.array_equal(RO.crop_resize_by_warp_affine(g["image"][b], c, s, in_res, cv2.INTER_LINEAR), g[f"img_{b}"])
+        assert np.array_equal(RO.crop_resize_by_warp_affine(coord_2d, c, s, out_res, cv2.INTER_LINEAR), g[f"coord_{b}"])
+        assert np.array_equal(RO.crop_resize_by_warp_affine(mask_obj[:, :, None], c, s, out_res, cv2.INTER_NEAREST), g[f"obj_{b}"])
+        roi_xyz = RO.crop_resize_by_warp_affine(xyz, c, s, out_res, cv2.INTER_NEAREST)
+        assert np.array_equal(roi_xyz, g[f"xyz_{b}"])
+        assert np.array_equal(RO.xyz_to_region(roi_xyz, g["fps"][b]), g[f"region_{b}"])
+
+
+def test_roi_kernels_emulated_match_reference_golden(emu, golden_dir):
+    """The host-emulated kernels against the reference helpers' stored outputs (nearest-sampled targets and labels exact up to a
+    stray pixel, coordinates within one 1/32-pixel step, image within one grey level)."""
+    g = np.load(os.path.join(golden_dir, "roi_targets_b3.npz"))
+    B, H, W = g["image"].shape[:3]
+    R, Ro, F_ = int(g["in_res"]), int(g["out_res"]), g["fps"].shape[1]
+    img, xyz = np.ascontiguousarray(g["image"]), np.ascontiguousarray(g["xyz"])
+    seg, trunc = np.ascontiguousarray(g["seg"]), np.ascontiguousarray(g["trunc"])
+    centers, scales = np.ascontiguousarray(g["centers"], np.float64), np.ascontiguousarray(g["scales"], np.float64)
+    ext, fps = np.ascontiguousarray(g["extents"]), np.ascontiguousarray(g["fps"])
+    out = dict(roi_img=np.zeros((B, 3, R, R), np.float32), roi_xyz=np.zeros((B, 3, Ro, Ro), np.float32),
+               roi_mask_trunc=np.zeros((B, Ro, Ro), np.float32), roi_mask_visib=np.zeros((B, Ro, Ro), np.float32),
+               roi_mask_obj=np.zeros((B, Ro, Ro), np.float32), roi_region=np.zeros((B, Ro, Ro), np.int64),
+               roi_coord_2d=np.zeros((B, 2, Ro, Ro), np.float32))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    assert emu.gdrn_roi_crop_image(P(img), P(centers), P(scales), P(out["roi_img"]), B, H, W, R, ctypes.c_float(255.0), None) == 0
+    assert emu.gdrn_roi_targets(P(xyz), P(seg), P(trunc), P(centers), P(scales), P(ext), P(fps), F_, P(out["roi_xyz"]),
+                                P(out["roi_mask_trunc"]), P(out["roi_mask_visib"]), P(out["roi_mask_obj"]), P(out["roi_region"]),
+                                P(out["roi_coord_2d"]), B, H, W, Ro, None) == 0
+    for b in range(B):
+        assert (out["roi_mask_obj"][b] != g[f"obj_{b}"]).mean() < 5e-4, b
+        assert (out["roi_region"][b] != g[f"region_{b}"]).mean() < 5e-4, b
+        want_xyz = g[f"xyz_{b}"].transpose(2, 0, 1) / g["extents"][b][:, None, None] + 0.5  # data_loader.py:541-545
+        assert (np.abs(out["roi_xyz"][b] - want_xyz) > 1e-6).mean() < 5e-4, b
+        dc = np.abs(out["roi_coord_2d"][b] - g[f"coord_{b}"].transpose(2, 0, 1))
+        assert dc.max() < 1.01 / (32.0 * (W - 1)) + 1e-6 and (dc > 1e-6).mean() < 5e-4, (b, dc.max())
+        d = np.abs(out["roi_img"][b] * 255.0 - g[f"img_{b}"].transpose(2, 0, 1).astype(np.float32))
+        assert d.max() <= 1.0 + 1e-3 and (d > 0.5).mean() < 0.02, (b, d.max(), (d > 0.5).mean())
