@@ -138,3 +138,46 @@ def test_batch_data_matches_reference_collate_keys():
     assert set(kw) <= set(inspect.signature(G.GDRN.forward).parameters)
     test = batch_data(None, data, device="cpu", phase="test")
     assert "roi_xyz" not in test and "roi_cam" in test
+
+
+def test_ranger_matches_reference_golden(golden_dir):
+    """solver.Ranger against the UNMODIFIED reference optimizer (lib/torch_utils/solver/ranger.py), whose parameters after 14 steps
+    on seeded gradients are stored in tests/golden/ranger_14steps.npz (oracle/make_golden_ranger.py)."""
+    import os
+
+    import numpy as np
+
+    from gdr_net_b200.solver import Ranger
+
+    g = np.load(os.path.join(golden_dir, "ranger_14steps.npz"))
+    for tag, wd in (("wd0", 0.0), ("wd1e-2", 1e-2)):
+        ps = [torch.from_numpy(g[f"p0_{i}"]).clone().requires_grad_(True) for i in range(3)]
+        opt = Ranger(ps, lr=1e-2, weight_decay=wd)
+        for t in range(14):
+            for i, p in enumerate(ps):
+                p.grad = torch.from_numpy(g[f"g{t}_{i}"]).clone()
+            opt.step()
+        for i, p in enumerate(ps):
+            assert torch.allclose(p.detach(), torch.from_numpy(g[f"{tag}_p{i}"]), rtol=1e-5, atol=1e-6), (tag, i)
+
+
+def test_batch_data_matches_reference_golden(golden_dir):
+    """train_harness.batch_data against the UNMODIFIED reference collate (engine_utils.py:6-60): identical key set, dtypes, shapes and
+    tensor bytes (tests/golden/batch_data_b3.json, made by oracle/make_golden_batch_data.py on the same seeded per-sample dicts)."""
+    import hashlib
+    import json
+    import os
+
+    from gdr_net_b200.train_harness import batch_data
+    from oracle.make_golden_batch_data import per_sample_dicts
+
+    gold = json.load(open(os.path.join(golden_dir, "batch_data_b3.json")))["train"]
+    out = batch_data(None, per_sample_dicts(), device="cpu")
+    assert set(out) == set(gold), (sorted(out), sorted(gold))
+    for k, want in gold.items():
+        v = out[k]
+        if "dtype" in want:
+            assert str(v.dtype) == want["dtype"] and list(v.shape) == want["shape"], (k, v.dtype, tuple(v.shape), want)
+            assert hashlib.sha1(v.contiguous().numpy().tobytes()).hexdigest() == want["sha1"], k
+        else:
+            assert type(v).__name__ == want["type"] and len(v) == want["len"], k
